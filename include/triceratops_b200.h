@@ -1,0 +1,134 @@
+/*
+ * triceratops_b200 -- C ABI of the B200 (sm_100a) marginal-likelihood engine.
+ *
+ * The reference (stevengiacalone/triceratops) is pure Python and has no FFI; its seams for this
+ * path are ordinary Python functions.  Each entry point below names the reference interface it
+ * stands in for (paths relative to the reference's triceratops/ package).  The Python host layer
+ * (triceratops_b200/_cabi.py) binds these with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions: every function returns 0 on success and a negative TRI_E* code on failure, with
+ * text available from tri_last_error().  One process drives one GPU (one context per process);
+ * calls are serialised by the caller.  The caller owns every buffer it passes; the library never
+ * keeps a host pointer after return.  All floating-point data is IEEE float64.
+ */
+#ifndef TRICERATOPS_B200_H
+#define TRICERATOPS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRI_OK 0
+#define TRI_ECUDA (-1)      /* CUDA runtime error                                   */
+#define TRI_EINVAL (-2)     /* bad argument (NULL, negative size, NaN light curve)  */
+#define TRI_ESTATE (-3)     /* tri_init / tri_set_lightcurve not called             */
+#define TRI_ENODEVICE (-4)  /* no CUDA device: there is no CPU fallback             */
+
+/* A per-draw column: stride 1 = array of N values, stride 0 = one value used for every draw
+ * (the reference broadcasts scalars with np.full(N, x), e.g. marginal_likelihoods.py:125-128). */
+typedef struct {
+    const double* ptr;
+    int64_t stride;
+} tri_col;
+
+/* Inputs of one TP-type scenario (lnZ_TTP/PTP/STP/DTP/BTP, marginal_likelihoods.py:39, :386,
+ * :869, :1379, :1840): the UNMASKED prior draws.  Geometry, masks, light curves, chi^2, the
+ * companion prior and the log-mean-exp all run on the GPU. */
+typedef struct {
+    int64_t N;
+    tri_col rp;       /* planet radius [R_earth]                       sample_rp            */
+    tri_col P_orb;    /* orbital period [d]                                                  */
+    tri_col inc;      /* inclination [deg]                             sample_inc           */
+    tri_col ecc;      /* eccentricity                                  sample_ecc           */
+    tri_col argp;     /* argument of periastron [deg]                  sample_w             */
+    tri_col mtot;     /* mass in Kepler's law [M_sun] (M_s, masses_comp, masses_comp[idxs])  */
+    tri_col rhost;    /* host-star radius [R_sun]                                            */
+    tri_col u1, u2;   /* quadratic limb-darkening coefficients of the host                  */
+    tri_col cfr;      /* companion_fluxratio                                                 */
+    tri_col lnprior;  /* lnprior_companion, ptr NULL = none (lnZ_TTP)                        */
+    const uint8_t* extra_mask; /* optional AND-term of the mask (qs_comp != 0, logg/Teff cuts) */
+    int32_t companion_is_host;
+} tri_tp_args;
+
+/* Inputs of one EB-type scenario (lnZ_TEB/PEB/SEB/DEB/BEB, marginal_likelihoods.py:175, :589,
+ * :1080, :1571, :2038).  One set of draws yields two results: q < 0.95 at period P ("EB") and
+ * q >= 0.95 at period 2P ("EBx2P"). */
+typedef struct {
+    int64_t N;
+    tri_col reb;      /* EB radius [R_sun]            stellar_relations                     */
+    tri_col ebfr;     /* EB_fluxratio                                                         */
+    tri_col q;        /* mass ratio                   sample_q                               */
+    tri_col P_orb, inc, ecc, argp;
+    tri_col mtot;     /* M_host + M_EB [M_sun]                                                */
+    tri_col rhost, u1, u2, cfr, lnprior;
+    const uint8_t* extra_mask;
+    int32_t companion_is_host;
+} tri_eb_args;
+
+/* Output of one scenario branch.  lnZ = m + ln(s) - ln(N) (-inf if no finite entry, +inf if any
+ * entry is +inf: _numerics.py:12-51); (m, s) are exposed so that ranks holding disjoint slices
+ * of the draws can be combined with one all-reduce. */
+typedef struct {
+    double lnZ;
+    double m, s;          /* max of the finite ln-weights and sum of exp(lnw - m)            */
+    int64_t n_finite;     /* finite ln-weights                                                */
+    int64_t n_posinf;     /* +inf ln-weights                                                  */
+    int64_t n_pass;       /* draws that survived the geometric mask of this branch           */
+    int64_t n_stamps;     /* time stamps evaluated inside transit windows (diagnostic)       */
+    double* lnL_out;      /* optional [N]: per-draw lnL (no prior), -inf where masked         */
+    uint8_t* mask_out;    /* optional [N]: the geometric mask                                 */
+} tri_result;
+
+/* Bind this process to one GPU, create the stream, build and upload the orbit table.  */
+int tri_init(int device);
+int tri_shutdown(void);
+const char* tri_last_error(void);
+
+/* Upload the (renormalised, NaN-free) folded light curve: what every lnZ_* receives as
+ * (time, flux, sigma, exptime, nsamples) -- triceratops.py:738-740, marginal_likelihoods.py:39-43. */
+int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, double sigma,
+                       double exptime, int32_t nsamples);
+
+/* L2 seam, host buffers: replaces the body of lnZ_* between the prior draws and _log_mean_exp. */
+int tri_eval_tp(const tri_tp_args* args, tri_result* out);
+int tri_eval_eb(const tri_eb_args* args, tri_result out[2]); /* [0]=EB, [1]=EBx2P */
+
+/* Same with every pointer (columns, extra_mask, lnL_out, mask_out) in DEVICE memory; work is
+ * queued on `stream` (a cudaStream_t, NULL = the library's stream) and the call returns after
+ * the small result record has been read back. */
+int tri_eval_tp_dev(const tri_tp_args* args, tri_result* out, void* stream);
+int tri_eval_eb_dev(const tri_eb_args* args, tri_result out[2], void* stream);
+
+/* L1 seam, host buffers: lnL_TP_p (likelihoods.py:443-487), lnL_EB_p (:490-539) and
+ * lnL_EB_twin_p (:542-587) on already-masked draws.  out[n] = +0.5 chi^2 (+inf where the
+ * secondary-depth cut fires, twin == 0 only), exactly what the reference functions return. */
+int tri_lnl_tp(int64_t n, const double* R_p, const double* P_orb, const double* inc,
+               const double* a, const double* R_s, const double* u1, const double* u2,
+               const double* ecc, const double* argp, const double* companion_fluxratio,
+               int32_t companion_is_host, double* out);
+int tri_lnl_eb(int64_t n, const double* R_EB, const double* EB_fluxratio, const double* P_orb,
+               const double* inc, const double* a, const double* R_s, const double* u1,
+               const double* u2, const double* ecc, const double* argp,
+               const double* companion_fluxratio, int32_t companion_is_host, int32_t twin,
+               double* out);
+
+/* _log_mean_exp (_numerics.py:12-51) of a host array on the GPU; fills lnZ, m, s, n_*. */
+int tri_log_mean_exp(const double* logw, int64_t n, tri_result* out);
+
+/* Device time [ms] of the kernels of the most recent eval/lnl call, from CUDA events on the
+ * stream they ran on: geometry, light-curve/chi^2, log-mean-exp, and their launch count. */
+int tri_last_timing(double* geometry_ms, double* lnl_ms, double* lse_ms, int32_t* launches);
+
+/* Measured FP64 FMA issue rate of this GPU [DFMA/s] (roofline denominator). */
+int tri_fp64_peak(double* dfma_per_s);
+
+/* SM count of the bound device. */
+int tri_sm_count(int32_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

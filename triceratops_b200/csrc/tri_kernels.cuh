@@ -1,0 +1,402 @@
+// sm_100a kernels of the marginal-likelihood path.
+//
+//   geometry_tp/eb_kernel  one thread per prior draw: Kepler's-law semi-major axis, transit
+//                          probability, collision and inclination masks (reference
+//                          marginal_likelihoods.py:107-123 for TP-type, :254-299 for EB-type),
+//                          and compaction of the surviving draws into a work list.
+//   lnl_kernel             persistent warps; one warp per surviving draw.  The lanes sweep the
+//                          time stamps inside the draw's transit window, each lane averaging its
+//                          own sub-exposures; a shuffle tree reduces chi^2.  Points outside the
+//                          window have model == 1 exactly and are added from a prefix sum of
+//                          (flux-1)^2.  EB-type draws first evaluate the 25-point secondary
+//                          eclipse (one point per lane) and its depth cut
+//                          (likelihoods.py:417-438, :535-538).
+//   lse_partial/final      log-mean-exp of lnL + lnprior as per-thread running (max, scaled sum)
+//                          pairs merged per block and then across blocks (_numerics.py:12-51).
+//
+// FP64 CUDA-core work throughout: the path is not a contraction, so no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tri_model.cuh"
+
+namespace tri {
+
+// pointer + stride (0 = one value broadcast to every sample, 1 = per-sample array)
+struct Col {
+    const double* p;
+    int64_t stride;
+    __device__ __forceinline__ double at(int64_t i) const { return __ldg(p + i * stride); }
+};
+
+// ---- geometry ------------------------------------------------------------------------------
+struct GeomTp {
+    int64_t N;
+    Col rp, P, inc, ecc, argp, mtot, rhost;
+    const uint8_t* extra_mask;  // optional AND term (qs_comp != 0, logg/Teff cuts)
+    double* a_out;              // [N] semi-major axis [cm] of surviving draws
+    double* lnl_out;            // [N] pre-filled with -inf for the rejected draws
+    uint8_t* mask_out;          // optional [N]
+    int64_t* items;             // work list (sample index << 1)
+    unsigned long long* n_items;
+};
+
+struct GeomEb {
+    int64_t N;
+    Col reb, q, P, inc, ecc, argp, mtot, rhost;
+    const uint8_t* extra_mask;
+    double* a_out;      // a (q < 0.95) or a_twin (q >= 0.95) of surviving draws
+    double* p_out;      // P or 2P
+    double* lnl_out;    // [N] EB branch, -inf default
+    double* lnl_twin_out;  // [N] twin branch, -inf default
+    uint8_t* mask_out;       // optional [N]: mask of the EB branch
+    uint8_t* mask_twin_out;  // optional [N]: mask of the twin branch
+    int64_t* items;     // (sample index << 1) | twin
+    unsigned long long* n_items;  // [0] all surviving draws, [1] of which twin
+};
+
+__device__ __forceinline__ double neg_inf() { return -INFINITY; }
+
+// a = ((G*M*Msun)/(4*pi**2)*(P*86400)**2)**(1/3)        marginal_likelihoods.py:75
+__device__ __forceinline__ double semi_major_axis(double mtot, double P) {
+    double ps = P * 86400.0;
+    return pow((kG * mtot * kMsun) / (4.0 * (kPi * kPi)) * (ps * ps), 1.0 / 3.0);
+}
+
+// inc_min = arccos(Ptra)*180/pi where Ptra <= 1 else 90          marginal_likelihoods.py:120-121
+__device__ __forceinline__ bool transits(double inc_deg, double Ptra) {
+    double inc_min = 90.0;
+    if (Ptra <= 1.0) inc_min = acos(Ptra) * 180.0 / kPi;
+    return inc_deg >= inc_min;
+}
+
+__device__ __forceinline__ void push_item(bool take, int64_t item, int64_t* items,
+                                          unsigned long long* n_items) {
+    unsigned ballot = __ballot_sync(0xffffffffu, take);
+    if (ballot == 0) return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(ballot) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(n_items, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (take) items[base + __popc(ballot & ((1u << lane) - 1u))] = item;
+}
+
+__global__ void geometry_tp_kernel(GeomTp g) {
+    int64_t n_round = (g.N + 31) / 32 * 32;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_round;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        bool take = false;
+        if (i < g.N) {
+            double rp = g.rp.at(i), P = g.P.at(i), inc = g.inc.at(i), ecc = g.ecc.at(i);
+            double argp = g.argp.at(i), rhost = g.rhost.at(i);
+            double a = semi_major_axis(g.mtot.at(i), P);
+            // e_corr, Ptra, coll                      marginal_likelihoods.py:111-115
+            double e_corr = (1.0 + ecc * sin(argp * kPi / 180.0)) / (1.0 - ecc * ecc);
+            double rsum = rp * kRearth + rhost * kRsun;
+            double Ptra = rsum / a * e_corr;
+            bool coll = rsum > a * (1.0 - ecc);
+            take = transits(inc, Ptra) && !coll;
+            if (g.extra_mask) take = take && (g.extra_mask[i] != 0);
+            g.lnl_out[i] = neg_inf();
+            if (take) g.a_out[i] = a;
+            if (g.mask_out) g.mask_out[i] = take ? 1 : 0;
+        }
+        push_item(take, i << 1, g.items, g.n_items);
+    }
+}
+
+__global__ void geometry_eb_kernel(GeomEb g) {
+    int64_t n_round = (g.N + 31) / 32 * 32;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_round;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        bool take = false;
+        int twin = 0;
+        if (i < g.N) {
+            double reb = g.reb.at(i), q = g.q.at(i), P = g.P.at(i), inc = g.inc.at(i);
+            double ecc = g.ecc.at(i), argp = g.argp.at(i), rhost = g.rhost.at(i);
+            double mtot = g.mtot.at(i);
+            // marginal_likelihoods.py:254-268
+            double e_corr = (1.0 + ecc * sin(argp * kPi / 180.0)) / (1.0 - ecc * ecc);
+            double rsum = reb * kRsun + rhost * kRsun;
+            twin = (q >= 0.95) ? 1 : 0;
+            double a, Ptra;
+            bool coll;
+            if (!twin) {
+                a = semi_major_axis(mtot, P);
+                Ptra = rsum / a * e_corr;
+                coll = rsum > a * (1.0 - ecc);
+            } else {
+                a = semi_major_axis(mtot, 2.0 * P);
+                Ptra = rsum / a * e_corr;
+                coll = (2.0 * rhost * kRsun) > a * (1.0 - ecc);
+            }
+            take = transits(inc, Ptra) && !coll;
+            if (g.extra_mask) take = take && (g.extra_mask[i] != 0);
+            g.lnl_out[i] = neg_inf();
+            g.lnl_twin_out[i] = neg_inf();
+            if (take) {
+                g.a_out[i] = a;
+                g.p_out[i] = twin ? 2.0 * P : P;
+            }
+            if (g.mask_out) g.mask_out[i] = (take && !twin) ? 1 : 0;
+            if (g.mask_twin_out) g.mask_twin_out[i] = (take && twin) ? 1 : 0;
+        }
+        push_item(take, (i << 1) | twin, g.items, g.n_items);
+        unsigned bt = __ballot_sync(0xffffffffu, take && twin);
+        if ((threadIdx.x & 31) == 0 && bt) atomicAdd(g.n_items + 1, (unsigned long long)__popc(bt));
+    }
+}
+
+// ---- light curve + chi^2 ---------------------------------------------------------------------
+struct LnlArgs {
+    LightCurve lc;
+    OrbitTable tab;
+    int eb;                  // 0 TP-type, 1 EB-type
+    int companion_is_host;
+    int raw;                 // 1: store +0.5 chi^2 (the lnL_*_p seam), +inf on the depth cut
+                             // 0: store -0.5 ln(2 pi) - ln(sigma) - 0.5 chi^2 (marginal_likelihoods.py:130)
+    int twin_uniform;        // twin flag when items == nullptr
+    Col body;                // R_p [R_earth] (TP) or R_EB [R_sun] (EB)
+    Col ebfr;                // EB flux ratio (EB only)
+    Col P, inc, a, rhost, u1, u2, ecc, argp, cfr;
+    const int64_t* items;    // nullptr: identity list 0..count-1
+    int64_t count;
+    unsigned long long* next;  // work-queue cursor
+    double* out;             // lnL of the (EB) branch, indexed by sample
+    double* out_twin;        // lnL of the twin branch (fused EB only)
+    unsigned long long* counters;  // optional [4]: evaluated model points / time stamps in window
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+constexpr int kLnlThreads = 128;
+
+__global__ void __launch_bounds__(kLnlThreads) lnl_kernel(LnlArgs A) {
+    extern __shared__ double smem[];
+    // Stage the folded light curve once per block when it fits (else read through L1/L2).
+    LightCurve lc = A.lc;
+    if (A.lc.time == nullptr) return;
+    {
+        size_t need = (size_t)(3 * lc.npts + 1) * sizeof(double);
+        unsigned dyn;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        if (need <= dyn) {
+            double* st = smem;
+            double* sf = smem + lc.npts;
+            double* sp = smem + 2 * lc.npts;
+            for (int j = threadIdx.x; j < lc.npts; j += blockDim.x) {
+                st[j] = A.lc.time[j];
+                sf[j] = A.lc.flux[j];
+            }
+            for (int j = threadIdx.x; j <= lc.npts; j += blockDim.x) sp[j] = A.lc.prefix[j];
+            __syncthreads();
+            lc.time = st;
+            lc.flux = sf;
+            lc.prefix = sp;
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    const double sigma = lc.sigma;
+    const double inv_ns = 1.0 / lc.nsamples;
+    unsigned long long n_pts_eval = 0, n_stamps = 0;
+
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(A.next, 1ull);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if ((int64_t)w >= A.count) break;
+        int64_t item = A.items ? A.items[w] : (((int64_t)w << 1) | A.twin_uniform);
+        const int64_t i = item >> 1;
+        const int twin = (int)(item & 1);
+
+        // ---- per-sample constants (every lane computes the same values)
+        const double P = A.P.at(i), e = A.ecc.at(i), argp = A.argp.at(i);
+        const double rhost = A.rhost.at(i);
+        const double a_rs = A.a.at(i) / (rhost * kRsun);          // likelihoods.py:343 / :409
+        const double inc = A.inc.at(i) * (kPi / 180.0);            // :344 / :410
+        const double w_rad = (90.0 - argp) * (kPi / 180.0);        // :345 / :411
+        const double cfr = A.cfr.at(i);
+        const double F_comp = cfr / (1.0 - cfr);
+        Limb L;
+        limb_setup(L, A.u1.at(i), A.u2.at(i));
+        Dilution D;
+        double k;
+        bool cut = false;
+        if (!A.eb) {
+            k = A.body.at(i) * kRearth / (rhost * kRsun);          // :340
+            D.two_stage = false;
+            D.d1 = 0.0;
+            D.d2 = A.companion_is_host ? 1.0 / F_comp : F_comp / 1.0;   // :352-357
+        } else {
+            const double reb = A.body.at(i);
+            const double fr = A.ebfr.at(i);
+            const double F_EB = fr / (1.0 - fr);
+            k = reb / rhost;                                       // :405-406
+            if ((k - 1.0) < 1e-6) k *= 0.999;
+            double ks = rhost / reb;                               // :417-418
+            if ((ks - 1.0) < 1e-6) ks *= 0.999;
+            const double ws = (90.0 - argp + 180.0) * (kPi / 180.0);  // :419
+            // secondary eclipse: 25 stamps on [-0.05, 0.05], no supersampling      :421-423
+            Orbit os;
+            orbit_setup(os, A.tab, ks, P, a_rs, inc, e, ws);
+            double sec = INFINITY;
+            if (lane < 25) {
+                double ts = (lane == 24) ? 0.05 : -0.05 + lane * ((0.05 - -0.05) / 24.0);
+                double z = z_at(os, A.tab, ts);
+                sec = (z > 1.0 + ks) ? 1.0 : occult_quad(z, ks, L);
+            }
+            sec = warp_min(sec);
+            double sd;
+            D.two_stage = true;
+            if (A.companion_is_host) {                              // :427-432
+                D.d1 = F_EB / F_comp;
+                sec = (sec + F_comp / F_EB) / (1.0 + F_comp / F_EB);
+                D.d2 = 1.0 / (F_comp + F_EB);
+            } else {                                                // :433-438
+                D.d1 = F_EB / 1.0;
+                sec = (sec + 1.0 / F_EB) / (1.0 + 1.0 / F_EB);
+                D.d2 = F_comp / (1.0 + F_EB);
+            }
+            sd = 1.0 - (sec + D.d2) / (1.0 + D.d2);
+            cut = !twin && !(sd < 1.5 * sigma);                     // :535-538
+        }
+        double* outp = (twin && A.out_twin) ? A.out_twin : A.out;
+        if (cut) {
+            if (lane == 0) outp[i] = A.raw ? INFINITY : -INFINITY;
+            continue;
+        }
+
+        Orbit o;
+        orbit_setup(o, A.tab, k, P, a_rs, inc, e, w_rad);
+
+        // ---- time stamps that can be in transit
+        int jlo = 0, jhi = lc.npts;
+        Window win;
+        if (transit_window(o, A.tab, a_rs, P, lc, win)) {
+            double half = 0.5 * lc.exptime;
+            jlo = lower_bound(lc.time, lc.npts, win.t_lo - half);
+            jhi = lower_bound(lc.time, lc.npts, win.t_hi + half);
+            if (jhi < jlo) jhi = jlo;
+        }
+
+        // ---- chi^2 over the window: lane <-> time stamp, serial over sub-exposures
+        double chi = 0.0;
+        for (int base = jlo; base < jhi; base += 32) {
+            int j = base + lane;
+            if (j < jhi) {
+                double t = lc.time[j];
+                double acc = 0.0;
+                for (int is = 1; is <= lc.nsamples; ++is) {
+                    double toff = lc.exptime * ((is - 0.5) * inv_ns - 0.5);
+                    double z = z_at(o, A.tab, t + toff);
+                    acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
+                }
+                double m = dilute(D, acc / lc.nsamples);
+                double r = lc.flux[j] - m;
+                chi = fma(r, r, chi);
+            }
+        }
+        chi = warp_sum(chi);
+        chi += (lc.prefix[jlo] - lc.prefix[0]) + (lc.prefix[lc.npts] - lc.prefix[jhi]);
+        if (lane == 0) {
+            double half_chi2 = 0.5 * (chi / (sigma * sigma));       // likelihoods.py:486
+            outp[i] = A.raw ? half_chi2
+                            : (-0.5 * log(2.0 * kPi) - log(sigma)) - half_chi2;
+            n_stamps += (unsigned long long)(jhi - jlo);
+        }
+    }
+    if (A.counters && lane == 0) {
+        n_pts_eval = n_stamps * (unsigned long long)lc.nsamples;
+        atomicAdd(A.counters + 0, n_pts_eval);
+        atomicAdd(A.counters + 1, n_stamps);
+    }
+}
+
+// ---- log-mean-exp ----------------------------------------------------------------------------
+struct LsePartial {
+    double m;      // running max of the finite entries (-inf if none)
+    double s;      // sum of exp(x - m)
+    unsigned long long n_finite, n_posinf;
+};
+
+__device__ __forceinline__ void lse_push(LsePartial& a, double x) {
+    if (isinf(x) && x > 0) { a.n_posinf++; return; }
+    if (!isfinite(x)) return;  // -inf and NaN: zero weight
+    a.n_finite++;
+    if (x > a.m) {
+        a.s = a.s * exp(a.m - x) + 1.0;   // exp(-inf) = 0 on the first finite entry
+        a.m = x;
+    } else {
+        a.s += exp(x - a.m);
+    }
+}
+
+__device__ __forceinline__ void lse_merge(LsePartial& a, const LsePartial& b) {
+    a.n_finite += b.n_finite;
+    a.n_posinf += b.n_posinf;
+    if (b.m == -INFINITY) return;
+    if (a.m == -INFINITY) { a.m = b.m; a.s = b.s; return; }
+    if (b.m > a.m) {
+        a.s = a.s * exp(a.m - b.m) + b.s;
+        a.m = b.m;
+    } else {
+        a.s += b.s * exp(b.m - a.m);
+    }
+}
+
+constexpr int kLseThreads = 256;
+
+// one partial per block over a contiguous slice: deterministic for a given grid
+__global__ void __launch_bounds__(kLseThreads)
+lse_partial_kernel(const double* lnl, Col lnprior, int64_t N, LsePartial* partials) {
+    __shared__ LsePartial sh[kLseThreads];
+    int64_t per_block = (N + gridDim.x - 1) / gridDim.x;
+    int64_t lo = blockIdx.x * per_block;
+    int64_t hi = lo + per_block < N ? lo + per_block : N;
+    LsePartial a{-INFINITY, 0.0, 0, 0};
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        double x = lnl[i];
+        if (lnprior.p) x += lnprior.at(i);
+        lse_push(a, x);
+    }
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = kLseThreads / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) lse_merge(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+
+__global__ void lse_final_kernel(const LsePartial* partials, int n, LsePartial* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    LsePartial a{-INFINITY, 0.0, 0, 0};
+    for (int b = 0; b < n; ++b) lse_merge(a, partials[b]);
+    *out = a;
+}
+
+// ---- FP64 issue-rate probe (roofline denominator measured on the box) -----------------------
+__global__ void dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double x = 1.0000001, y = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+        a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+    }
+    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace tri

@@ -1,0 +1,209 @@
+"""Host-side handle of the GPU engine: one process <-> one B200.
+
+Wraps the C ABI (include/triceratops_b200.h) for numpy callers.  Device selection follows the
+one-process-per-GPU launch convention (LOCAL_RANK), and results of ranks that hold disjoint
+slices of the prior draws are merged with `combine_lse`.
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import tri_col, tri_eb_args, tri_result, tri_tp_args
+
+_engine = None
+
+
+def get_engine(device=None):
+    """Process-wide engine bound to `device` (default: LOCAL_RANK or 0)."""
+    global _engine
+    if _engine is None:
+        _engine = Engine(device)
+    elif device is not None and device != _engine.device:
+        raise RuntimeError("engine already bound to device %d" % _engine.device)
+    return _engine
+
+
+class BranchResult:
+    """One scenario branch: lnZ pieces + optional per-draw arrays."""
+    __slots__ = ("lnZ", "m", "s", "n_finite", "n_posinf", "n_pass", "n_stamps", "lnL", "mask", "N")
+
+    def __init__(self, r, N, lnL, mask):
+        self.lnZ, self.m, self.s = r.lnZ, r.m, r.s
+        self.n_finite, self.n_posinf = r.n_finite, r.n_posinf
+        self.n_pass, self.n_stamps = r.n_pass, r.n_stamps
+        self.lnL, self.mask, self.N = lnL, mask, N
+
+
+def combine_lse(parts, N_total):
+    """lnZ from per-rank (m, s, n_finite, n_posinf) records over disjoint slices of N_total draws.
+
+    m = max_r m_r ; S = sum_r s_r exp(m_r - m) ; lnZ = m + ln S - ln N_total, with the
+    reference's edge semantics (_numerics.py:46-51): any +inf -> +inf, nothing finite -> -inf.
+    """
+    if any(p[3] > 0 for p in parts):
+        return math.inf
+    fin = [p for p in parts if p[2] > 0]
+    if not fin:
+        return -math.inf
+    m = max(p[0] for p in fin)
+    S = sum(p[1] * math.exp(p[0] - m) for p in fin)
+    return m + math.log(S) - math.log(N_total)
+
+
+class Engine:
+    def __init__(self, device=None):
+        self.lib = _cabi.load()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = int(device)
+        _cabi.check(self.lib.tri_init(self.device))
+        self._lc_key = None
+        self._keep = []
+
+    # ------------------------------------------------------------------ light curve
+    def set_lightcurve(self, time, flux, sigma, exptime, nsamples):
+        time = _cabi.f64(time)
+        flux = _cabi.f64(flux)
+        if time.shape != flux.shape or time.ndim != 1:
+            raise ValueError("time and flux must be 1-D arrays of equal length")
+        key = (time.tobytes(), flux.tobytes(), float(sigma), float(exptime), int(nsamples))
+        if key == self._lc_key:
+            return
+        _cabi.check(self.lib.tri_set_lightcurve(_cabi.dptr(time), _cabi.dptr(flux), time.size,
+                                                float(sigma), float(exptime), int(nsamples)))
+        self._lc_key = key
+
+    # ------------------------------------------------------------------ helpers
+    def _col(self, x, N):
+        """numpy array of N values (stride 1) or scalar (stride 0) -> tri_col (keeps a ref)."""
+        if x is None:
+            return tri_col(None, 0)
+        a = np.asarray(x, dtype=np.float64)
+        if a.ndim == 0 or (a.size == 1 and N != 1):
+            a = np.ascontiguousarray(a.reshape(1))
+            stride = 0
+        else:
+            a = np.ascontiguousarray(a)
+            if a.shape != (N,):
+                raise ValueError("column has shape %s, expected (%d,)" % (a.shape, N))
+            stride = 1
+        self._keep.append(a)
+        return tri_col(a.ctypes.data, stride)
+
+    def _mask(self, m, N):
+        if m is None:
+            return None
+        a = np.ascontiguousarray(np.asarray(m).astype(np.uint8))
+        if a.shape != (N,):
+            raise ValueError("extra_mask has shape %s, expected (%d,)" % (a.shape, N))
+        self._keep.append(a)
+        return a.ctypes.data
+
+    def _result(self, N, want_lnL, want_mask):
+        r = tri_result()
+        lnL = np.empty(N) if want_lnL else None
+        mask = np.empty(N, dtype=np.uint8) if want_mask else None
+        r.lnL_out = lnL.ctypes.data if want_lnL else None
+        r.mask_out = mask.ctypes.data if want_mask else None
+        return r, lnL, mask
+
+    # ------------------------------------------------------------------ L2 seam
+    def eval_tp(self, N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
+                extra_mask=None, companion_is_host=False, want_lnL=True, want_mask=False):
+        N = int(N)
+        self._keep = []
+        a = tri_tp_args()
+        a.N = N
+        for name, val in (("rp", rp), ("P_orb", P_orb), ("inc", inc), ("ecc", ecc),
+                          ("argp", argp), ("mtot", mtot), ("rhost", rhost), ("u1", u1),
+                          ("u2", u2), ("cfr", cfr), ("lnprior", lnprior)):
+            setattr(a, name, self._col(val, N))
+        a.extra_mask = self._mask(extra_mask, N)
+        a.companion_is_host = int(bool(companion_is_host))
+        r, lnL, mask = self._result(N, want_lnL, want_mask)
+        _cabi.check(self.lib.tri_eval_tp(ctypes.byref(a), ctypes.byref(r)))
+        self._keep = []
+        return BranchResult(r, N, lnL, mask.astype(bool) if mask is not None else None)
+
+    def eval_eb(self, N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr,
+                lnprior=None, extra_mask=None, companion_is_host=False, want_lnL=True,
+                want_mask=False):
+        N = int(N)
+        self._keep = []
+        a = tri_eb_args()
+        a.N = N
+        for name, val in (("reb", reb), ("ebfr", ebfr), ("q", q), ("P_orb", P_orb), ("inc", inc),
+                          ("ecc", ecc), ("argp", argp), ("mtot", mtot), ("rhost", rhost),
+                          ("u1", u1), ("u2", u2), ("cfr", cfr), ("lnprior", lnprior)):
+            setattr(a, name, self._col(val, N))
+        a.extra_mask = self._mask(extra_mask, N)
+        a.companion_is_host = int(bool(companion_is_host))
+        rr = (tri_result * 2)()
+        outs = []
+        for b in range(2):
+            r, lnL, mask = self._result(N, want_lnL, want_mask)
+            rr[b] = r
+            outs.append((lnL, mask))
+        _cabi.check(self.lib.tri_eval_eb(ctypes.byref(a), rr))
+        self._keep = []
+        return tuple(BranchResult(rr[b], N, outs[b][0],
+                                  outs[b][1].astype(bool) if outs[b][1] is not None else None)
+                     for b in range(2))
+
+    # ------------------------------------------------------------------ L1 seam
+    def lnl_tp(self, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr, companion_is_host):
+        n = int(np.size(R_p))
+        cols = [self._full(x, n) for x in (R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr)]
+        out = np.empty(n)
+        _cabi.check(self.lib.tri_lnl_tp(n, *[_cabi.dptr(c) for c in cols],
+                                        int(bool(companion_is_host)), _cabi.dptr(out)))
+        return out
+
+    def lnl_eb(self, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
+               companion_is_host, twin):
+        n = int(np.size(R_EB))
+        cols = [self._full(x, n) for x in (R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc,
+                                           argp, cfr)]
+        out = np.empty(n)
+        _cabi.check(self.lib.tri_lnl_eb(n, *[_cabi.dptr(c) for c in cols],
+                                        int(bool(companion_is_host)), int(bool(twin)),
+                                        _cabi.dptr(out)))
+        return out
+
+    @staticmethod
+    def _full(x, n):
+        a = np.asarray(x, dtype=np.float64)
+        if a.ndim == 0:
+            a = np.full(n, float(a))
+        a = np.ascontiguousarray(a)
+        if a.shape != (n,):
+            raise ValueError("array has shape %s, expected (%d,)" % (a.shape, n))
+        return a
+
+    # ------------------------------------------------------------------ misc
+    def log_mean_exp(self, logw):
+        logw = _cabi.f64(logw)
+        r = tri_result()
+        _cabi.check(self.lib.tri_log_mean_exp(_cabi.dptr(logw), logw.size, ctypes.byref(r)))
+        return r.lnZ, (r.m, r.s, r.n_finite, r.n_posinf)
+
+    def last_timing(self):
+        g, l, s = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        n = ctypes.c_int32()
+        _cabi.check(self.lib.tri_last_timing(ctypes.byref(g), ctypes.byref(l), ctypes.byref(s),
+                                             ctypes.byref(n)))
+        return {"geometry_ms": g.value, "lnl_ms": l.value, "lse_ms": s.value,
+                "launches": n.value}
+
+    def fp64_peak(self):
+        v = ctypes.c_double()
+        _cabi.check(self.lib.tri_fp64_peak(ctypes.byref(v)))
+        return v.value
+
+    def sm_count(self):
+        n = ctypes.c_int32()
+        _cabi.check(self.lib.tri_sm_count(ctypes.byref(n)))
+        return n.value
