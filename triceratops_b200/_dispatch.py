@@ -1,0 +1,139 @@
+"""Glue between the lnZ_* host functions and the GPU engine: sharding of the prior draws over
+ranks (one process per GPU), the single small collective that merges the per-rank
+(max, scaled-sum) records and best-draw candidates, and selection of the 100 best draws
+(reference marginal_likelihoods.py:152-154).
+
+Sharding follows SURVEY.md section 8e: every rank makes the same host draws (same seed), rank r
+evaluates the contiguous slice [r*N/G, (r+1)*N/G), and one all-gather of a 205-double record per
+scenario branch replaces any exchange of per-draw data.
+"""
+import math
+
+import numpy as np
+
+from . import engine as _engine_mod
+
+N_BEST = 100
+
+# test hook: tests replace this with an oracle-backed stand-in to exercise the host logic and the
+# multi-rank combine on CPU (gloo); the product path always gets the CUDA engine.
+_engine_factory = _engine_mod.get_engine
+
+
+def get_engine():
+    return _engine_factory()
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+    except Exception:  # pragma: no cover
+        return None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def shard_bounds(N, rank=None, world=None):
+    """Contiguous slice of the N draws owned by `rank`."""
+    d = _dist()
+    if rank is None:
+        rank = d.get_rank() if d else 0
+    if world is None:
+        world = d.get_world_size() if d else 1
+    return (rank * N) // world, ((rank + 1) * N) // world
+
+
+def _slice(x, lo, hi):
+    if x is None or np.ndim(x) == 0:
+        return x
+    return x[lo:hi]
+
+
+def _mask_slice(m, lo, hi):
+    """AND-term of the mask for this rank; None when it excludes nothing (saves the upload)."""
+    if m is None:
+        return None
+    m = m[lo:hi]
+    return None if m.all() else m
+
+
+def best_indices(lnL, n_best=N_BEST):
+    """First n_best entries of (-lnL).argsort() (marginal_likelihoods.py:152-153) without a
+    full sort when enough finite entries exist."""
+    n = lnL.size
+    if n <= 4 * n_best:
+        return (-lnL).argsort()[:n_best]
+    neg = -lnL
+    cand = np.argpartition(neg, n_best)[:n_best]
+    vals = neg[cand]
+    if not np.all(np.isfinite(vals)):
+        # fewer than n_best finite draws: the reference's order among the -inf entries is that
+        # of numpy's sort on the full array
+        return neg.argsort()[:n_best]
+    order = np.lexsort((cand, vals))
+    return cand[order][:n_best]
+
+
+class Branch:
+    """Globally combined result of one scenario branch."""
+    __slots__ = ("lnZ", "idx", "n_pass", "lnL_local", "lo", "hi")
+
+
+def _gather_branch(res, lo, hi, N):
+    """Merge per-rank results: lnZ from (m, s) records, best draws from per-rank candidates."""
+    br = Branch()
+    br.lo, br.hi = lo, hi
+    br.lnL_local = res.lnL
+    d = _dist()
+    local_best = best_indices(res.lnL) if res.lnL is not None and res.lnL.size else \
+        np.zeros(0, dtype=np.int64)
+    if d is None:
+        br.lnZ = res.lnZ
+        br.n_pass = res.n_pass
+        br.idx = local_best
+        return br
+    import torch
+    world = d.get_world_size()
+    rec = np.full(5 + 2 * N_BEST, np.nan)
+    rec[0:5] = (res.m, res.s, res.n_finite, res.n_posinf, res.n_pass)
+    k = local_best.size
+    rec[5:5 + k] = res.lnL[local_best]
+    rec[5 + N_BEST:5 + N_BEST + k] = (local_best + lo).astype(np.float64)
+    dev = "cuda" if d.get_backend() == "nccl" else "cpu"
+    mine = torch.from_numpy(rec).to(dev)
+    allrec = torch.empty(world * rec.size, dtype=torch.float64, device=dev)
+    d.all_gather_into_tensor(allrec, mine)
+    allrec = allrec.cpu().numpy().reshape(world, rec.size)
+    parts = [(r[0], r[1], int(r[2]), int(r[3])) for r in allrec]
+    br.lnZ = _engine_mod.combine_lse(parts, N)
+    br.n_pass = int(sum(r[4] for r in allrec))
+    vals = allrec[:, 5:5 + N_BEST].ravel()
+    gidx = allrec[:, 5 + N_BEST:].ravel()
+    ok = ~np.isnan(gidx)
+    vals, gidx = vals[ok], gidx[ok].astype(np.int64)
+    order = np.lexsort((gidx, -vals))
+    br.idx = gidx[order][:N_BEST]
+    return br
+
+
+def run_tp(N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
+           extra_mask=None, companion_is_host=False):
+    lo, hi = shard_bounds(N)
+    eng = get_engine()
+    res = eng.eval_tp(hi - lo, *[_slice(x, lo, hi) for x in (rp, P_orb, inc, ecc, argp, mtot,
+                                                              rhost, u1, u2, cfr)],
+                      lnprior=_slice(lnprior, lo, hi), extra_mask=_mask_slice(extra_mask, lo, hi),
+                      companion_is_host=companion_is_host, want_lnL=True)
+    return _gather_branch(res, lo, hi, N)
+
+
+def run_eb(N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
+           extra_mask=None, companion_is_host=False):
+    lo, hi = shard_bounds(N)
+    eng = get_engine()
+    r0, r1 = eng.eval_eb(hi - lo, *[_slice(x, lo, hi) for x in (reb, ebfr, q, P_orb, inc, ecc,
+                                                                 argp, mtot, rhost, u1, u2, cfr)],
+                         lnprior=_slice(lnprior, lo, hi), extra_mask=_mask_slice(extra_mask, lo, hi),
+                         companion_is_host=companion_is_host, want_lnL=True)
+    return _gather_branch(r0, lo, hi, N), _gather_branch(r1, lo, hi, N)

@@ -1,0 +1,498 @@
+"""The ten `lnZ_*` scenario functions of TRICERATOPS on the B200 engine.
+
+Drop-in for triceratops/marginal_likelihoods.py of the reference: same names, same positional
+and keyword arguments, same return dictionaries (keys M_s, R_s, u1, u2, P_orb, inc, b, R_p, ecc,
+argp, M_EB, R_EB, fluxratio_EB, fluxratio_comp: the 100 best draws, best first; plus lnZ).
+EB-type functions return (res, res_twin).
+
+Division of labour:
+  host (this file)  prior draws from numpy's global RNG in the reference's exact call order, so
+                    that a given np.random.seed produces the reference's arrays; stellar
+                    relations, flux ratios, companion priors, limb-darkening look-ups.
+  GPU (csrc/)       Kepler's-law geometry, transit-probability / collision / inclination masks,
+                    supersampled quadratic-limb-darkened light curve, secondary-eclipse cut,
+                    chi^2, + companion prior, log-mean-exp.  Draws are sent UNMASKED.
+
+`parallel` is accepted for signature compatibility.  The engine always evaluates with the
+semantics of the reference's vectorised branch (parallel=True: lnL_TP_p / lnL_EB_p /
+lnL_EB_twin_p), which is the reference's production path; its scalar loop (parallel=False) is
+not numerically identical to it (likelihoods.py:121-123 vs :406) and is not reproduced.
+"""
+import numpy as np
+from pandas import read_csv
+
+from . import _dispatch
+from ._constants import G, Msun, Rearth, Rsun, pi
+from ._ldc import grid_for
+from .funcs import (file_to_contrast_curve, flux_relation, stellar_relations, trilegal_results)
+from .priors import (lnprior_background, lnprior_bound_EB, lnprior_bound_TP, sample_ecc,
+                     sample_inc, sample_q, sample_q_companion, sample_rp, sample_w)
+
+np.seterr(divide='ignore')
+
+N_SAMPLES = 100
+
+__all__ = ["lnZ_TTP", "lnZ_TEB", "lnZ_PTP", "lnZ_PEB", "lnZ_STP", "lnZ_SEB", "lnZ_DTP",
+           "lnZ_DEB", "lnZ_BTP", "lnZ_BEB"]
+
+
+# ------------------------------------------------------------------------------ shared pieces
+def _periods(P_orb, N):
+    """Fixed period or uniform draws over a range (marginal_likelihoods.py:67-72).  Returns
+    (array or scalar for the engine, callable idx -> P_orb[idx], mean period)."""
+    if type(P_orb) not in [float, int]:
+        P = np.random.uniform(low=P_orb[0], high=P_orb[-1], size=N)
+        return P, np.mean(P)
+    # np.mean(np.full(N, P)) is what the reference hands to sample_ecc; it can differ from P in
+    # the last bits, which only matters at the P <= 10 switch, so take the same route
+    return float(P_orb), np.mean(np.full(N, P_orb))
+
+
+def _take(x, idx):
+    """x[idx] for per-draw arrays, np.full for broadcast scalars."""
+    if np.ndim(x) == 0:
+        return np.full(len(idx), x)
+    return x[idx]
+
+
+def _logg(M, R):
+    return np.log10(G * (M * Msun) / (R * Rsun) ** 2)
+
+
+def _semi_major_axis(mtot, P):
+    return ((G * mtot * Msun) / (4 * pi ** 2) * (P * 86400) ** 2) ** (1 / 3)
+
+
+def _impact(a, ecc, argp, inc, R_host):
+    """b of marginal_likelihoods.py:107-108 for the selected draws."""
+    r = a * (1 - ecc ** 2) / (1 + ecc * np.sin(argp * np.pi / 180))
+    return r * np.cos(inc * pi / 180) / (R_host * Rsun)
+
+
+def _draw_planet(N, host_masses, flatpriors, P_mean):
+    rps = sample_rp(np.random.rand(N), host_masses, flatpriors)
+    incs = sample_inc(np.random.rand(N))
+    eccs = sample_ecc(np.random.rand(N), planet=True, P_orb=P_mean)
+    argps = sample_w(np.random.rand(N))
+    return rps, incs, eccs, argps
+
+
+def _companion_q(N, M_s, molusc_file):
+    """Mass ratios of bound companions: prior draws or a MOLUSC table (e.g. :455-464)."""
+    if molusc_file is None:
+        return sample_q_companion(np.random.rand(N), M_s)
+    df = read_csv(molusc_file)
+    sma = df["semi-major axis(AU)"].values
+    e = df["eccentricity"].values
+    q = df[sma * (1 - e) > 10]["mass ratio"].values
+    q[q < 0.1 / M_s] = 0.1 / M_s
+    return np.pad(q, (0, N - len(q)))
+
+
+def _fluxratio(masses, M_s, filt="TESS"):
+    f = flux_relation(masses, filt)
+    return f / (f + flux_relation(np.array([M_s]), filt))
+
+
+def _clip_prior(lnprior, delta_mags):
+    lnprior[lnprior > 0.0] = 0.0
+    lnprior[delta_mags > 0.0] = -np.inf
+    return lnprior
+
+
+def _bound_prior(prior_fn, M_s, plx, N, molusc_file, contrast_curve_file, fr_tess, fr_cc_fn):
+    """Companion prior of the P*/S* scenarios (e.g. :478-509).  fr_tess: flux-ratio term in the
+    TESS band; fr_cc_fn(): the same term in the contrast-curve band (evaluated lazily)."""
+    if molusc_file is not None:
+        return np.zeros(N)
+    if contrast_curve_file is None:
+        delta_mags = 2.5 * np.log10(fr_tess)
+        lnprior = prior_fn(M_s, plx, np.abs(delta_mags), np.array([2.2]), np.array([1.0]))
+    else:
+        delta_mags = 2.5 * np.log10(fr_cc_fn())
+        separations, contrasts = file_to_contrast_curve(contrast_curve_file)
+        lnprior = prior_fn(M_s, plx, np.abs(delta_mags), separations, contrasts)
+    return _clip_prior(lnprior, delta_mags)
+
+
+class _Background:
+    """TRILEGAL population behind the target (e.g. :1452-1461)."""
+
+    def __init__(self, trilegal_fname, Tmag, Jmag, Hmag, Kmag):
+        (self.Tmags, self.masses, self.loggs, self.Teffs, self.Zs, Jm, Hm, Km) = \
+            trilegal_results(trilegal_fname, Tmag)
+        self.delta = {"T": Tmag - self.Tmags, "J": Jmag - Jm, "H": Hmag - Hm, "K": Kmag - Km}
+        self.fluxratios = 10 ** (self.delta["T"] / 2.5) / (1 + 10 ** (self.delta["T"] / 2.5))
+        self.N_comp = self.Tmags.shape[0]
+
+    def band(self, filt):
+        return self.delta[filt] if filt in ("J", "H", "K") else self.delta["T"]
+
+    def fluxratios_in(self, filt):
+        d = self.band(filt)
+        return 10 ** (d / 2.5) / (1 + 10 ** (d / 2.5))
+
+    def radii(self):
+        return np.sqrt(G * self.masses * Msun / 10 ** self.loggs) / Rsun
+
+
+def _background_prior(bg, N, contrast_curve_file, dmag_tess, dmag_cc):
+    """Chance-alignment prior of the D*/B* scenarios (e.g. :1466-1492)."""
+    if contrast_curve_file is None:
+        lnprior = np.full(N, np.log((bg.N_comp / 0.1) * (1 / 3600) ** 2 * 2.2 ** 2))
+        return _clip_prior(lnprior, dmag_tess)
+    separations, contrasts = file_to_contrast_curve(contrast_curve_file)
+    lnprior = lnprior_background(bg.N_comp, np.abs(dmag_cc), separations, contrasts)
+    return _clip_prior(lnprior, dmag_cc)
+
+
+def _tp_result(br, M_host, R_host, u1, u2, P, mtot, incs, rps, eccs, argps, cfr):
+    idx = br.idx
+    P_i = _take(P, idx)
+    a_i = _semi_major_axis(_take(mtot, idx), P_i)
+    zeros = np.zeros(N_SAMPLES)
+    return {
+        'M_s': _take(M_host, idx), 'R_s': _take(R_host, idx),
+        'u1': _take(u1, idx), 'u2': _take(u2, idx),
+        'P_orb': P_i, 'inc': incs[idx],
+        'b': _impact(a_i, eccs[idx], argps[idx], incs[idx], _take(R_host, idx)),
+        'R_p': rps[idx], 'ecc': eccs[idx], 'argp': argps[idx],
+        'M_EB': zeros, 'R_EB': zeros.copy(), 'fluxratio_EB': zeros.copy(),
+        'fluxratio_comp': _take(cfr, idx) if np.ndim(cfr) else zeros.copy(),
+        'lnZ': br.lnZ,
+    }
+
+
+def _eb_result(br, twin, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, masses, radii,
+               fluxratios, cfr):
+    idx = br.idx
+    P_i = _take(P, idx)
+    P_eff = 2 * P_i if twin else P_i
+    a_i = _semi_major_axis(_take(mtot, idx), P_eff)
+    zeros = np.zeros(N_SAMPLES)
+    return {
+        'M_s': _take(M_host, idx), 'R_s': _take(R_host, idx),
+        'u1': _take(u1, idx), 'u2': _take(u2, idx),
+        'P_orb': P_eff, 'inc': incs[idx],
+        'b': _impact(a_i, eccs[idx], argps[idx], incs[idx], _take(R_host, idx)),
+        'R_p': zeros, 'ecc': eccs[idx], 'argp': argps[idx],
+        'M_EB': masses[idx], 'R_EB': radii[idx], 'fluxratio_EB': fluxratios[idx],
+        'fluxratio_comp': _take(cfr, idx) if np.ndim(cfr) else zeros.copy(),
+        'lnZ': br.lnZ,
+    }
+
+
+def _run_tp(N, M_host, R_host, u1, u2, P, mtot, rps, incs, eccs, argps, cfr, lnprior,
+            extra_mask, companion_is_host):
+    br = _dispatch.run_tp(N, rps, P, incs, eccs, argps, mtot, R_host, u1, u2, cfr,
+                          lnprior=lnprior, extra_mask=extra_mask,
+                          companion_is_host=companion_is_host)
+    return _tp_result(br, M_host, R_host, u1, u2, P, mtot, incs, rps, eccs, argps, cfr)
+
+
+def _run_eb(N, M_host, R_host, u1, u2, P, mtot, incs, qs, eccs, argps, masses, radii,
+            fluxratios, cfr, lnprior, extra_mask, companion_is_host):
+    br, br_twin = _dispatch.run_eb(N, radii, fluxratios, qs, P, incs, eccs, argps, mtot, R_host,
+                                   u1, u2, cfr, lnprior=lnprior, extra_mask=extra_mask,
+                                   companion_is_host=companion_is_host)
+    common = (M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, masses, radii, fluxratios, cfr)
+    return _eb_result(br, False, *common), _eb_result(br_twin, True, *common)
+
+
+# ------------------------------------------------------------------- target-star scenarios
+def lnZ_TTP(time: np.ndarray, flux: np.ndarray, sigma: float,
+            P_orb: float, M_s: float, R_s: float, Teff: float,
+            Z: float, N: int = 1000000, parallel: bool = False,
+            mission: str = "TESS", flatpriors: bool = False,
+            exptime: float = 0.00139, nsamples: int = 20):
+    """Transiting planet on the target star (marginal_likelihoods.py:39-172).  Also used for a
+    nearby star (NTP) by calc_probs."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
+    return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, 0.0, None, None, False)
+
+
+def _draw_binary(N, M_s, P_mean):
+    incs = sample_inc(np.random.rand(N))
+    qs = sample_q(np.random.rand(N), M_s)
+    eccs = sample_ecc(np.random.rand(N), planet=False, P_orb=P_mean)
+    argps = sample_w(np.random.rand(N))
+    return incs, qs, eccs, argps
+
+
+def lnZ_TEB(time: np.ndarray, flux: np.ndarray, sigma: float,
+            P_orb: float, M_s: float, R_s: float, Teff: float,
+            Z: float, N: int = 1000000, parallel: bool = False,
+            mission: str = "TESS", flatpriors: bool = False,
+            exptime: float = 0.00139, nsamples: int = 20):
+    """Eclipsing binary on the target star, periods P and 2P (marginal_likelihoods.py:175-383).
+    Also used for a nearby star (NEB, NEBx2P) by calc_probs."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
+    masses = qs * M_s
+    radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
+    fluxratios = _fluxratio(masses, M_s)
+    return _run_eb(N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses, radii,
+                   fluxratios, 0.0, None, None, False)
+
+
+# ---------------------------------------------------------------- bound-companion scenarios
+def lnZ_PTP(time: np.ndarray, flux: np.ndarray, sigma: float,
+            P_orb: float, M_s: float, R_s: float, Teff: float,
+            Z: float, plx: float, contrast_curve_file: str = None,
+            filt: str = "TESS",
+            N: int = 1000000, parallel: bool = False,
+            mission: str = "TESS", flatpriors: bool = False,
+            exptime: float = 0.00139, nsamples: int = 20,
+            molusc_file: str = None):
+    """Planet on the target, diluted by an unresolved bound companion (:386-586)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    qs_comp = _companion_q(N, M_s, molusc_file)
+    masses_comp = qs_comp * M_s
+    fluxratios_comp = _fluxratio(masses_comp, M_s)
+
+    def cc_term():
+        fr = _fluxratio(masses_comp, M_s, filt)
+        return fr / (1 - fr)
+
+    lnprior = _bound_prior(lnprior_bound_TP, M_s, plx, N, molusc_file, contrast_curve_file,
+                           fluxratios_comp / (1 - fluxratios_comp), cc_term)
+    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
+    return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, fluxratios_comp,
+                   lnprior, qs_comp != 0.0, False)
+
+
+def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
+            P_orb: float, M_s: float, R_s: float, Teff: float,
+            Z: float, plx: float, contrast_curve_file: str = None,
+            filt: str = "TESS",
+            N: int = 1000000, parallel: bool = False,
+            mission: str = "TESS", flatpriors: bool = False,
+            exptime: float = 0.00139, nsamples: int = 20,
+            molusc_file: str = None):
+    """EB on the target, diluted by an unresolved bound companion (:589-866)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
+    qs_comp = _companion_q(N, M_s, molusc_file)
+    masses = qs * M_s
+    radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
+    fluxratios = _fluxratio(masses, M_s)
+    masses_comp = qs_comp * M_s
+    fluxratios_comp = _fluxratio(masses_comp, M_s)
+
+    def cc_term():
+        fr = _fluxratio(masses_comp, M_s, filt)
+        return fr / (1 - fr)
+
+    lnprior = _bound_prior(lnprior_bound_EB, M_s, plx, N, molusc_file, contrast_curve_file,
+                           fluxratios_comp / (1 - fluxratios_comp), cc_term)
+    return _run_eb(N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses, radii,
+                   fluxratios, fluxratios_comp, lnprior, qs_comp != 0.0, False)
+
+
+def _companion_stars(N, M_s, R_s, Teff, Z, mission, qs_comp, Teff_cap):
+    """Properties of the drawn bound companions when THEY host the event (:927-972)."""
+    masses_comp = qs_comp * M_s
+    radii_comp, Teffs_comp = stellar_relations(masses_comp, np.full(N, R_s), np.full(N, Teff))
+    loggs_comp = np.log10(G * (masses_comp * Msun) / (radii_comp * Rsun) ** 2)
+    fluxratios_comp = _fluxratio(masses_comp, M_s)
+    u1s, u2s = grid_for(mission).at_Z_rounded(Z, Teffs_comp, loggs_comp, Teff_cap)
+    return masses_comp, radii_comp, Teffs_comp, fluxratios_comp, u1s, u2s
+
+
+def lnZ_STP(time: np.ndarray, flux: np.ndarray, sigma: float,
+            P_orb: float, M_s: float, R_s: float, Teff: float, Z: float,
+            plx: float, contrast_curve_file: str = None,
+            filt: str = "TESS",
+            N: int = 1000000, parallel: bool = False,
+            mission: str = "TESS", flatpriors: bool = False,
+            exptime: float = 0.00139, nsamples: int = 20,
+            molusc_file: str = None):
+    """Planet on an unresolved bound companion of the target (:869-1077)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    qs_comp = _companion_q(N, M_s, molusc_file)
+    (masses_comp, radii_comp, _, fluxratios_comp, u1s, u2s) = _companion_stars(
+        N, M_s, R_s, Teff, Z, mission, qs_comp, 10000)
+
+    def cc_term():
+        fr = _fluxratio(masses_comp, M_s, filt)
+        return fr / (1 - fr)
+
+    lnprior = _bound_prior(lnprior_bound_TP, M_s, plx, N, molusc_file, contrast_curve_file,
+                           fluxratios_comp / (1 - fluxratios_comp), cc_term)
+    rps, incs, eccs, argps = _draw_planet(N, masses_comp, flatpriors, P_mean)
+    return _run_tp(N, masses_comp, radii_comp, u1s, u2s, P, masses_comp, rps, incs, eccs, argps,
+                   fluxratios_comp, lnprior, qs_comp != 0.0, True)
+
+
+def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
+            P_orb: float, M_s: float, R_s: float, Teff: float,
+            Z: float, plx: float, contrast_curve_file: str = None,
+            filt: str = "TESS",
+            N: int = 1000000, parallel: bool = False,
+            mission: str = "TESS", flatpriors: bool = False,
+            exptime: float = 0.00139, nsamples: int = 20,
+            molusc_file: str = None):
+    """EB on an unresolved bound companion of the target (:1080-1376)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
+    qs_comp = _companion_q(N, M_s, molusc_file)
+    # Teff clamp of 13000 K (grid stops at 10000 K) as in the reference, :1181
+    (masses_comp, radii_comp, Teffs_comp, fluxratios_comp, u1s, u2s) = _companion_stars(
+        N, M_s, R_s, Teff, Z, mission, qs_comp, 13000)
+    masses = qs * masses_comp
+    radii, _ = stellar_relations(masses, radii_comp, Teffs_comp)
+    fluxratios = _fluxratio(masses, M_s)
+
+    def cc_term():
+        fr = _fluxratio(masses, M_s, filt)
+        fr_comp = _fluxratio(masses_comp, M_s, filt)
+        return (fr_comp / (1 - fr_comp)) + (fr / (1 - fr))
+
+    lnprior = _bound_prior(lnprior_bound_EB, M_s, plx, N, molusc_file, contrast_curve_file,
+                           (fluxratios_comp / (1 - fluxratios_comp))
+                           + (fluxratios / (1 - fluxratios)), cc_term)
+    return _run_eb(N, masses_comp, radii_comp, u1s, u2s, P, masses_comp + masses, incs, qs, eccs,
+                   argps, masses, radii, fluxratios, fluxratios_comp, lnprior, qs_comp != 0.0,
+                   True)
+
+
+# --------------------------------------------------------------------- background scenarios
+def lnZ_DTP(time: np.ndarray, flux: np.ndarray, sigma: float,
+            P_orb: float, M_s: float, R_s: float, Teff: float,
+            Z: float, Tmag: float, Jmag: float, Hmag: float,
+            Kmag: float, trilegal_fname: str,
+            contrast_curve_file: str = None, filt: str = "TESS",
+            N: int = 1000000, parallel: bool = False,
+            mission: str = "TESS", flatpriors: bool = False,
+            exptime: float = 0.00139, nsamples: int = 20):
+    """Planet on the target, diluted by a chance-aligned background star (:1379-1568)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
+    idxs = np.random.randint(0, bg.N_comp - 1, N)     # upper bound N_comp-1, as :1463
+    cfr = bg.fluxratios[idxs]
+    lnprior = _background_prior(bg, N, contrast_curve_file,
+                                2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
+    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
+    return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, cfr, lnprior, None,
+                   False)
+
+
+def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
+            P_orb: float, M_s: float, R_s: float, Teff: float,
+            Z: float, Tmag: float, Jmag: float, Hmag: float,
+            Kmag: float, trilegal_fname: str,
+            contrast_curve_file: str = None, filt: str = "TESS",
+            N: int = 1000000, parallel: bool = False,
+            mission: str = "TESS", flatpriors: bool = False,
+            exptime: float = 0.00139, nsamples: int = 20):
+    """EB on the target, diluted by a chance-aligned background star (:1571-1837)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
+    masses = qs * M_s
+    radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
+    fluxratios = _fluxratio(masses, M_s)
+    bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
+    idxs = np.random.randint(0, bg.N_comp - 1, N)     # :1672
+    cfr = bg.fluxratios[idxs]
+    lnprior = _background_prior(bg, N, contrast_curve_file,
+                                2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
+    return _run_eb(N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses, radii,
+                   fluxratios, cfr, lnprior, None, False)
+
+
+def lnZ_BTP(time: np.ndarray, flux: np.ndarray, sigma: float,
+            P_orb: float, M_s: float, R_s: float, Teff: float,
+            Tmag: float, Jmag: float, Hmag: float, Kmag: float,
+            trilegal_fname: str,
+            contrast_curve_file: str = None, filt: str = "TESS",
+            N: int = 1000000, parallel: bool = False,
+            mission: str = "TESS", flatpriors: bool = False,
+            exptime: float = 0.00139, nsamples: int = 20):
+    """Planet on a chance-aligned background star (:1840-2035)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
+    radii_comp = bg.radii()
+    u1s_comp, u2s_comp = grid_for(mission).nearest_each(bg.Teffs, bg.loggs, bg.Zs)
+    idxs = np.random.randint(0, bg.N_comp, N)         # :1926
+    cfr = bg.fluxratios[idxs]
+    lnprior = _background_prior(bg, N, contrast_curve_file,
+                                2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
+    host_masses = bg.masses[idxs]
+    rps, incs, eccs, argps = _draw_planet(N, host_masses, flatpriors, P_mean)
+    extra = (bg.loggs[idxs] >= 3.5) & (bg.Teffs[idxs] <= 10000)
+    return _run_tp(N, host_masses, radii_comp[idxs], u1s_comp[idxs], u2s_comp[idxs], P,
+                   host_masses, rps, incs, eccs, argps, cfr, lnprior, extra, True)
+
+
+def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
+            P_orb: float, M_s: float, R_s: float, Teff: float,
+            Tmag: float, Jmag: float, Hmag: float, Kmag: float,
+            trilegal_fname: str,
+            contrast_curve_file: str = None, filt: str = "TESS",
+            N: int = 1000000, parallel: bool = False,
+            mission: str = "TESS", flatpriors: bool = False,
+            exptime: float = 0.00139, nsamples: int = 20):
+    """EB on a chance-aligned background star (:2038-2362)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    incs = sample_inc(np.random.rand(N))
+    qs = sample_q(np.random.rand(N), M_s)
+    sample_q_companion(np.random.rand(N), M_s)        # drawn and never used, as :2089
+    eccs = sample_ecc(np.random.rand(N), planet=False, P_orb=P_mean)
+    argps = sample_w(np.random.rand(N))
+    bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
+    radii_comp = bg.radii()
+    u1s_comp, u2s_comp = grid_for(mission).nearest_each(bg.Teffs, bg.loggs, bg.Zs)
+    idxs = np.random.randint(0, bg.N_comp, N)         # :2139
+    host_masses = bg.masses[idxs]
+    host_radii = radii_comp[idxs]
+    cfr = bg.fluxratios[idxs]
+    masses = qs * host_masses
+    radii, _ = stellar_relations(masses, host_radii, bg.Teffs[idxs])
+
+    def distance_corrected(band):
+        # EB flux ratio scaled from "bound at the target's distance" to the background star's
+        # actual brightness (:2147-2182)
+        cfr_band = bg.fluxratios_in(band)[idxs]
+        bound = _fluxratio(host_masses, M_s, band)
+        return _fluxratio(masses, M_s, band) * (cfr_band / bound), cfr_band
+
+    fluxratios, _ = distance_corrected("TESS")
+    if contrast_curve_file is None:
+        dmag = 2.5 * np.log10((cfr / (1 - cfr)) + (fluxratios / (1 - fluxratios)))
+        lnprior = _background_prior(bg, N, None, dmag, None)
+    else:
+        # "TESS" and "Vis" share one flux relation and use the TESS-band magnitudes
+        fr_cc, cfr_cc = distance_corrected(filt if filt in ("J", "H", "K") else "TESS")
+        dmag = 2.5 * np.log10((cfr_cc / (1 - cfr_cc)) + (fr_cc / (1 - fr_cc)))
+        lnprior = _background_prior(bg, N, contrast_curve_file, None, dmag)
+    extra = (bg.loggs[idxs] >= 3.5) & (bg.Teffs[idxs] <= 10000)
+    return _run_eb(N, host_masses, host_radii, u1s_comp[idxs], u2s_comp[idxs], P,
+                   host_masses + masses, incs, qs, eccs, argps, masses, radii, fluxratios, cfr,
+                   lnprior, extra, True)
