@@ -48,7 +48,8 @@ def stars_table(ID, Tmag, Jmag, Hmag, Kmag, mass, rad, Teff, plx, n_neighbours=1
     # target: the observed depth needs the full aperture flux; one bright-enough neighbour could
     # host it too, the others would need tdepth > 1
     df.loc[0, "tdepth"] = 0.0105
-    df.loc[1, "tdepth"] = 0.62
-    df.loc[1, "fluxratio"] = 0.015
-    df.loc[1, ["mass", "rad", "Teff"]] = [0.62, 0.60, 4100.0]
+    if n_neighbours > 0:
+        df.loc[1, "tdepth"] = 0.62
+        df.loc[1, "fluxratio"] = 0.015
+        df.loc[1, ["mass", "rad", "Teff"]] = [0.62, 0.60, 4100.0]
     return df

@@ -1,0 +1,129 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+TOI465 = dict(P=3.836169, M=0.811, R=0.84738, Teff=4936.0, plx=8.16366,
+              T=10.7307, J=9.906, H=9.473, K=9.339)
+KEP10 = dict(P=0.837, M=1.017, R=1.08974, Teff=5706.0, plx=5.36185)
+
+
+def load_lc(name):
+    lc = np.loadtxt(os.path.join(GOLD, name), delimiter=",")
+    return lc[:, 0].copy(), lc[:, 1].copy(), float(np.mean(lc[:, 2]))
+
+
+@pytest.fixture(scope="session")
+def toi465_lc():
+    return load_lc("TOI465_01_lightcurve.csv")
+
+
+@pytest.fixture(scope="session")
+def kepler10b_lc():
+    return load_lc("Kepler10b_lightcurve.csv")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    def _load(name):
+        return np.load(os.path.join(GOLD, name), allow_pickle=False)
+    return _load
+
+
+@pytest.fixture(scope="session")
+def trilegal_file():
+    return os.path.join(GOLD, "trilegal_synth.csv")
+
+
+@pytest.fixture(scope="session")
+def contrast_file():
+    return os.path.join(GOLD, "TOI465_01_contrastcurve.csv")
+
+
+@pytest.fixture()
+def oracle_engine():
+    """Routes the host layer to the CPU oracle stand-in for the duration of a test."""
+    import _oracle_engine
+    eng = _oracle_engine.install()
+    yield eng
+    _oracle_engine.uninstall()
+
+
+@pytest.fixture(scope="session")
+def gpu_engine():
+    """The real CUDA engine; fails (does not skip) if the extension cannot run."""
+    from triceratops_b200.engine import get_engine
+    return get_engine()
+
+
+def lnz_calls(star, N, tri, cc, lc, mission="TESS", exptime=0.00139):
+    """The scenario calls of oracle/gen_golden.py, against any module exposing lnZ_*."""
+    t, f, s = lc
+    base = (t, f, s, star["P"], star["M"], star["R"], star["Teff"])
+    tail = (N, True, mission, False, exptime, 20)
+    mags = (star.get("T"), star.get("J"), star.get("H"), star.get("K"))
+    calls = {
+        "TTP": lambda m: m.lnZ_TTP(*base, 0.0, *tail),
+        "TEB": lambda m: m.lnZ_TEB(*base, 0.0, *tail),
+    }
+    if tri is None:
+        return calls
+    calls.update({
+        "PTP": lambda m: m.lnZ_PTP(*base, 0.0, star["plx"], None, "TESS", *tail, None),
+        "PTPcc": lambda m: m.lnZ_PTP(*base, 0.0, star["plx"], cc, "K", *tail, None),
+        "PEB": lambda m: m.lnZ_PEB(*base, 0.0, star["plx"], None, "TESS", *tail, None),
+        "PEBcc": lambda m: m.lnZ_PEB(*base, 0.0, star["plx"], cc, "K", *tail, None),
+        "STP": lambda m: m.lnZ_STP(*base, 0.0, star["plx"], None, "TESS", *tail, None),
+        "STPcc": lambda m: m.lnZ_STP(*base, 0.0, star["plx"], cc, "K", *tail, None),
+        "SEB": lambda m: m.lnZ_SEB(*base, 0.0, star["plx"], None, "TESS", *tail, None),
+        "SEBcc": lambda m: m.lnZ_SEB(*base, 0.0, star["plx"], cc, "K", *tail, None),
+        "DTP": lambda m: m.lnZ_DTP(*base, 0.0, *mags, tri, None, "TESS", *tail),
+        "DTPcc": lambda m: m.lnZ_DTP(*base, 0.0, *mags, tri, cc, "K", *tail),
+        "DEB": lambda m: m.lnZ_DEB(*base, 0.0, *mags, tri, None, "TESS", *tail),
+        "DEBcc": lambda m: m.lnZ_DEB(*base, 0.0, *mags, tri, cc, "J", *tail),
+        "BTP": lambda m: m.lnZ_BTP(*base, *mags, tri, None, "TESS", *tail),
+        "BTPcc": lambda m: m.lnZ_BTP(*base, *mags, tri, cc, "H", *tail),
+        "BEB": lambda m: m.lnZ_BEB(*base, *mags, tri, None, "TESS", *tail),
+        "BEBcc": lambda m: m.lnZ_BEB(*base, *mags, tri, cc, "K", *tail),
+    })
+    return calls
+
+
+RESULT_KEYS = ("M_s", "R_s", "u1", "u2", "P_orb", "inc", "b", "R_p", "ecc", "argp", "M_EB",
+               "R_EB", "fluxratio_EB", "fluxratio_comp")
+
+
+def check_against_golden(name, res, gold, lnz_atol=1e-6, arr_rtol=1e-9):
+    """lnZ within tolerance (north_star: 1e-6); best-draw tables equal up to rounding.
+
+    Draws with bit-identical lnL (e.g. every draw whose eclipse misses the observed window) are
+    ordered arbitrarily by the reference's unstable argsort (marginal_likelihoods.py:153) and by
+    index here, so a table that differs row-for-row must still match as a multiset of rows.
+    """
+    branches = res if isinstance(res, tuple) else (res,)
+    for b, r in enumerate(branches):
+        g_lnz = float(gold["%s/%d/lnZ" % (name, b)])
+        if np.isfinite(g_lnz):
+            assert abs(r["lnZ"] - g_lnz) <= lnz_atol * max(1.0, abs(g_lnz)), \
+                (name, b, r["lnZ"], g_lnz)
+        else:
+            assert r["lnZ"] == g_lnz, (name, b, r["lnZ"], g_lnz)
+        mine = np.stack([np.asarray(r[k], float) for k in RESULT_KEYS], axis=1)
+        want = np.stack([gold["%s/%d/%s" % (name, b, k)] for k in RESULT_KEYS], axis=1)
+        if not np.allclose(mine, want, rtol=arr_rtol, atol=0, equal_nan=True):
+            mine = mine[np.lexsort(mine.T[::-1])]
+            want = want[np.lexsort(want.T[::-1])]
+        np.testing.assert_allclose(mine, want, rtol=arr_rtol, atol=0,
+                                   err_msg="%s branch %d best-draw table" % (name, b))

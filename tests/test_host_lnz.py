@@ -1,0 +1,103 @@
+"""The Python host layer (prior draws, wiring of the ten lnZ_* functions, result tables,
+calc_probs) against fixtures produced by the reference's own marginal_likelihoods.py /
+triceratops.py.  The GPU is replaced by the oracle stand-in (tests/_oracle_engine.py), so this
+isolates the host logic; the same comparisons run on the real engine in test_gpu_lnz.py."""
+import numpy as np
+import pytest
+
+from conftest import KEP10, TOI465, check_against_golden, lnz_calls
+
+import triceratops_b200.marginal_likelihoods as ml
+
+NAMES = ["TTP", "TEB", "PTP", "PTPcc", "PEB", "PEBcc", "STP", "STPcc", "SEB", "SEBcc", "DTP",
+         "DTPcc", "DEB", "DEBcc", "BTP", "BTPcc", "BEB", "BEBcc"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_lnz_functions_reproduce_reference(name, oracle_engine, golden, toi465_lc, trilegal_file,
+                                           contrast_file):
+    g = golden("lnz_toi465.npz")
+    calls = lnz_calls(TOI465, int(g["N"]), trilegal_file, contrast_file, toi465_lc)
+    np.random.seed(int(g["seed"]))
+    check_against_golden(name, calls[name](ml), g, lnz_atol=1e-9, arr_rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["TTP", "TEB"])
+def test_kepler_long_cadence(name, oracle_engine, golden, kepler10b_lc):
+    g = golden("lnz_kepler10b.npz")
+    calls = lnz_calls(KEP10, int(g["N"]), None, None, kepler10b_lc, mission="Kepler",
+                      exptime=0.0204)
+    np.random.seed(int(g["seed"]))
+    check_against_golden(name, calls[name](ml), g, lnz_atol=1e-9, arr_rtol=1e-12)
+
+
+def test_period_range_is_sampled(oracle_engine, toi465_lc):
+    t, f, s = toi465_lc
+    np.random.seed(3)
+    res = ml.lnZ_TTP(t, f, s, [3.8, 3.9], 0.811, 0.84738, 4936.0, 0.0, 400, True)
+    assert res["P_orb"].min() >= 3.8 and res["P_orb"].max() <= 3.9
+    assert len(set(res["P_orb"])) > 1
+
+
+def test_numpy_scalar_period_is_treated_as_a_range_like_the_reference(oracle_engine, toi465_lc):
+    t, f, s = toi465_lc
+    with pytest.raises((IndexError, TypeError)):
+        ml.lnZ_TTP(t, f, s, np.float64(3.8), 0.811, 0.84738, 4936.0, 0.0, 100, True)
+
+
+def test_molusc_padding_masks_missing_companions(oracle_engine, toi465_lc, tmp_path):
+    import pandas as pd
+    t, f, s = toi465_lc
+    p = tmp_path / "molusc.csv"
+    pd.DataFrame({"semi-major axis(AU)": [50.0, 5.0, 80.0], "eccentricity": [0.1, 0.1, 0.2],
+                  "mass ratio": [0.5, 0.6, 0.05]}).to_csv(p, index=False)
+    np.random.seed(1)
+    res = ml.lnZ_PTP(t, f, s, 3.836169, 0.811, 0.84738, 4936.0, 0.0, 8.16, None, "TESS", 300,
+                     True, "TESS", False, 0.00139, 20, str(p))
+    # only the two wide companions exist; every padded draw has q == 0 and is masked
+    assert np.isfinite(res["lnZ"]) or res["lnZ"] == -np.inf
+
+
+def test_calc_probs_reproduces_reference(oracle_engine, golden, toi465_lc, trilegal_file,
+                                         contrast_file):
+    from oracle import synth
+    from triceratops_b200.triceratops import target
+    g = golden("calc_probs.npz")
+    t, f, s = toi465_lc
+    stars = synth.stars_table(270380593, TOI465["T"], TOI465["J"], TOI465["H"], TOI465["K"],
+                              TOI465["M"], TOI465["R"], TOI465["Teff"], TOI465["plx"])
+    tgt = target(270380593, stars=stars, trilegal_fname=trilegal_file)
+    np.random.seed(int(g["seed"]))
+    tgt.calc_probs(t, f, s, TOI465["P"], contrast_curve_file=contrast_file, filt="K",
+                   N=int(g["N"]), parallel=True, verbose=0)
+    assert list(tgt.probs.scenario.values) == list(g["scenario"])
+    assert np.array_equal(tgt.probs.ID.values, g["ID"])
+    assert np.array_equal(tgt.star_num, g["star_num"])
+    np.testing.assert_allclose(tgt.lnZ, g["lnZ"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(tgt.probs.prob.values, g["prob"], rtol=0, atol=1e-9)
+    assert abs(tgt.FPP - float(g["FPP"])) < 1e-9 and abs(tgt.NFPP - float(g["NFPP"])) < 1e-9
+    for col in ("M_s", "R_s", "P_orb", "inc", "b", "ecc", "w", "R_p", "M_EB", "R_EB"):
+        np.testing.assert_allclose(tgt.probs[col].values, g["probs/" + col], rtol=1e-12)
+    assert tgt.FPP_degenerate is False
+
+
+def test_calc_probs_drop_scenario_and_degenerate_warning(oracle_engine, toi465_lc, trilegal_file):
+    from oracle import synth
+    from triceratops_b200.triceratops import target
+    t, f, s = toi465_lc
+    stars = synth.stars_table(1, 10.7, 9.9, 9.5, 9.3, 0.811, 0.847, 4936.0, 8.16, n_neighbours=0)
+    tgt = target(1, stars=stars, trilegal_fname=trilegal_file)
+    everything = ["TP", "EB", "PTP", "PEB", "STP", "SEB", "DTP", "DEB", "BTP", "BEB"]
+    with pytest.warns(RuntimeWarning):
+        tgt.calc_probs(t, f, s, 3.836169, N=50, parallel=True, drop_scenario=everything,
+                       verbose=0)
+    assert tgt.FPP_degenerate is True and len(tgt.probs) == 15 and tgt.NFPP == 0.0
+    assert np.all(np.isneginf(tgt.lnZ))
+
+
+def test_target_requires_a_stars_table():
+    from triceratops_b200.triceratops import target
+    with pytest.raises(NotImplementedError):
+        target(1, sectors=np.array([1]))
+    with pytest.raises(ValueError):
+        target(1, mission="Hubble")

@@ -39,7 +39,7 @@ __all__ = ["lnZ_TTP", "lnZ_TEB", "lnZ_PTP", "lnZ_PEB", "lnZ_STP", "lnZ_SEB", "ln
 # ------------------------------------------------------------------------------ shared pieces
 def _periods(P_orb, N):
     """Fixed period or uniform draws over a range (marginal_likelihoods.py:67-72).  Returns
-    (array or scalar for the engine, callable idx -> P_orb[idx], mean period)."""
+    (per-draw array, or a float that the engine broadcasts; mean period for sample_ecc)."""
     if type(P_orb) not in [float, int]:
         P = np.random.uniform(low=P_orb[0], high=P_orb[-1], size=N)
         return P, np.mean(P)
@@ -84,7 +84,8 @@ def _companion_q(N, M_s, molusc_file):
     df = read_csv(molusc_file)
     sma = df["semi-major axis(AU)"].values
     e = df["eccentricity"].values
-    q = df[sma * (1 - e) > 10]["mass ratio"].values
+    # copy: pandas >= 3 hands out read-only views (the reference assigns into .values)
+    q = np.array(df[sma * (1 - e) > 10]["mass ratio"].values, dtype=float)
     q[q < 0.1 / M_s] = 0.1 / M_s
     return np.pad(q, (0, N - len(q)))
 

@@ -1,0 +1,208 @@
+"""`target.calc_probs(...)`: the caller of the marginal-likelihood path, as a drop-in.
+
+Mirrors the reference's triceratops/triceratops.py:673-1485 (calc_probs) with the same signature,
+scenario table layout (15 target-star rows + 3 per nearby star with tdepth > 0), attributes
+(`probs`, `lnZ`, `FPP`, `NFPP`, `FPP_degenerate`, `star_num`, `u1`, `u2`, `fluxratio_EB`,
+`fluxratio_comp`) and warnings.
+
+The rest of the reference's `target` class -- TIC/Gaia/TessCut queries in __init__, plotting,
+aperture bookkeeping, calc_depths -- is outside this package's scope (SURVEY.md section 2 rows
+8-11): there is no network here, so a `target` is built from a stars table the caller already
+has (the reference's `target.stars` DataFrame, e.g. saved from an online session) and a saved
+TRILEGAL file.
+"""
+import warnings
+
+import numpy as np
+from pandas import DataFrame
+
+from ._numerics import _normalize_probabilities
+from .funcs import renorm_flux
+from .marginal_likelihoods import (lnZ_BEB, lnZ_BTP, lnZ_DEB, lnZ_DTP, lnZ_PEB, lnZ_PTP, lnZ_SEB,
+                                   lnZ_STP, lnZ_TEB, lnZ_TTP)
+
+_STAR_COLUMNS = ("ID", "Tmag", "Jmag", "Hmag", "Kmag", "ra", "dec", "mass", "rad", "Teff", "plx",
+                 "fluxratio", "tdepth")
+
+_RESULT_KEYS = ("M_s", "R_s", "u1", "u2", "P_orb", "inc", "b", "R_p", "ecc", "argp", "M_EB",
+                "R_EB", "fluxratio_EB", "fluxratio_comp")
+
+# (drop_scenario key, first row, star_num, scenario names) in the reference's order
+# (triceratops.py:784-1332)
+_TARGET_SCENARIOS = (
+    ("TP", 0, 1, ("TP",)),
+    ("EB", 1, 1, ("EB", "EBx2P")),
+    ("PTP", 3, 1, ("PTP",)),
+    ("PEB", 4, 1, ("PEB", "PEBx2P")),
+    ("STP", 6, 2, ("STP",)),
+    ("SEB", 7, 2, ("SEB", "SEBx2P")),
+    ("DTP", 9, 1, ("DTP",)),
+    ("DEB", 10, 1, ("DEB", "DEBx2P")),
+    ("BTP", 12, 2, ("BTP",)),
+    ("BEB", 13, 2, ("BEB", "BEBx2P")),
+)
+
+
+class target:
+    def __init__(self, ID: int, sectors=None, search_radius: int = 10, mission: str = "TESS",
+                 lightkurve_cache_dir=None, trilegal_fname=None, ra: float = None,
+                 dec: float = None, verify_ssl: bool = True, stars: DataFrame = None):
+        """Offline constructor: same leading arguments as the reference (triceratops.py:42-45)
+        plus `stars`, the table the reference would have assembled from TIC (one row per star,
+        target first, columns ID, Tmag, Jmag, Hmag, Kmag, ra, dec, mass, rad, Teff, plx,
+        fluxratio, tdepth)."""
+        if mission != "TESS" and mission != "Kepler" and mission != "K2":
+            raise ValueError("Introduced invalid mission: " + mission)
+        if stars is None:
+            raise NotImplementedError(
+                "catalogue queries are outside triceratops_b200 (no network): pass the stars "
+                "table as target(..., stars=DataFrame)")
+        missing = [c for c in _STAR_COLUMNS if c not in stars.columns]
+        if missing:
+            raise ValueError("stars table lacks columns: " + ", ".join(missing))
+        self.ID = ID
+        self.mission = mission
+        self.sectors = sectors
+        self.search_radius = search_radius
+        self.N_pix = 2 * search_radius + 2
+        self.stars = stars.reset_index(drop=True)
+        self.trilegal_fname = trilegal_fname
+        self.trilegal_url = None
+
+    def calc_probs(self, time: np.ndarray, flux_0: np.ndarray,
+                   flux_err_0: float, P_orb,
+                   contrast_curve_file: str = None, filt: str = "TESS",
+                   N: int = 1000000, parallel: bool = False,
+                   drop_scenario: list = [],
+                   verbose: int = 1, flatpriors: bool = False,
+                   exptime: float = 0.00139, nsamples: int = 20,
+                   molusc_file: str = None):
+        """Relative probability of every scenario, FPP and NFPP (triceratops.py:673-1485)."""
+        keep = ~np.isnan(time) & ~np.isnan(flux_0)
+        time = time[keep]
+        flux_0 = flux_0[keep]
+        filtered = self.stars[self.stars["tdepth"] > 0]
+        n_rows = 3 * len(filtered) + 12
+        targets = np.zeros(n_rows, dtype=np.dtype("i8"))
+        star_num = np.zeros(n_rows, dtype=np.dtype("i8"))
+        scenarios = np.zeros(n_rows, dtype=np.dtype("U6"))
+        best = {k: np.zeros(n_rows) for k in _RESULT_KEYS}
+        lnZ = np.zeros(n_rows)
+
+        def store(j, ID, num, name, res):
+            targets[j], star_num[j], scenarios[j] = ID, num, name
+            if res is None:
+                lnZ[j] = -np.inf
+                return
+            for k in _RESULT_KEYS:
+                best[k][j] = res[k][0]
+            lnZ[j] = res["lnZ"]
+
+        def say(msg):
+            if verbose == 1:
+                print(msg)
+
+        if self.trilegal_fname is None:
+            raise RuntimeError("no saved TRILEGAL table: pass trilegal_fname to target(); "
+                               "the online query of the reference is out of scope")
+        trilegal_fname = self.trilegal_fname
+
+        for i, ID in enumerate(filtered["ID"].values):
+            star = {c: filtered[c].values[i] for c in _STAR_COLUMNS}
+            flux, flux_err = renorm_flux(flux_0, flux_err_0, star["fluxratio"])
+            M_s, R_s, Teff, plx = star["mass"], star["rad"], star["Teff"], star["plx"]
+            mags = (star["Tmag"], star["Jmag"], star["Hmag"], star["Kmag"])
+            Z = 0.0
+            lc = (time, flux, flux_err, P_orb)
+            tail = (N, parallel, self.mission, flatpriors, exptime, nsamples)
+
+            if i == 0:
+                if np.isnan(M_s) or np.isnan(R_s) or np.isnan(Teff) or np.isnan(plx):
+                    print("Insufficient information to validate " + str(ID)
+                          + ". Please ensure a stellar mass (in M_Sun), radius (in R_Sun), "
+                          + "Teff (in K), and plx (in mas) are provided in the .stars dataframe.")
+                    break
+                runners = {
+                    "TP": lambda: lnZ_TTP(*lc, M_s, R_s, Teff, Z, *tail),
+                    "EB": lambda: lnZ_TEB(*lc, M_s, R_s, Teff, Z, *tail),
+                    "PTP": lambda: lnZ_PTP(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                           filt, *tail, molusc_file),
+                    "PEB": lambda: lnZ_PEB(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                           filt, *tail, molusc_file),
+                    "STP": lambda: lnZ_STP(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                           filt, *tail, molusc_file),
+                    "SEB": lambda: lnZ_SEB(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                           filt, *tail, molusc_file),
+                    "DTP": lambda: lnZ_DTP(*lc, M_s, R_s, Teff, Z, *mags, trilegal_fname,
+                                           contrast_curve_file, filt, *tail),
+                    "DEB": lambda: lnZ_DEB(*lc, M_s, R_s, Teff, Z, *mags, trilegal_fname,
+                                           contrast_curve_file, filt, *tail),
+                    "BTP": lambda: lnZ_BTP(*lc, M_s, R_s, Teff, *mags, trilegal_fname,
+                                           contrast_curve_file, filt, *tail),
+                    "BEB": lambda: lnZ_BEB(*lc, M_s, R_s, Teff, *mags, trilegal_fname,
+                                           contrast_curve_file, filt, *tail),
+                }
+                for key, row, num, names in _TARGET_SCENARIOS:
+                    if key in drop_scenario:
+                        for k, name in enumerate(names):
+                            store(row + k, ID, num, name, None)
+                        continue
+                    if len(names) == 1:
+                        say("Calculating " + names[0] + " scenario probability for "
+                            + str(ID) + ".")
+                        store(row, ID, num, names[0], runners[key]())
+                    else:
+                        say("Calculating " + names[0] + " and " + names[1]
+                            + " scenario probabilities for " + str(ID) + ".")
+                        res, res_twin = runners[key]()
+                        store(row, ID, num, names[0], res)
+                        store(row + 1, ID, num, names[1], res_twin)
+            else:
+                # nearby star: unknown properties default to solar (triceratops.py:1345-1350)
+                if np.isnan(Teff):
+                    Teff = 5777
+                if np.isnan(M_s):
+                    M_s = 1.0
+                if np.isnan(R_s):
+                    R_s = 1.0
+                say("Calculating NTP, NEB, and NEB2xP scenario probabilities for "
+                    + str(ID) + ".")
+                row = 15 + 3 * (i - 1)
+                store(row, ID, 1, "NTP", lnZ_TTP(*lc, M_s, R_s, Teff, Z, *tail))
+                res, res_twin = lnZ_TEB(*lc, M_s, R_s, Teff, Z, *tail)
+                store(row + 1, ID, 1, "NEB", res)
+                store(row + 2, ID, 1, "NEBx2P", res_twin)
+
+        relative_probs, status = _normalize_probabilities(lnZ)
+        if status == 'anomaly':
+            warnings.warn(
+                "Unexpected NaN or +inf in scenario log-evidences. This indicates a numerical "
+                "anomaly unrelated to geometric exclusions. Inspect self.lnZ for diagnostics.",
+                RuntimeWarning, stacklevel=2)
+            self.FPP_degenerate = True
+        elif status == 'all_neginf':
+            warnings.warn(
+                "All scenario log-evidences are -inf: every MC draw was geometrically invalid. "
+                "FPP=1.0 reflects a failed computation, not a confident false positive. "
+                "Inspect self.lnZ for diagnostics.",
+                RuntimeWarning, stacklevel=2)
+            self.FPP_degenerate = True
+        else:
+            self.FPP_degenerate = False
+
+        self.probs = DataFrame({
+            "ID": targets, "scenario": scenarios,
+            "M_s": best["M_s"], "R_s": best["R_s"], "P_orb": best["P_orb"], "inc": best["inc"],
+            "b": best["b"], "ecc": best["ecc"], "w": best["argp"], "R_p": best["R_p"],
+            "M_EB": best["M_EB"], "R_EB": best["R_EB"], "prob": relative_probs,
+        })
+        self.lnZ = lnZ
+        self.star_num = star_num
+        self.u1 = best["u1"]
+        self.u2 = best["u2"]
+        self.fluxratio_EB = best["fluxratio_EB"]
+        self.fluxratio_comp = best["fluxratio_comp"]
+        prob = self.probs.prob
+        self.FPP = 1 - (prob[0] + prob[3] + prob[9])
+        self.NFPP = np.sum(prob[15:]) if len(prob) > 15 else 0.0
+        return
