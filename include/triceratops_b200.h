@@ -78,6 +78,8 @@ typedef struct {
     int64_t n_posinf;     /* +inf ln-weights                                                  */
     int64_t n_pass;       /* draws that survived the geometric mask of this branch           */
     int64_t n_stamps;     /* time stamps evaluated inside transit windows (diagnostic)       */
+    int64_t n_interior;   /* evaluated model points with the occultor inside the disc        */
+    int64_t n_limb;       /* evaluated model points with the occultor on the limb            */
     double* lnL_out;      /* optional [N]: per-draw lnL (no prior), -inf where masked         */
     uint8_t* mask_out;    /* optional [N]: the geometric mask                                 */
 } tri_result;

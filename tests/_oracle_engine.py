@@ -1,132 +1,2 @@
-"""TEST-ONLY stand-in for triceratops_b200.engine.Engine backed by the CPU oracle.
-
-Lets the CPU test-suite exercise the Python host layer (prior draws, argument wiring, result
-dictionaries, multi-rank combine over gloo) without a GPU.  It restates the geometry / mask
-expressions of the reference (marginal_likelihoods.py:107-123, :254-299) in numpy and calls
-oracle/coracle.py for the light curves.  Never imported by the package.
-"""
-import math
-
-import numpy as np
-
-from oracle import coracle
-from triceratops_b200._constants import G, Msun, Rearth, Rsun, ln2pi, pi
-
-
-class _Res:
-    pass
-
-
-def _full(x, N):
-    return np.full(N, float(x)) if np.ndim(x) == 0 else np.asarray(x, dtype=float)
-
-
-def _lse_record(lnw, N, res):
-    fin = np.isfinite(lnw)
-    res.n_posinf = int(np.isposinf(lnw).sum())
-    res.n_finite = int(fin.sum())
-    if res.n_finite:
-        res.m = float(lnw[fin].max())
-        res.s = float(np.exp(lnw[fin] - res.m).sum())
-    else:
-        res.m, res.s = -math.inf, 0.0
-    if res.n_posinf:
-        res.lnZ = math.inf
-    elif not res.n_finite:
-        res.lnZ = -math.inf
-    else:
-        res.lnZ = res.m + math.log(res.s) - math.log(N)
-    return res
-
-
-class OracleEngine:
-    device = -1
-
-    def set_lightcurve(self, time, flux, sigma, exptime, nsamples):
-        self.lc = (np.asarray(time, float), np.asarray(flux, float), float(sigma),
-                   float(exptime), int(nsamples))
-
-    def eval_tp(self, N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
-                extra_mask=None, companion_is_host=False, want_lnL=True, want_mask=False):
-        t, f, s, exptime, ns = self.lc
-        rp, P, inc, ecc, argp, mtot, rhost, u1, u2, cfr = [
-            _full(x, N) for x in (rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr)]
-        a = ((G * mtot * Msun) / (4 * pi ** 2) * (P * 86400) ** 2) ** (1 / 3)
-        e_corr = (1 + ecc * np.sin(argp * pi / 180)) / (1 - ecc ** 2)
-        Ptra = (rp * Rearth + rhost * Rsun) / a * e_corr
-        coll = (rp * Rearth + rhost * Rsun) > a * (1 - ecc)
-        inc_min = np.full(N, 90.)
-        ok = Ptra <= 1.
-        inc_min[ok] = np.arccos(Ptra[ok]) * 180. / pi
-        mask = (inc >= inc_min) & (coll == False)  # noqa: E712
-        if extra_mask is not None:
-            mask &= np.asarray(extra_mask, bool)
-        lnL = np.full(N, -np.inf)
-        if mask.any():
-            lnL[mask] = -0.5 * ln2pi - np.log(s) - coracle.lnL_TP_p(
-                t, f, s, rp[mask], P[mask], inc[mask], a[mask], rhost[mask], u1[mask], u2[mask],
-                ecc[mask], argp[mask], cfr[mask], companion_is_host, exptime, ns)
-        res = _Res()
-        res.N, res.lnL, res.mask, res.n_pass, res.n_stamps = N, lnL, mask, int(mask.sum()), 0
-        return _lse_record(lnL if lnprior is None else lnL + _full(lnprior, N), N, res)
-
-    def eval_eb(self, N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr,
-                lnprior=None, extra_mask=None, companion_is_host=False, want_lnL=True,
-                want_mask=False):
-        t, f, s, exptime, ns = self.lc
-        reb, ebfr, q, P, inc, ecc, argp, mtot, rhost, u1, u2, cfr = [
-            _full(x, N) for x in (reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr)]
-        e_corr = (1 + ecc * np.sin(argp * pi / 180)) / (1 - ecc ** 2)
-        out = []
-        for twin in (False, True):
-            Pk = 2 * P if twin else P
-            a = ((G * mtot * Msun) / (4 * pi ** 2) * (Pk * 86400) ** 2) ** (1 / 3)
-            Ptra = (reb * Rsun + rhost * Rsun) / a * e_corr
-            if twin:
-                coll = (2 * rhost * Rsun) > a * (1 - ecc)
-            else:
-                coll = (reb * Rsun + rhost * Rsun) > a * (1 - ecc)
-            inc_min = np.full(N, 90.)
-            ok = Ptra <= 1.
-            inc_min[ok] = np.arccos(Ptra[ok]) * 180. / pi
-            mask = (inc >= inc_min) & (coll == False) & ((q >= 0.95) if twin else (q < 0.95))  # noqa: E712
-            if extra_mask is not None:
-                mask &= np.asarray(extra_mask, bool)
-            lnL = np.full(N, -np.inf)
-            if mask.any():
-                fn = coracle.lnL_EB_twin_p if twin else coracle.lnL_EB_p
-                lnL[mask] = -0.5 * ln2pi - np.log(s) - fn(
-                    t, f, s, reb[mask], ebfr[mask], Pk[mask], inc[mask], a[mask], rhost[mask],
-                    u1[mask], u2[mask], ecc[mask], argp[mask], cfr[mask], companion_is_host,
-                    exptime, ns)
-            res = _Res()
-            res.N, res.lnL, res.mask, res.n_pass, res.n_stamps = N, lnL, mask, int(mask.sum()), 0
-            out.append(_lse_record(lnL if lnprior is None else lnL + _full(lnprior, N), N, res))
-        return tuple(out)
-
-    def lnl_tp(self, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr, companion_is_host):
-        t, f, s, exptime, ns = self.lc
-        return coracle.lnL_TP_p(t, f, s, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
-                                companion_is_host, exptime, ns)
-
-    def lnl_eb(self, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
-               companion_is_host, twin):
-        t, f, s, exptime, ns = self.lc
-        fn = coracle.lnL_EB_twin_p if twin else coracle.lnL_EB_p
-        return fn(t, f, s, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
-                  companion_is_host, exptime, ns)
-
-
-_instance = OracleEngine()
-
-
-def install():
-    """Route triceratops_b200's host layer to the oracle stand-in (tests only)."""
-    from triceratops_b200 import _dispatch
-    _dispatch._engine_factory = lambda: _instance
-    return _instance
-
-
-def uninstall():
-    from triceratops_b200 import _dispatch, engine
-    _dispatch._engine_factory = engine.get_engine
+"""Test helper: the CPU oracle port of the engine (oracle/engine_port.py) under its test name."""
+from oracle.engine_port import OracleEngine, install, uninstall  # noqa: F401

@@ -44,6 +44,7 @@ class tri_result(ctypes.Structure):
     _fields_ = [("lnZ", ctypes.c_double), ("m", ctypes.c_double), ("s", ctypes.c_double),
                 ("n_finite", ctypes.c_int64), ("n_posinf", ctypes.c_int64),
                 ("n_pass", ctypes.c_int64), ("n_stamps", ctypes.c_int64),
+                ("n_interior", ctypes.c_int64), ("n_limb", ctypes.c_int64),
                 ("lnL_out", ctypes.c_void_p), ("mask_out", ctypes.c_void_p)]
 
 

@@ -206,11 +206,8 @@ int eval_tp_device(const tri_tp_args& a, tri_result* out, cudaStream_t s) {
     g.launches += 1;
     CU(cudaGetLastError());
     CU(cudaEventRecord(g.ev[1], s));
-    CU(cudaMemcpyAsync(g.h_counters, g.d_counters, 8 * sizeof(unsigned long long),
-                       cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    const int64_t n_items = (int64_t)g.h_counters[0];
 
+    // the work-list length stays on the device: no host round trip between the two kernels
     LnlArgs A{};
     A.lc = g.lc; A.tab = g.tab; A.eb = 0; A.companion_is_host = a.companion_is_host; A.raw = 0;
     A.twin_uniform = 0;
@@ -218,9 +215,10 @@ int eval_tp_device(const tri_tp_args& a, tri_result* out, cudaStream_t s) {
     A.P = to_col(a.P_orb); A.inc = to_col(a.inc); A.a = Col{S.a, 1}; A.rhost = to_col(a.rhost);
     A.u1 = to_col(a.u1); A.u2 = to_col(a.u2); A.ecc = to_col(a.ecc); A.argp = to_col(a.argp);
     A.cfr = to_col(a.cfr);
-    A.items = S.items; A.count = n_items; A.next = g.d_counters + 2;
+    A.items = S.items; A.count = 0; A.count_dev = g.d_counters + 0; A.next = g.d_counters + 2;
     A.out = S.lnl; A.out_twin = nullptr; A.counters = g.d_counters + 4;
-    if (n_items > 0) { rc = launch_lnl(A, s); if (rc) return rc; }
+    rc = launch_lnl(A, s);
+    if (rc) return rc;
     CU(cudaEventRecord(g.ev[2], s));
     rc = launch_lse(S.lnl, to_col(a.lnprior), N, S.partials, g.d_lse_out, s);
     if (rc) return rc;
@@ -231,8 +229,10 @@ int eval_tp_device(const tri_tp_args& a, tri_result* out, cudaStream_t s) {
     CU(cudaStreamSynchronize(s));
     g.timing_valid = true;
     finish_result(g.h_lse_out[0], N, out);
-    out->n_pass = n_items;
+    out->n_pass = (int64_t)g.h_counters[0];
     out->n_stamps = (int64_t)g.h_counters[5];
+    out->n_interior = (int64_t)g.h_counters[6];
+    out->n_limb = (int64_t)g.h_counters[7];
     return TRI_OK;
 }
 
@@ -266,11 +266,6 @@ int eval_eb_device(const tri_eb_args& a, tri_result out[2], cudaStream_t s) {
     g.launches += 1;
     CU(cudaGetLastError());
     CU(cudaEventRecord(g.ev[1], s));
-    CU(cudaMemcpyAsync(g.h_counters, g.d_counters, 8 * sizeof(unsigned long long),
-                       cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    const int64_t n_items = (int64_t)g.h_counters[0];
-    const int64_t n_twin = (int64_t)g.h_counters[1];
 
     LnlArgs A{};
     A.lc = g.lc; A.tab = g.tab; A.eb = 1; A.companion_is_host = a.companion_is_host; A.raw = 0;
@@ -279,9 +274,10 @@ int eval_eb_device(const tri_eb_args& a, tri_result out[2], cudaStream_t s) {
     A.P = Col{S.p, 1}; A.inc = to_col(a.inc); A.a = Col{S.a, 1}; A.rhost = to_col(a.rhost);
     A.u1 = to_col(a.u1); A.u2 = to_col(a.u2); A.ecc = to_col(a.ecc); A.argp = to_col(a.argp);
     A.cfr = to_col(a.cfr);
-    A.items = S.items; A.count = n_items; A.next = g.d_counters + 2;
+    A.items = S.items; A.count = 0; A.count_dev = g.d_counters + 0; A.next = g.d_counters + 2;
     A.out = S.lnl; A.out_twin = S.lnl_twin; A.counters = g.d_counters + 4;
-    if (n_items > 0) { rc = launch_lnl(A, s); if (rc) return rc; }
+    rc = launch_lnl(A, s);
+    if (rc) return rc;
     CU(cudaEventRecord(g.ev[2], s));
     rc = launch_lse(S.lnl, to_col(a.lnprior), N, S.partials, g.d_lse_out, s);
     if (rc) return rc;
@@ -297,9 +293,13 @@ int eval_eb_device(const tri_eb_args& a, tri_result out[2], cudaStream_t s) {
     g.timing_valid = true;
     finish_result(g.h_lse_out[0], N, &out[0]);
     finish_result(g.h_lse_out[1], N, &out[1]);
-    out[0].n_pass = n_items - n_twin;
-    out[1].n_pass = n_twin;
-    out[0].n_stamps = out[1].n_stamps = (int64_t)g.h_counters[5];
+    out[0].n_pass = (int64_t)g.h_counters[0] - (int64_t)g.h_counters[1];
+    out[1].n_pass = (int64_t)g.h_counters[1];
+    for (int b = 0; b < 2; ++b) {   // the two branches share one launch: totals are joint
+        out[b].n_stamps = (int64_t)g.h_counters[5];
+        out[b].n_interior = (int64_t)g.h_counters[6];
+        out[b].n_limb = (int64_t)g.h_counters[7];
+    }
     return TRI_OK;
 }
 
@@ -460,7 +460,7 @@ int tri_eval_tp_dev(const tri_tp_args* a, tri_result* out, void* stream) {
     if (a->N == 0) {
         LsePartial z{-INFINITY, 0.0, 0, 0};
         finish_result(z, 0, out);
-        out->n_pass = out->n_stamps = 0;
+        out->n_pass = out->n_stamps = out->n_interior = out->n_limb = 0;
         return TRI_OK;
     }
     return eval_tp_device(*a, out, stream ? (cudaStream_t)stream : g.stream);
@@ -478,7 +478,7 @@ int tri_eval_eb_dev(const tri_eb_args* a, tri_result out[2], void* stream) {
         LsePartial z{-INFINITY, 0.0, 0, 0};
         for (int b = 0; b < 2; ++b) {
             finish_result(z, 0, &out[b]);
-            out[b].n_pass = out[b].n_stamps = 0;
+            out[b].n_pass = out[b].n_stamps = out[b].n_interior = out[b].n_limb = 0;
         }
         return TRI_OK;
     }
@@ -608,7 +608,7 @@ static int lnl_seam(int eb, int64_t n, const double* body, const double* ebfr, c
     double* d_out = g.staging.take<double>(n);
     g.launches = 0;
     CU(cudaMemsetAsync(g.d_counters, 0, 8 * sizeof(unsigned long long), s));
-    A.items = nullptr; A.count = n; A.next = g.d_counters + 2;
+    A.items = nullptr; A.count = n; A.count_dev = nullptr; A.next = g.d_counters + 2;
     A.out = d_out; A.out_twin = nullptr; A.counters = g.d_counters + 4;
     CU(cudaEventRecord(g.ev[0], s));
     CU(cudaEventRecord(g.ev[1], s));

@@ -162,11 +162,13 @@ struct LnlArgs {
     Col ebfr;                // EB flux ratio (EB only)
     Col P, inc, a, rhost, u1, u2, ecc, argp, cfr;
     const int64_t* items;    // nullptr: identity list 0..count-1
-    int64_t count;
+    int64_t count;             // number of work items when count_dev == nullptr
+    const unsigned long long* count_dev;  // else read from device memory (written by geometry)
     unsigned long long* next;  // work-queue cursor
     double* out;             // lnL of the (EB) branch, indexed by sample
     double* out_twin;        // lnL of the twin branch (fused EB only)
-    unsigned long long* counters;  // optional [4]: evaluated model points / time stamps in window
+    unsigned long long* counters;  // optional [4]: model points evaluated, time stamps in
+                                   // windows, interior-case points, limb/edge-case points
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -211,12 +213,15 @@ __global__ void __launch_bounds__(kLnlThreads) lnl_kernel(LnlArgs A) {
     const double sigma = lc.sigma;
     const double inv_ns = 1.0 / lc.nsamples;
     unsigned long long n_pts_eval = 0, n_stamps = 0;
+    unsigned n_interior = 0, n_limb = 0;   // per lane; flushed per draw
+    unsigned long long n_int_tot = 0, n_limb_tot = 0;
+    const int64_t count = A.count_dev ? (int64_t)(*A.count_dev) : A.count;
 
     for (;;) {
         unsigned long long w = 0;
         if (lane == 0) w = atomicAdd(A.next, 1ull);
         w = __shfl_sync(0xffffffffu, w, 0);
-        if ((int64_t)w >= A.count) break;
+        if ((int64_t)w >= count) break;
         int64_t item = A.items ? A.items[w] : (((int64_t)w << 1) | A.twin_uniform);
         const int64_t i = item >> 1;
         const int twin = (int)(item & 1);
@@ -302,6 +307,10 @@ __global__ void __launch_bounds__(kLnlThreads) lnl_kernel(LnlArgs A) {
                     double toff = lc.exptime * ((is - 0.5) * inv_ns - 0.5);
                     double z = z_at(o, A.tab, t + toff);
                     acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
+                    // work classes of SURVEY.md 8(d): interior (z <= 1-k) / limb-crossing
+                    if (z >= 0.0 && z <= 1.0 + k && !(k >= 1.0 && z <= k - 1.0)) {
+                        if (z < 1.0 - k) ++n_interior; else ++n_limb;
+                    }
                 }
                 double m = dilute(D, acc / lc.nsamples);
                 double r = lc.flux[j] - m;
@@ -316,11 +325,22 @@ __global__ void __launch_bounds__(kLnlThreads) lnl_kernel(LnlArgs A) {
                             : (-0.5 * log(2.0 * kPi) - log(sigma)) - half_chi2;
             n_stamps += (unsigned long long)(jhi - jlo);
         }
+        n_int_tot += n_interior;
+        n_limb_tot += n_limb;
+        n_interior = n_limb = 0;
     }
-    if (A.counters && lane == 0) {
-        n_pts_eval = n_stamps * (unsigned long long)lc.nsamples;
-        atomicAdd(A.counters + 0, n_pts_eval);
-        atomicAdd(A.counters + 1, n_stamps);
+    if (A.counters) {
+        for (int o = 16; o > 0; o >>= 1) {
+            n_int_tot += __shfl_xor_sync(0xffffffffu, n_int_tot, o);
+            n_limb_tot += __shfl_xor_sync(0xffffffffu, n_limb_tot, o);
+        }
+        if (lane == 0) {
+            n_pts_eval = n_stamps * (unsigned long long)lc.nsamples;
+            atomicAdd(A.counters + 0, n_pts_eval);
+            atomicAdd(A.counters + 1, n_stamps);
+            atomicAdd(A.counters + 2, n_int_tot);
+            atomicAdd(A.counters + 3, n_limb_tot);
+        }
     }
 }
 

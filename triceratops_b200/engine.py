@@ -28,12 +28,14 @@ def get_engine(device=None):
 
 class BranchResult:
     """One scenario branch: lnZ pieces + optional per-draw arrays."""
-    __slots__ = ("lnZ", "m", "s", "n_finite", "n_posinf", "n_pass", "n_stamps", "lnL", "mask", "N")
+    __slots__ = ("lnZ", "m", "s", "n_finite", "n_posinf", "n_pass", "n_stamps", "n_interior",
+                 "n_limb", "lnL", "mask", "N")
 
     def __init__(self, r, N, lnL, mask):
         self.lnZ, self.m, self.s = r.lnZ, r.m, r.s
         self.n_finite, self.n_posinf = r.n_finite, r.n_posinf
         self.n_pass, self.n_stamps = r.n_pass, r.n_stamps
+        self.n_interior, self.n_limb = r.n_interior, r.n_limb
         self.lnL, self.mask, self.N = lnL, mask, N
 
 
