@@ -4,7 +4,7 @@ ranks (one process per GPU), the single small collective that merges the per-ran
 (reference marginal_likelihoods.py:152-154).
 
 Sharding follows SURVEY.md section 8e: every rank makes the same host draws (same seed), rank r
-evaluates the contiguous slice [r*N/G, (r+1)*N/G), and one all-gather of a 205-double record per
+evaluates the contiguous slice [r*N/G, (r+1)*N/G), and one all-gather of a 206-double record per
 scenario branch replaces any exchange of per-draw data.
 """
 import math
@@ -77,7 +77,7 @@ def best_indices(lnL, n_best=N_BEST):
 
 class Branch:
     """Globally combined result of one scenario branch."""
-    __slots__ = ("lnZ", "idx", "n_pass", "lnL_local", "lo", "hi")
+    __slots__ = ("lnZ", "idx", "n_pass", "n_evaluated", "lnL_local", "lo", "hi")
 
 
 def _gather_branch(res, lo, hi, N):
@@ -88,18 +88,21 @@ def _gather_branch(res, lo, hi, N):
     d = _dist()
     local_best = best_indices(res.lnL) if res.lnL is not None and res.lnL.size else \
         np.zeros(0, dtype=np.int64)
+    n_eval = int(np.isfinite(res.lnL).sum()) if res.lnL is not None else 0
     if d is None:
         br.lnZ = res.lnZ
         br.n_pass = res.n_pass
+        br.n_evaluated = n_eval
         br.idx = local_best
         return br
     import torch
     world = d.get_world_size()
-    rec = np.full(5 + 2 * N_BEST, np.nan)
-    rec[0:5] = (res.m, res.s, res.n_finite, res.n_posinf, res.n_pass)
+    H = 6
+    rec = np.full(H + 2 * N_BEST, np.nan)
+    rec[0:H] = (res.m, res.s, res.n_finite, res.n_posinf, res.n_pass, n_eval)
     k = local_best.size
-    rec[5:5 + k] = res.lnL[local_best]
-    rec[5 + N_BEST:5 + N_BEST + k] = (local_best + lo).astype(np.float64)
+    rec[H:H + k] = res.lnL[local_best]
+    rec[H + N_BEST:H + N_BEST + k] = (local_best + lo).astype(np.float64)
     dev = "cuda" if d.get_backend() == "nccl" else "cpu"
     mine = torch.from_numpy(rec).to(dev)
     allrec = torch.empty(world * rec.size, dtype=torch.float64, device=dev)
@@ -108,8 +111,9 @@ def _gather_branch(res, lo, hi, N):
     parts = [(r[0], r[1], int(r[2]), int(r[3])) for r in allrec]
     br.lnZ = _engine_mod.combine_lse(parts, N)
     br.n_pass = int(sum(r[4] for r in allrec))
-    vals = allrec[:, 5:5 + N_BEST].ravel()
-    gidx = allrec[:, 5 + N_BEST:].ravel()
+    br.n_evaluated = int(sum(r[5] for r in allrec))
+    vals = allrec[:, H:H + N_BEST].ravel()
+    gidx = allrec[:, H + N_BEST:].ravel()
     ok = ~np.isnan(gidx)
     vals, gidx = vals[ok], gidx[ok].astype(np.int64)
     order = np.lexsort((gidx, -vals))

@@ -147,12 +147,27 @@ def _background_prior(bg, N, contrast_curve_file, dmag_tess, dmag_cc):
     return _clip_prior(lnprior, dmag_cc)
 
 
+class ScenarioResult(dict):
+    """The reference's result dictionary (same keys) with two diagnostics as attributes:
+    n_pass (draws surviving the geometric mask) and n_evaluated (draws with a finite lnL; when
+    it is below 100 the tail of the best-draw table holds draws of zero weight in arbitrary
+    order, as in the reference)."""
+    n_pass = 0
+    n_evaluated = 0
+
+
+def _finish(br, table):
+    out = ScenarioResult(table)
+    out.n_pass, out.n_evaluated = br.n_pass, br.n_evaluated
+    return out
+
+
 def _tp_result(br, M_host, R_host, u1, u2, P, mtot, incs, rps, eccs, argps, cfr):
     idx = br.idx
     P_i = _take(P, idx)
     a_i = _semi_major_axis(_take(mtot, idx), P_i)
     zeros = np.zeros(N_SAMPLES)
-    return {
+    return _finish(br, {
         'M_s': _take(M_host, idx), 'R_s': _take(R_host, idx),
         'u1': _take(u1, idx), 'u2': _take(u2, idx),
         'P_orb': P_i, 'inc': incs[idx],
@@ -161,7 +176,7 @@ def _tp_result(br, M_host, R_host, u1, u2, P, mtot, incs, rps, eccs, argps, cfr)
         'M_EB': zeros, 'R_EB': zeros.copy(), 'fluxratio_EB': zeros.copy(),
         'fluxratio_comp': _take(cfr, idx) if np.ndim(cfr) else zeros.copy(),
         'lnZ': br.lnZ,
-    }
+    })
 
 
 def _eb_result(br, twin, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, masses, radii,
@@ -171,7 +186,7 @@ def _eb_result(br, twin, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, mas
     P_eff = 2 * P_i if twin else P_i
     a_i = _semi_major_axis(_take(mtot, idx), P_eff)
     zeros = np.zeros(N_SAMPLES)
-    return {
+    return _finish(br, {
         'M_s': _take(M_host, idx), 'R_s': _take(R_host, idx),
         'u1': _take(u1, idx), 'u2': _take(u2, idx),
         'P_orb': P_eff, 'inc': incs[idx],
@@ -180,7 +195,7 @@ def _eb_result(br, twin, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, mas
         'M_EB': masses[idx], 'R_EB': radii[idx], 'fluxratio_EB': fluxratios[idx],
         'fluxratio_comp': _take(cfr, idx) if np.ndim(cfr) else zeros.copy(),
         'lnZ': br.lnZ,
-    }
+    })
 
 
 def _run_tp(N, M_host, R_host, u1, u2, P, mtot, rps, incs, eccs, argps, cfr, lnprior,
