@@ -52,7 +52,7 @@ extern "C" {
 
 double hc_occult_quad(double z, double k, double u1, double u2) {
     Limb L;
-    limb_setup(L, u1, u2);
+    limb_setup(L, u1, u2, k);
     return occult_quad(z, k, L);
 }
 
@@ -91,12 +91,12 @@ void hc_lnl(int eb, int64_t npts, const double* time_sorted, const double* flux_
         const double cfr = cfr_[i];
         const double F_comp = cfr / (1.0 - cfr);
         Limb L;
-        limb_setup(L, u1[i], u2[i]);
         Dilution D;
         double k;
         bool cut = false;
         if (!eb) {
             k = body[i] * kRearth / (rhost * kRsun);
+            limb_setup(L, u1[i], u2[i], k);
             D.two_stage = false;
             D.d1 = 0;
             D.d2 = is_host ? 1.0 / F_comp : F_comp / 1.0;
@@ -110,13 +110,16 @@ void hc_lnl(int eb, int64_t npts, const double* time_sorted, const double* flux_
             const double ws = (90.0 - argp[i] + 180.0) * (kPi / 180.0);
             Orbit os;
             orbit_setup(os, g_tab, ks, P[i], a_rs, inc, ecc[i], ws);
+            Limb Ls;
+            limb_setup(Ls, u1[i], u2[i], ks);
             double sec = INFINITY;
             for (int lane = 0; lane < 25; lane++) {
                 double ts = (lane == 24) ? 0.05 : -0.05 + lane * ((0.05 - -0.05) / 24.0);
                 double z = z_at(os, g_tab, ts);
-                double m = (z > 1.0 + ks) ? 1.0 : occult_quad(z, ks, L);
+                double m = (z > 1.0 + ks) ? 1.0 : occult_quad(z, ks, Ls);
                 sec = std::fmin(sec, m);
             }
+            limb_setup(L, u1[i], u2[i], k);
             D.two_stage = true;
             if (is_host) {
                 D.d1 = F_EB / F_comp;

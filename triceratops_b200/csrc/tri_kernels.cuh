@@ -184,8 +184,9 @@ __device__ __forceinline__ double warp_min(double v) {
 }
 
 constexpr int kLnlThreads = 128;
+constexpr int kLnlMinBlocks = 4;   // 128 registers per thread: 16 warps per SM
 
-__global__ void __launch_bounds__(kLnlThreads) lnl_kernel(LnlArgs A) {
+__global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs A) {
     extern __shared__ double smem[];
     // Stage the folded light curve once per block when it fits (else read through L1/L2).
     LightCurve lc = A.lc;
@@ -211,12 +212,12 @@ __global__ void __launch_bounds__(kLnlThreads) lnl_kernel(LnlArgs A) {
     }
     const int lane = threadIdx.x & 31;
     const double sigma = lc.sigma;
-    const double inv_ns = 1.0 / lc.nsamples;
-    unsigned long long n_pts_eval = 0, n_stamps = 0;
+    unsigned long long n_stamps = 0;
     unsigned n_interior = 0, n_limb = 0;   // per lane; flushed per draw
     unsigned long long n_int_tot = 0, n_limb_tot = 0;
     const int64_t count = A.count_dev ? (int64_t)(*A.count_dev) : A.count;
 
+#pragma unroll 1
     for (;;) {
         unsigned long long w = 0;
         if (lane == 0) w = atomicAdd(A.next, 1ull);
@@ -231,93 +232,114 @@ __global__ void __launch_bounds__(kLnlThreads) lnl_kernel(LnlArgs A) {
         const double rhost = A.rhost.at(i);
         const double a_rs = A.a.at(i) / (rhost * kRsun);          // likelihoods.py:343 / :409
         const double inc = A.inc.at(i) * (kPi / 180.0);            // :344 / :410
-        const double w_rad = (90.0 - argp) * (kPi / 180.0);        // :345 / :411
         const double cfr = A.cfr.at(i);
         const double F_comp = cfr / (1.0 - cfr);
-        Limb L;
-        limb_setup(L, A.u1.at(i), A.u2.at(i));
+        const double u1 = A.u1.at(i), u2 = A.u2.at(i);
+        double k_pri, k_sec = 0.0, F_EB = 0.0;
         Dilution D;
-        double k;
-        bool cut = false;
         if (!A.eb) {
-            k = A.body.at(i) * kRearth / (rhost * kRsun);          // :340
+            k_pri = A.body.at(i) * kRearth / (rhost * kRsun);      // :340
             D.two_stage = false;
             D.d1 = 0.0;
             D.d2 = A.companion_is_host ? 1.0 / F_comp : F_comp / 1.0;   // :352-357
         } else {
             const double reb = A.body.at(i);
             const double fr = A.ebfr.at(i);
-            const double F_EB = fr / (1.0 - fr);
-            k = reb / rhost;                                       // :405-406
-            if ((k - 1.0) < 1e-6) k *= 0.999;
-            double ks = rhost / reb;                               // :417-418
-            if ((ks - 1.0) < 1e-6) ks *= 0.999;
-            const double ws = (90.0 - argp + 180.0) * (kPi / 180.0);  // :419
-            // secondary eclipse: 25 stamps on [-0.05, 0.05], no supersampling      :421-423
-            Orbit os;
-            orbit_setup(os, A.tab, ks, P, a_rs, inc, e, ws);
-            double sec = INFINITY;
-            if (lane < 25) {
-                double ts = (lane == 24) ? 0.05 : -0.05 + lane * ((0.05 - -0.05) / 24.0);
-                double z = z_at(os, A.tab, ts);
-                sec = (z > 1.0 + ks) ? 1.0 : occult_quad(z, ks, L);
-            }
-            sec = warp_min(sec);
-            double sd;
+            F_EB = fr / (1.0 - fr);
+            k_pri = reb / rhost;                                   // :405-406
+            if ((k_pri - 1.0) < 1e-6) k_pri *= 0.999;
+            k_sec = rhost / reb;                                   // :417-418
+            if ((k_sec - 1.0) < 1e-6) k_sec *= 0.999;
             D.two_stage = true;
             if (A.companion_is_host) {                              // :427-432
                 D.d1 = F_EB / F_comp;
-                sec = (sec + F_comp / F_EB) / (1.0 + F_comp / F_EB);
                 D.d2 = 1.0 / (F_comp + F_EB);
             } else {                                                // :433-438
                 D.d1 = F_EB / 1.0;
-                sec = (sec + 1.0 / F_EB) / (1.0 + 1.0 / F_EB);
                 D.d2 = F_comp / (1.0 + F_EB);
             }
-            sd = 1.0 - (sec + D.d2) / (1.0 + D.d2);
-            cut = !twin && !(sd < 1.5 * sigma);                     // :535-538
         }
         double* outp = (twin && A.out_twin) ? A.out_twin : A.out;
+
+        // Two passes through ONE copy of the model code: pass 0 (EB-type only) is the
+        // 25-stamp secondary eclipse on [-0.05, 0.05] d with the roles swapped and no
+        // supersampling (likelihoods.py:417-423), reduced with a minimum; pass 1 is the
+        // observed light curve, reduced to chi^2.
+        double chi = 0.0;
+        bool cut = false;
+        int jlo = 0, jhi = 0;
+#pragma unroll 1
+        for (int pass = A.eb ? 0 : 1; pass < 2; ++pass) {
+            const bool primary = (pass == 1);
+            const double k = primary ? k_pri : k_sec;
+            // w = (90 - argp) pi/180, + 180 deg for the secondary          :345 / :419
+            const double w_rad = primary ? (90.0 - argp) * (kPi / 180.0)
+                                         : (90.0 - argp + 180.0) * (kPi / 180.0);
+            Orbit o;
+            orbit_setup(o, A.tab, k, P, a_rs, inc, e, w_rad);
+            Limb L;
+            limb_setup(L, u1, u2, k);
+            const int ns = primary ? lc.nsamples : 1;
+            const double exptime = primary ? lc.exptime : 0.0;
+            const double inv_ns = 1.0 / ns;
+            if (primary) {
+                // time stamps that can be in transit
+                jlo = 0;
+                jhi = lc.npts;
+                Window win;
+                if (transit_window(o, A.tab, a_rs, P, lc, win)) {
+                    double half = 0.5 * lc.exptime;
+                    jlo = lower_bound(lc.time, lc.npts, win.t_lo - half);
+                    jhi = lower_bound(lc.time, lc.npts, win.t_hi + half);
+                    if (jhi < jlo) jhi = jlo;
+                }
+            } else {
+                jlo = 0;
+                jhi = 25;
+            }
+            double red = primary ? 0.0 : INFINITY;
+            // lane <-> time stamp, serial over sub-exposures
+#pragma unroll 1
+            for (int base = jlo; base < jhi; base += 32) {
+                const int j = base + lane;
+                if (j < jhi) {
+                    const double t = primary ? lc.time[j]
+                                             : ((j == 24) ? 0.05 : -0.05 + j * ((0.05 - -0.05) / 24.0));
+                    double acc = 0.0;
+#pragma unroll 1
+                    for (int is = 1; is <= ns; ++is) {
+                        const double toff = exptime * ((is - 0.5) * inv_ns - 0.5);
+                        const double z = z_at(o, A.tab, t + toff);
+                        acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
+                        // work classes of SURVEY.md 8(d): interior (z <= 1-k) / limb-crossing
+                        if (primary && z >= 0.0 && z <= 1.0 + k && !(k >= 1.0 && z <= k - 1.0)) {
+                            if (z < 1.0 - k) ++n_interior; else ++n_limb;
+                        }
+                    }
+                    const double m = acc / ns;
+                    if (primary) {
+                        const double r = lc.flux[j] - dilute(D, m);
+                        red = fma(r, r, red);
+                    } else {
+                        red = fmin(red, m);
+                    }
+                }
+            }
+            if (!primary) {
+                double sec = warp_min(red);
+                if (A.companion_is_host) sec = (sec + F_comp / F_EB) / (1.0 + F_comp / F_EB);
+                else sec = (sec + 1.0 / F_EB) / (1.0 + 1.0 / F_EB);
+                const double sd = 1.0 - (sec + D.d2) / (1.0 + D.d2);
+                cut = !twin && !(sd < 1.5 * sigma);                 // :535-538
+                if (cut) break;
+            } else {
+                chi = warp_sum(red);
+            }
+        }
         if (cut) {
             if (lane == 0) outp[i] = A.raw ? INFINITY : -INFINITY;
             continue;
         }
-
-        Orbit o;
-        orbit_setup(o, A.tab, k, P, a_rs, inc, e, w_rad);
-
-        // ---- time stamps that can be in transit
-        int jlo = 0, jhi = lc.npts;
-        Window win;
-        if (transit_window(o, A.tab, a_rs, P, lc, win)) {
-            double half = 0.5 * lc.exptime;
-            jlo = lower_bound(lc.time, lc.npts, win.t_lo - half);
-            jhi = lower_bound(lc.time, lc.npts, win.t_hi + half);
-            if (jhi < jlo) jhi = jlo;
-        }
-
-        // ---- chi^2 over the window: lane <-> time stamp, serial over sub-exposures
-        double chi = 0.0;
-        for (int base = jlo; base < jhi; base += 32) {
-            int j = base + lane;
-            if (j < jhi) {
-                double t = lc.time[j];
-                double acc = 0.0;
-                for (int is = 1; is <= lc.nsamples; ++is) {
-                    double toff = lc.exptime * ((is - 0.5) * inv_ns - 0.5);
-                    double z = z_at(o, A.tab, t + toff);
-                    acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
-                    // work classes of SURVEY.md 8(d): interior (z <= 1-k) / limb-crossing
-                    if (z >= 0.0 && z <= 1.0 + k && !(k >= 1.0 && z <= k - 1.0)) {
-                        if (z < 1.0 - k) ++n_interior; else ++n_limb;
-                    }
-                }
-                double m = dilute(D, acc / lc.nsamples);
-                double r = lc.flux[j] - m;
-                chi = fma(r, r, chi);
-            }
-        }
-        chi = warp_sum(chi);
         chi += (lc.prefix[jlo] - lc.prefix[0]) + (lc.prefix[lc.npts] - lc.prefix[jhi]);
         if (lane == 0) {
             double half_chi2 = 0.5 * (chi / (sigma * sigma));       // likelihoods.py:486
@@ -335,8 +357,7 @@ __global__ void __launch_bounds__(kLnlThreads) lnl_kernel(LnlArgs A) {
             n_limb_tot += __shfl_xor_sync(0xffffffffu, n_limb_tot, o);
         }
         if (lane == 0) {
-            n_pts_eval = n_stamps * (unsigned long long)lc.nsamples;
-            atomicAdd(A.counters + 0, n_pts_eval);
+            atomicAdd(A.counters + 0, n_stamps * (unsigned long long)lc.nsamples);
             atomicAdd(A.counters + 1, n_stamps);
             atomicAdd(A.counters + 2, n_int_tot);
             atomicAdd(A.counters + 3, n_limb_tot);

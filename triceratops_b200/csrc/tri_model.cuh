@@ -37,6 +37,48 @@ constexpr double kMsun = 1.988409870698051e+33;
 constexpr double kRsun = 69570000000.0;
 constexpr double kRearth = 637810000.0;
 
+// Reciprocal, reciprocal square root and square root for operands that are known to be normal
+// and well scaled (radius ratios, separations, AGM iterates): hardware seed + Newton steps,
+// without the IEEE slow paths (subnormals, correct rounding).  Accurate to ~1 ulp, which is far
+// inside the 1e-9 tolerance on lnL; on the host (tests/hostcheck) they are the exact operations.
+TRI_HD double fast_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
+#endif
+}
+
+TRI_HD double fast_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);
+    y = fma(y * 0.5, e, y);
+    e = fma(-x * y, y, 1.0);
+    return fma(y * 0.5, e, y);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// sqrt(x) for x >= 0 (0 -> 0, negative -> NaN as with sqrt)
+TRI_HD double fast_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    double y = fast_rsqrt(x);
+    double s = x * y;
+    s = fma(fma(-s, s, x), 0.5 * y, s);
+    return x == 0.0 ? 0.0 : s;
+#else
+    return sqrt(x);
+#endif
+}
+
 constexpr int kTableNe = 256;
 constexpr int kTableNm = 512;
 constexpr double kTableMaxE = 0.95;
@@ -76,10 +118,10 @@ struct Orbit {
     bool table_clamped;  // e beyond the table: last cell extrapolated (monotonicity not guaranteed)
 };
 
-TRI_HD double mean_anomaly_offset(double e, double w) {
-    double s, c;
-    sincos(kHalfPi - w, &s, &c);
-    double off = atan2(sqrt(1.0 - e * e) * s, e + c);
+// Mean anomaly at mid-transit (true anomaly pi/2 - w), from sin w and cos w:
+// sin(pi/2 - w) = cos w, cos(pi/2 - w) = sin w.
+TRI_HD double mean_anomaly_offset(double e, double sinw, double cosw) {
+    double off = atan2(sqrt(1.0 - e * e) * cosw, e + sinw);
     off -= e * sin(off);
     return off;
 }
@@ -89,10 +131,10 @@ TRI_HD void orbit_setup(Orbit& o, const OrbitTable& T, double k, double p, doubl
     o.k = k;
     o.e = e;
     o.n_rate = kTwoPi / p;
-    double off = mean_anomaly_offset(e, w);
+    sincos(w, &o.sinw, &o.cosw);
+    double off = mean_anomaly_offset(e, o.sinw, o.cosw);
     o.ma_tr = off;
     o.c0 = 0.0 - off * p / kTwoPi;
-    sincos(w, &o.sinw, &o.cosw);
     double si = sin(inc_rad);
     o.sini2 = si * si;
     o.a1me2 = a_rs * (1.0 - e * e);
@@ -139,7 +181,7 @@ TRI_HD double z_from_ta(const Orbit& o, double ta) {
     double st, ct;
     sincos(ta, &st, &ct);
     double swt = o.sinw * ct + o.cosw * st;  // sin(w + f)
-    double z = o.a1me2 / (1.0 + o.e * ct) * sqrt(1.0 - swt * swt * o.sini2);
+    double z = o.a1me2 * fast_rcp(1.0 + o.e * ct) * fast_sqrt(1.0 - swt * swt * o.sini2);
     return swt < 0.0 ? -z : z;
 }
 
@@ -148,9 +190,9 @@ TRI_HD double z_at(const Orbit& o, const OrbitTable& T, double t) {
 }
 
 // ---------------------------------------------------------------- elliptic integrals
-// K and E share m1 = 1 - q^2 and its logarithm (Hastings, A&S 17.3.34 / 17.3.36).
-TRI_HD void ellke(double q, double& Kk, double& Ek) {
-    double m1 = 1.0 - q * q;
+// K and E from the complementary parameter m1 = 1 - q^2; they share its logarithm
+// (Hastings, A&S 17.3.34 / 17.3.36).
+TRI_HD void ellke_m1(double m1, double& Kk, double& Ek) {
     double lg = log(m1);
     double ek1 = 1.38629436112 + m1 * (0.09666344259 + m1 * (0.03590092383
                + m1 * (0.03742563713 + m1 * 0.01451196212)));
@@ -164,18 +206,20 @@ TRI_HD void ellke(double q, double& Kk, double& Ek) {
     Ek = ee1 - ee2 * lg;
 }
 
-// Bulirsch (1965) third-kind integral.  One reciprocal per sweep instead of two divisions, and
-// the convergence test |1 - kc/g| > 1e-8 written without its division; the sweep count can only
-// differ from the oracle's when the test is within rounding of its threshold, where one more
-// (quadratically convergent) sweep changes the value below 1e-16.
-TRI_HD double ellpicb(double n, double q) {
-    double kc = sqrt(1.0 - q * q);
+// Bulirsch (1965) third-kind integral, started from kc = sqrt(1 - q^2), p = sqrt(n + 1) and
+// d = 1/p (the callers have closed forms for p and d, see occult_quad).  One reciprocal per
+// sweep instead of two divisions, and the oracle's convergence test |1 - kc/g| > 1e-8 written
+// without its division; the sweep count can only differ from the oracle's when the test is
+// within rounding of its threshold, where one more (quadratically convergent) sweep changes the
+// value below 1e-16.  NaN inputs fall through the test and return NaN, as in the oracle.
+TRI_HD double ellpicb(double kc, double p, double d) {
     double e = kc;
-    double p = sqrt(n + 1.0);
     double m0 = 1.0, c = 1.0;
-    double d = 1.0 / p;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int it = 0; it < 64; ++it) {
-        double ip = 1.0 / p;
+        double ip = fast_rcp(p);
         double f = c;
         c = fma(d, ip, c);
         double g = e * ip;
@@ -184,10 +228,10 @@ TRI_HD double ellpicb(double n, double q) {
         g = m0;
         m0 = kc + m0;
         if (fabs(g - kc) > 1e-8 * g) {
-            kc = 2.0 * sqrt(e);
+            kc = 2.0 * fast_sqrt(e);
             e = kc * m0;
         } else {
-            return kHalfPi * fma(c, m0, d) / (m0 * (m0 + p));
+            return kHalfPi * fma(c, m0, d) * fast_rcp(m0 * (m0 + p));
         }
     }
     return 0.0;
@@ -197,89 +241,111 @@ TRI_HD double ellpicb(double n, double q) {
 // Limb-darkening mix for one sample: flux = 1 - (c_le*le + c_ld*ld + u2*ed) * inv_omega
 struct Limb {
     double c_le, c_ld, u2, inv_omega;
+    double inv_k;   // 1/k of the occultor this mix is used with
 };
 
-TRI_HD void limb_setup(Limb& L, double u1, double u2) {
+TRI_HD void limb_setup(Limb& L, double u1, double u2, double k) {
     L.c_le = 1.0 - u1 - 2.0 * u2;
     L.c_ld = u1 + 2.0 * u2;
     L.u2 = u2;
     L.inv_omega = 1.0 / (1.0 - u1 / 3.0 - u2 / 6.0);
+    L.inv_k = 1.0 / k;
 }
 
-// Relative flux at separation z (any sign), radius ratio k.  Mirrors oracle eval_quad():
-// same case tests, same expressions; K, E and Pi are evaluated once for whichever of the two
-// general cases (limb-crossing III / interior IV) applies so that divergent lanes share them.
+// Relative flux at separation z (any sign), radius ratio k.  Mirrors oracle eval_quad(): same
+// case tests, same formulas, with the algebra arranged for the GPU:
+//   * K, E and Pi are evaluated once for whichever of the two general cases (limb-crossing III /
+//     interior IV) applies, so divergent lanes share them;
+//   * m1 = 1 - q^2 is formed directly (the oracle takes q = sqrt(..) and squares it again);
+//   * the third-kind parameter n only enters through p = sqrt(n + 1), which is
+//     (k+z)/|k-z| in case IV and 1/|k-z| in case III, and 1/x1 follows from the same
+//     reciprocal: no square root or extra division is needed for them.
 TRI_HD double occult_quad(double z, double k, const Limb& L) {
     if (fabs(z - k) < 1e-6) z += 1e-6;
     if (z > 1.0 + k || z < 0.0) return 1.0;
     if (k >= 1.0 && z <= k - 1.0) return 0.0;
 
     const double k2 = k * k, z2 = z * z;
-    const double x1 = (k - z) * (k - z), x2 = (k + z) * (k + z), x3 = k * k - z * z;
+    const double dkz = k - z, skz = k + z;
+    const double x1 = dkz * dkz, x2 = skz * skz, x3 = k * k - z * z;
     double le = 0.0, ld = 0.0, ed = 0.0, kap0 = 0.0, kap1 = 0.0;
 
     const bool partial = (z >= fabs(1.0 - k) && z <= 1.0 + k);
     if (partial) {
-        kap1 = acos(fmin((1.0 - k2 + z2) * 0.5 / z, 1.0));
-        kap0 = acos(fmin((k2 + z2 - 1.0) * 0.5 / k / z, 1.0));
+        double iz = fast_rcp(z);
+        kap1 = acos(fmin((1.0 - k2 + z2) * 0.5 * iz, 1.0));
+        kap0 = acos(fmin((k2 + z2 - 1.0) * 0.5 * iz * L.inv_k, 1.0));
         double t = 1.0 + z2 - k2;
         le = (k2 * kap0 + kap1 - 0.5 * sqrt(fmax(4.0 * z2 - t * t, 0.0))) * kInvPi;
     }
     if (z <= 1.0 - k) le = k2;
 
-    const bool edge = fabs(z - k) < 1e-4 * (z + k);
+    const bool edge = fabs(dkz) < 1e-4 * skz;
     const bool case3 = !edge && ((z > 0.5 + fabs(k - 0.5) && z < 1.0 + k)
                                  || (k > 0.5 && z > fabs(1.0 - k) * 1.0001 && z < k));
     const bool case4 = !edge && !case3 && (k <= 1.0 && z < (1.0 - k) * 1.0001);
 
-    if (case3 || case4) {
-        double q, n;
+    const bool edge_ke = edge && (k != 0.5);
+    if (case3 || case4 || edge_ke) {
+        const double om = 1.0 - x1;
+        const double adk = fabs(dkz);
+        double m1, p = 1.0, d = 1.0, rs = 1.0, ix1 = 0.0;
         if (case3) {
-            q = sqrt((1.0 - x1) * 0.25 / z / k);
-            n = 1.0 / x1 - 1.0;
+            // q^2 = (1-x1)/(4kz);  n + 1 = 1/x1
+            rs = fast_rsqrt(k * z);                 // 1/sqrt(kz)
+            m1 = 1.0 - om * 0.25 * rs * rs;
+            p = fast_rcp(adk);
+            d = adk;
+            ix1 = p * p;                            // 1/x1
+        } else if (case4) {
+            // q^2 = (x2-x1)/(1-x1);  n + 1 = x2/x1
+            rs = fast_rsqrt(om);                    // 1/sqrt(1-x1)
+            m1 = 1.0 - (x2 - x1) * rs * rs;
+            double i3 = fast_rcp(adk * skz);        // 1/|k^2 - z^2|
+            p = x2 * i3;
+            d = x1 * i3;
+            ix1 = i3 * p;                           // 1/x1
         } else {
-            q = sqrt((x2 - x1) / (1.0 - x1));
-            n = x2 / x1 - 1.0;
+            // occultor's edge at the disc centre: q = 1/(2k) (z > 1/2) or 2k (z < 1/2)
+            double q = (z > 0.5) ? 0.5 * L.inv_k : 2.0 * k;
+            m1 = 1.0 - q * q;
         }
         double Kk, Ek;
-        ellke(q, Kk, Ek);
-        double Pk = ellpicb(n, q);
-        double pterm = 3.0 * x3 / x1 * Pk;
-        if (case3) {
-            ld = 1.0 / 9.0 * kInvPi / sqrt(k * z)
-               * (((1.0 - x2) * (2.0 * x2 + x1 - 3.0) - 3.0 * x3 * (x2 - 2.0)) * Kk
-                  + 4.0 * k * z * (z2 + 7.0 * k2 - 4.0) * Ek - pterm);
-            if (z < k) ld += 2.0 / 3.0;
-            ed = 0.5 * kInvPi * (kap1 + k2 * (k2 + 2.0 * z2) * kap0
-               - (1.0 + 5.0 * k2 + z2) * 0.25 * sqrt((1.0 - x1) * (x2 - 1.0)));
-        } else {
-            ld = 2.0 / 9.0 * kInvPi / sqrt(1.0 - x1)
-               * ((1.0 - 5.0 * z2 + k2 + x3 * x3) * Kk
-                  + (1.0 - x1) * (z2 + 7.0 * k2 - 4.0) * Ek - pterm);
-            if (z < k) ld += 2.0 / 3.0;
-            if (fabs(k + z - 1.0) < 1e-4)
-                ld = 2.0 / 3.0 * kInvPi * acos(1.0 - 2.0 * k)
-                   - 4.0 / 9.0 * kInvPi * sqrt(k * (1.0 - k)) * (3.0 + 2.0 * k - 8.0 * k2);
-            ed = k2 * 0.5 * (k2 + 2.0 * z2);
-        }
-    } else if (edge) {
-        if (k == 0.5) {
-            ld = 1.0 / 3.0 - 4.0 * kInvPi / 9.0;
-            ed = 3.0 / 32.0;
+        ellke_m1(m1, Kk, Ek);
+        if (!edge_ke) {
+            const double Pk = ellpicb(fast_sqrt(m1), p, d);
+            // x3 keeps the oracle's k*k - z*z rounding (it cancels near z = k)
+            const double spterm = 3.0 * x3 * ix1 * Pk;
+            if (case3) {
+                ld = 1.0 / 9.0 * kInvPi * rs
+                   * (((1.0 - x2) * (2.0 * x2 + x1 - 3.0) - 3.0 * x3 * (x2 - 2.0)) * Kk
+                      + 4.0 * k * z * (z2 + 7.0 * k2 - 4.0) * Ek - spterm);
+                if (z < k) ld += 2.0 / 3.0;
+            } else {
+                ld = 2.0 / 9.0 * kInvPi * rs
+                   * ((1.0 - 5.0 * z2 + k2 + x3 * x3) * Kk
+                      + om * (z2 + 7.0 * k2 - 4.0) * Ek - spterm);
+                if (z < k) ld += 2.0 / 3.0;
+                if (fabs(k + z - 1.0) < 1e-4)
+                    ld = 2.0 / 3.0 * kInvPi * acos(1.0 - 2.0 * k)
+                       - 4.0 / 9.0 * kInvPi * sqrt(k * (1.0 - k)) * (3.0 + 2.0 * k - 8.0 * k2);
+            }
         } else if (z > 0.5) {
-            double Kk, Ek;
-            ellke(0.5 / k, Kk, Ek);
             ld = 1.0 / 3.0 + 16.0 * k / 9.0 * kInvPi * (2.0 * k2 - 1.0) * Ek
-               - (32.0 * (k2 * k2) - 20.0 * k2 + 3.0) / 9.0 * kInvPi / k * Kk;
-            ed = 0.5 * kInvPi * (kap1 + k2 * (k2 + 2.0 * z2) * kap0
-               - (1.0 + 5.0 * k2 + z2) * 0.25 * sqrt((1.0 - x1) * (x2 - 1.0)));
+               - (32.0 * (k2 * k2) - 20.0 * k2 + 3.0) / 9.0 * kInvPi * L.inv_k * Kk;
         } else {
-            double Kk, Ek;
-            ellke(2.0 * k, Kk, Ek);
             ld = 1.0 / 3.0 + 2.0 / 9.0 * kInvPi * (4.0 * (2.0 * k2 - 1.0) * Ek
                + (1.0 - 4.0 * k2) * Kk);
-            ed = k2 * 0.5 * (k2 + 2.0 * z2);
         }
+        // eta: limb-crossing form when the occultor reaches beyond the disc centre side
+        if (case3 || (edge_ke && z > 0.5))
+            ed = 0.5 * kInvPi * (kap1 + k2 * (k2 + 2.0 * z2) * kap0
+               - (1.0 + 5.0 * k2 + z2) * 0.25 * sqrt((1.0 - x1) * (x2 - 1.0)));
+        else
+            ed = k2 * 0.5 * (k2 + 2.0 * z2);
+    } else if (edge) {   // k == 1/2 exactly
+        ld = 1.0 / 3.0 - 4.0 * kInvPi / 9.0;
+        ed = 3.0 / 32.0;
     }
     return 1.0 - (L.c_le * le + L.c_ld * ld + L.u2 * ed) * L.inv_omega;
 }
@@ -323,25 +389,30 @@ TRI_HD bool transit_window(const Orbit& o, const OrbitTable& T, double a_rs, dou
     double cmax = (1.0 + o.k) / rmin * (1.0 + 1e-9) + 1e-12;
     if (!(cmax < 0.95)) return false;  // wide arcs: not worth it / not safe
     // f(M) is monotone (bilinear blend of monotone rows); M is taken relative to mid-transit.
+    // Per side: probe the centre (must be inside), the opposite point (must be outside), then
+    // bisect; one probe site keeps the code small.
     double ma0 = o.ma_tr - kTwoPi * floor(o.ma_tr * kInvTwoPi);
-    if (!in_arc(o, ta_from_ma(o, T, ma0 >= kTwoPi ? ma0 - kTwoPi : ma0), cmax)) return false;
     double edge[2];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int side = 0; side < 2; ++side) {
         double sgn = side ? 1.0 : -1.0;
         double lo = 0.0, hi = kPi;  // offset from mid-transit; lo inside the arc, hi outside
-        {
-            double m = ma0 + sgn * hi;
-            m -= kTwoPi * floor(m * kInvTwoPi);
-            if (m >= kTwoPi) m -= kTwoPi;
-            if (in_arc(o, ta_from_ma(o, T, m), cmax)) return false;
-        }
-        for (int it = 0; it < 26; ++it) {
-            double mid = 0.5 * (lo + hi);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int it = -2; it < 26; ++it) {
+            double mid = (it == -2) ? 0.0 : (it == -1) ? kPi : 0.5 * (lo + hi);
             double m = ma0 + sgn * mid;
             m -= kTwoPi * floor(m * kInvTwoPi);
             if (m >= kTwoPi) m -= kTwoPi;
             if (m < 0.0) m += kTwoPi;
-            if (in_arc(o, ta_from_ma(o, T, m), cmax)) lo = mid; else hi = mid;
+            bool inside = in_arc(o, ta_from_ma(o, T, m), cmax);
+            if (it == -2) { if (!inside) return false; }
+            else if (it == -1) { if (inside) return false; }
+            else if (inside) lo = mid;
+            else hi = mid;
         }
         edge[side] = hi;  // first offset known to be outside
     }
