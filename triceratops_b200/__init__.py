@@ -4,5 +4,57 @@ Drop-in for `target.calc_probs(...)` and the ten `lnZ_*` functions of the refere
 (stevengiacalone/triceratops, triceratops/marginal_likelihoods.py): the host code stays in Python
 and mirrors the reference signatures; geometry, light curves, chi^2 and the log-mean-exp run in
 hand-written CUDA kernels behind a C ABI (include/triceratops_b200.h).  No CPU fallback.
+
+    import triceratops_b200
+    triceratops_b200.patch()          # an installed reference now runs this path on the GPU
 """
+import importlib
+
 __version__ = "0.1.0"
+
+LNZ_NAMES = ("lnZ_TTP", "lnZ_TEB", "lnZ_PTP", "lnZ_PEB", "lnZ_STP", "lnZ_SEB", "lnZ_DTP",
+             "lnZ_DEB", "lnZ_BTP", "lnZ_BEB")
+LNL_NAMES = ("lnL_TP_p", "lnL_EB_p", "lnL_EB_twin_p")
+
+_saved = []
+
+
+def patch(level="lnZ", package="triceratops"):
+    """Route an installed reference package through the GPU engine.
+
+    level="lnZ": replace the ten scenario functions.  `calc_probs` resolves them from the globals
+                 of `<package>.triceratops` (star import, triceratops.py:30), so they are set there
+                 and in `<package>.marginal_likelihoods`.
+    level="lnL": keep the reference's own lnZ_* host code and replace only the three per-draw
+                 likelihood functions it calls (`from .likelihoods import *`,
+                 marginal_likelihoods.py:6); requires parallel=True.
+    Returns the list of (module, name) pairs that were replaced; undo with unpatch().
+    """
+    from . import likelihoods, marginal_likelihoods
+    ml = importlib.import_module(package + ".marginal_likelihoods")
+    mods = [ml]
+    try:
+        mods.append(importlib.import_module(package + ".triceratops"))
+    except Exception:  # the class module needs the catalogue stack; the functions do not
+        pass
+    if level == "lnZ":
+        names, source = LNZ_NAMES, marginal_likelihoods
+    elif level == "lnL":
+        names, source = LNL_NAMES, likelihoods
+    else:
+        raise ValueError("level must be 'lnZ' or 'lnL'")
+    done = []
+    for mod in mods:
+        for name in names:
+            if hasattr(mod, name):
+                _saved.append((mod, name, getattr(mod, name)))
+                setattr(mod, name, getattr(source, name))
+                done.append((mod.__name__, name))
+    return done
+
+
+def unpatch():
+    """Restore everything patch() replaced."""
+    while _saved:
+        mod, name, fn = _saved.pop()
+        setattr(mod, name, fn)
