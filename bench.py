@@ -197,12 +197,15 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
     torch.cuda.set_device(local)
+    N = args.draws
+    # host draws first, while no process group exists: calc_probs' host code shards the draws
+    # over ranks when one does, and this bench is weak scaling (N draws per scenario per GPU)
+    calls, npts, host_prep_s = build_workload(N, SEED + rank)
+    assert all(c["N"] == N for c in calls)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = get_engine(local)
     lib = eng.lib
-    N = args.draws
-    calls, npts, host_prep_s = build_workload(N, SEED + rank)
     units_per_step = N_ROWS * N * npts            # samples x points, this rank
 
     # ---- device-resident copies (value path) and pinned host copies (e2e path)
