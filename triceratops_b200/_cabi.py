@@ -57,7 +57,8 @@ _lib = None
 
 
 def library_path():
-    return _build.SO_PATH
+    # TRI_B200_LIB lets developers A/B a differently tuned build of the same sources
+    return os.environ.get("TRI_B200_LIB", _build.SO_PATH)
 
 
 def load():

@@ -184,7 +184,10 @@ __device__ __forceinline__ double warp_min(double v) {
 }
 
 constexpr int kLnlThreads = 128;
-constexpr int kLnlMinBlocks = 4;   // 128 registers per thread: 16 warps per SM
+#ifndef TRI_LNL_MIN_BLOCKS
+#define TRI_LNL_MIN_BLOCKS 6       // 80 registers per thread: 24 warps per SM (A/B: 4->137, 5->130, 6->128, 7->128, 8->130 ms)
+#endif
+constexpr int kLnlMinBlocks = TRI_LNL_MIN_BLOCKS;
 
 __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs A) {
     extern __shared__ double smem[];
