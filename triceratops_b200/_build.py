@@ -6,6 +6,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libtriceratops_b200.so")
+HOST_SO_PATH = os.path.join(CSRC, "libtriceratops_host.so")   # prior-draw helpers (host_prep.c)
 SOURCES = ["tri_cabi.cu"]
 HEADERS = ["tri_kernels.cuh", "tri_model.cuh", os.path.join("..", "..", "include", "triceratops_b200.h")]
 
@@ -32,8 +33,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_host(force=False):
+    """gcc build of csrc/host_prep.c (OpenMP spline evaluation for the prior-draw preparation)."""
+    src = os.path.join(CSRC, "host_prep.c")
+    if (not force and os.path.exists(HOST_SO_PATH)
+            and os.path.getmtime(HOST_SO_PATH) >= os.path.getmtime(src)):
+        return HOST_SO_PATH
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    base = [cc, "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c11"]
+    for extra in (["-fopenmp"], []):
+        if subprocess.run(base + extra + ["-o", HOST_SO_PATH, src]).returncode == 0:
+            return HOST_SO_PATH
+    raise RuntimeError("could not build " + HOST_SO_PATH)
+
+
 def build(force=False, verbose=False):
     """Compile the CUDA library if sources are newer than the .so; returns its path."""
+    build_host(force)
     if not force and not needs_build():
         return SO_PATH
     cmd = [_nvcc()] + NVCC_FLAGS + ["-o", SO_PATH] + [os.path.join(CSRC, s) for s in SOURCES]

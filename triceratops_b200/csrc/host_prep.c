@@ -1,0 +1,69 @@
+/*
+ * Host-side helpers for the PRIOR-DRAW preparation of the lnZ_* functions (not a compute
+ * fallback: nothing of the light-curve path lives here).
+ *
+ * trih_splev: evaluation of a FITPACK B-spline (t, c, k) at m points with extrapolation, the
+ * operation behind scipy's InterpolatedUnivariateSpline.__call__ that the reference uses for its
+ * stellar relations (funcs.py:31-119).  scipy evaluates it single-threaded under the GIL and it
+ * is ~45 % of the host time of a calc_probs at N = 1e6.  This is the same de Boor recurrence in
+ * the same operation order (Dierckx, fpbspl/splev), so the results are bit-identical, spread
+ * over the host cores with OpenMP.  Build: gcc -O2 -ffp-contract=off -fopenmp.
+ */
+#include <stdint.h>
+
+#define KMAX 5
+
+int trih_splev(const double* t, int n, const double* c, int k, const double* x, double* y,
+               int64_t m) {
+    if (k < 1 || k > KMAX || n < 2 * (k + 1)) return -1;
+    const int k1 = k + 1;
+    const int nk1 = n - k1;
+    /* 1-based knot/coefficient access as in the Fortran original */
+    const double* T = t - 1;
+    const double* C = c - 1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < m; i++) {
+        const double arg = x[i];
+        /* knot interval T(l) <= arg < T(l+1), clamped to [k1, nk1] (extrapolation uses the end
+         * polynomial pieces) */
+        int lo = k1, hi = nk1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (arg >= T[mid]) lo = mid; else hi = mid - 1;
+        }
+        const int l = lo;
+        double h[KMAX + 2], hh[KMAX + 1];
+        h[1] = 1.0;
+        for (int j = 1; j <= k; j++) {
+            for (int q = 1; q <= j; q++) hh[q] = h[q];
+            h[1] = 0.0;
+            for (int q = 1; q <= j; q++) {
+                const int li = l + q, lj = li - j;
+                if (T[li] == T[lj]) {
+                    h[q + 1] = 0.0;
+                } else {
+                    const double f = hh[q] / (T[li] - T[lj]);
+                    h[q] = h[q] + f * (T[li] - arg);
+                    h[q + 1] = f * (arg - T[lj]);
+                }
+            }
+        }
+        double sp = 0.0;
+        int ll = l - k1;
+        for (int j = 1; j <= k1; j++) {
+            ll = ll + 1;
+            sp = sp + C[ll] * h[j];
+        }
+        y[i] = sp;
+    }
+    return 0;
+}
+
+int trih_num_threads(void) {
+#ifdef _OPENMP
+    extern int omp_get_max_threads(void);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

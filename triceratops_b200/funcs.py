@@ -9,6 +9,9 @@ import numpy as np
 from pandas import read_csv
 from scipy.interpolate import InterpolatedUnivariateSpline as _Spline
 
+from . import _hostpar
+from ._hostpar import splev as _splev
+
 # --- mass -> (radius, Teff): Torres (2010) above 0.63 Msun, cool-dwarf relation below
 #     (funcs.py:19-51)
 _HOT_M = np.array([0.26, 0.47, 0.59, 0.69, 0.87, 0.98, 1.085, 1.4, 1.65, 2.0, 2.5, 3.0, 4.4,
@@ -45,10 +48,11 @@ def stellar_relations(Masses, max_Radii, max_Teffs):
     cool = Masses <= 0.63
     Radii = np.zeros(len(Masses))
     Teffs = np.zeros(len(Masses))
-    Radii[hot] = _hot_R(Masses[hot])
-    Teffs[hot] = _hot_T(Masses[hot])
-    Radii[cool] = _cool_R(Masses[cool])
-    Teffs[cool] = _cool_T(Masses[cool])
+    m_hot, m_cool = Masses[hot], Masses[cool]
+    Radii[hot] = _splev(_hot_R, m_hot)
+    Teffs[hot] = _splev(_hot_T, m_hot)
+    Radii[cool] = _splev(_cool_R, m_cool)
+    Teffs[cool] = _splev(_cool_T, m_cool)
     big = Radii > max_Radii
     Radii[big] = max_Radii[big]
     warm = Teffs > max_Teffs
@@ -60,7 +64,8 @@ def stellar_relations(Masses, max_Radii, max_Teffs):
 
 def flux_relation(Masses, filt: str = "TESS"):
     """Flux relative to a ~1 Msun star in band `filt` (TESS, Vis, J, H, K) -- funcs.py:121-140."""
-    return 10 ** _FLUX_SPLINES[filt](Masses)
+    y = _splev(_FLUX_SPLINES[filt], Masses)
+    return _hostpar.pmap_concat(lambda v: 10 ** v, y.shape[0], y) if y.ndim else 10 ** y
 
 
 def renorm_flux(flux, flux_err, star_fluxratio: float):

@@ -13,6 +13,7 @@ order) are the same as in the reference expressions, which is what keeps the arr
 import numpy as np
 from scipy.stats import beta, powerlaw
 
+from . import _hostpar
 from ._constants import G, Msun, au, pi
 from .funcs import separation_at_contrast
 
@@ -36,22 +37,27 @@ def _piecewise_powerlaw(x, select, edges, powers, amps):
         tot = tot + integrals[k]
         cum.append(tot)
     norm = 1 / tot
-    # all segment masks are taken from the untouched deviates before any is overwritten
-    masks = []
-    for k in range(nseg):
-        m = x <= norm * cum[k]
-        if k > 0:
-            m = (x > norm * cum[k - 1]) & m
-        if select is not None:
-            m = m & select
-        masks.append(m)
-    for k in range(nseg):
-        m = masks[k]
-        p1 = powers[k] + 1
-        u = x[m] / norm
-        for j in range(k):
-            u = u - integrals[j]
-        x[m] = (u * p1 / amps[k] + edges[k] ** p1) ** (1 / p1)
+
+    def transform(xv, sel):
+        # all segment masks are taken from the untouched deviates before any is overwritten
+        masks = []
+        for k in range(nseg):
+            m = xv <= norm * cum[k]
+            if k > 0:
+                m = (xv > norm * cum[k - 1]) & m
+            if sel is not None:
+                m = m & sel
+            masks.append(m)
+        for k in range(nseg):
+            m = masks[k]
+            p1 = powers[k] + 1
+            u = xv[m] / norm
+            for j in range(k):
+                u = u - integrals[j]
+            xv[m] = (u * p1 / amps[k] + edges[k] ** p1) ** (1 / p1)
+
+    # element-wise and in place: chunks of the same array can be transformed concurrently
+    _hostpar.pmap(transform, x.shape[0], x, select)
     return x
 
 
@@ -76,7 +82,8 @@ def sample_inc(x, lower=0, upper=90):
     """Inclinations [deg], isotropic between lower and upper (priors.py:119-132)."""
     c_lo = np.cos(lower * np.pi / 180)
     norm = 1 / (c_lo - np.cos(upper * np.pi / 180))
-    return np.arccos(c_lo - x / norm) * 180 / np.pi
+    return _hostpar.pmap_concat(lambda xv: np.arccos(c_lo - xv / norm) * 180 / np.pi,
+                                x.shape[0], x)
 
 
 def sample_ecc(x, planet, P_orb):
@@ -147,43 +154,45 @@ def _bound_companion_lnprior(M_s, plx, delta_mags, separations, contrasts, first
     f3 = 0.078 - 0.05 * lm + 0.04 * (lm) ** 2
     alpha = 0.018
     dlogP = 0.7
-    max_Porbs = ((4 * pi ** 2) / (G * M_s * Msun) * (seps * au) ** 3) ** (1 / 2) / 86400
-    lp = np.log10(max_Porbs)
-
     slope = f2 - f1 - alpha * dlogP
-    t2_partial = 0.5 * (lp - 1.0) * (2.0 * f1 + slope * (lp - 1.0))
-    t2 = 0.5 * (2.0 - 1.0) * (2.0 * f1 + slope * (2.0 - 1.0))
-    t3_partial = 0.5 * alpha * (lp ** 2 - 5.4 * lp + 6.8) + f2 * (lp - 2.0)
-    t3 = 0.5 * alpha * (3.4 ** 2 - 5.4 * 3.4 + 6.8) + f2 * (3.4 - 2.0)
     slope2 = f3 - f2 - alpha * dlogP
-    t4_partial = (alpha * dlogP * (lp - 3.4) + f2 * (lp - 3.4)
-                  + slope2 * (0.238095 * lp ** 2 - 0.952381 * lp + 0.485714))
+    t2 = 0.5 * (2.0 - 1.0) * (2.0 * f1 + slope * (2.0 - 1.0))
+    t3 = 0.5 * alpha * (3.4 ** 2 - 5.4 * 3.4 + 6.8) + f2 * (3.4 - 2.0)
     t4 = (alpha * dlogP * (5.5 - 3.4) + f2 * (5.5 - 3.4)
           + slope2 * (0.238095 * 5.5 ** 2 - 0.952381 * 5.5 + 0.485714))
-    t5_partial = f3 * (3.33333 - 17.3566 * np.exp(-0.3 * lp))
     t5 = f3 * (3.33333 - 17.3566 * np.exp(-0.3 * 8.0))
 
-    f_comp = np.zeros(len(seps))
-    seg2 = (lp >= 1.0) & (lp < 2.0)
-    seg3 = (lp >= 2.0) & (lp < 3.4)
-    seg4 = (lp >= 3.4) & (lp < 5.5)
-    seg5 = (lp >= 5.5) & (lp < 8.0)
-    seg6 = lp >= 8.0
-    if first_decade:
-        f_comp[seg2] = t2_partial[seg2]
-        f_comp[seg3] = t2 + t3_partial[seg3]
-        f_comp[seg4] = t2 + t3 + t4_partial[seg4]
-        f_comp[seg5] = t2 + t3 + t4 + t5_partial[seg5]
-        f_comp[seg6] = t2 + t3 + t4 + t5
-    else:
-        f_comp[seg4] = t4_partial[seg4]
-        f_comp[seg5] = t4 + t5_partial[seg5]
-        f_comp[seg6] = t4 + t5
-    if M_act >= 1.0:
-        return np.log(f_comp)
-    f_act = 0.65 * f_comp + 0.35 * f_comp * M_act
-    f_act[f_act < 0.0] = 0.0
-    return np.log(f_act)
+    def fraction(seps):
+        max_Porbs = ((4 * pi ** 2) / (G * M_s * Msun) * (seps * au) ** 3) ** (1 / 2) / 86400
+        lp = np.log10(max_Porbs)
+        t2_partial = 0.5 * (lp - 1.0) * (2.0 * f1 + slope * (lp - 1.0))
+        t3_partial = 0.5 * alpha * (lp ** 2 - 5.4 * lp + 6.8) + f2 * (lp - 2.0)
+        t4_partial = (alpha * dlogP * (lp - 3.4) + f2 * (lp - 3.4)
+                      + slope2 * (0.238095 * lp ** 2 - 0.952381 * lp + 0.485714))
+        t5_partial = f3 * (3.33333 - 17.3566 * np.exp(-0.3 * lp))
+        f_comp = np.zeros(len(seps))
+        seg2 = (lp >= 1.0) & (lp < 2.0)
+        seg3 = (lp >= 2.0) & (lp < 3.4)
+        seg4 = (lp >= 3.4) & (lp < 5.5)
+        seg5 = (lp >= 5.5) & (lp < 8.0)
+        seg6 = lp >= 8.0
+        if first_decade:
+            f_comp[seg2] = t2_partial[seg2]
+            f_comp[seg3] = t2 + t3_partial[seg3]
+            f_comp[seg4] = t2 + t3 + t4_partial[seg4]
+            f_comp[seg5] = t2 + t3 + t4 + t5_partial[seg5]
+            f_comp[seg6] = t2 + t3 + t4 + t5
+        else:
+            f_comp[seg4] = t4_partial[seg4]
+            f_comp[seg5] = t4 + t5_partial[seg5]
+            f_comp[seg6] = t4 + t5
+        if M_act >= 1.0:
+            return np.log(f_comp)
+        f_act = 0.65 * f_comp + 0.35 * f_comp * M_act
+        f_act[f_act < 0.0] = 0.0
+        return np.log(f_act)
+
+    return _hostpar.pmap_concat(fraction, seps.shape[0], seps)
 
 
 def lnprior_bound_TP(M_s, plx, delta_mags, separations, contrasts):
