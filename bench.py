@@ -14,7 +14,8 @@ host, by the package's own lnZ_* code (numpy seed), exactly as `calc_probs` make
   value  : 18 * N * npts / t, inputs already resident in HBM, through tri_eval_*_dev on the
            torch stream, timed with CUDA events (max over ranks).
   e2e    : the same metric through the host-buffer C ABI (tri_eval_tp / tri_eval_eb): every
-           step copies the draws from pinned host memory and reads the per-draw lnL back.
+           step copies the draws from pinned host memory and reads back each row's evidence
+           record and its 100 best draws.
   roofline: FP64-issue roofline of the dominant kernel (lnl_kernel), see DESIGN.md.
   cpu_baseline / --impl reference: the oracle port (C restatement + numpy masks, all host
            cores) on a bounded slice of the same draws.
@@ -41,6 +42,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 TOI465 = dict(ID=270380593, P=3.836169, M=0.811, R=0.84738, Teff=4936.0, plx=8.16366,
               T=10.7307, J=9.906, H=9.473, K=9.339)
 N_ROWS = 18            # scenario rows of the configuration
+N_BEST = 100           # best draws returned per row (marginal_likelihoods.py:152)
 SEED = 2026
 
 # FP64 issue slots per model point (DESIGN.md "Roofline", frozen from SURVEY.md 8d)
@@ -239,12 +241,17 @@ def run_ours(args):
         nb = 1 if c["kind"] == "tp" else 2
         dres, hres = (tri_result * nb)(), (tri_result * nb)()
         for b in range(nb):
-            dl = torch.empty(c["N"], dtype=torch.float64, device="cuda")
-            pt = torch.empty(c["N"], dtype=torch.float64, pin_memory=True)
-            keep += [dl, pt]
-            dres[b].lnL_out = dl.data_ptr()
-            hres[b].lnL_out = pt.numpy().ctypes.data
-            d2h_bytes += c["N"] * 8
+            # what the production host layer asks for: the 100 best draws (selected on the
+            # device) and the evidence record; the per-draw lnL stays in HBM
+            di = torch.empty(N_BEST, dtype=torch.int64, device="cuda")
+            dv = torch.empty(N_BEST, dtype=torch.float64, device="cuda")
+            pi_ = torch.empty(N_BEST, dtype=torch.int64, pin_memory=True)
+            pv = torch.empty(N_BEST, dtype=torch.float64, pin_memory=True)
+            keep += [di, dv, pi_, pv]
+            dres[b].top_cap = hres[b].top_cap = N_BEST
+            dres[b].top_idx, dres[b].top_lnL = di.data_ptr(), dv.data_ptr()
+            hres[b].top_idx, hres[b].top_lnL = pi_.numpy().ctypes.data, pv.numpy().ctypes.data
+            d2h_bytes += N_BEST * 16 + ctypes.sizeof(tri_result)
         dev_calls.append((c, da, dres))
         host_calls.append((c, ha, hres))
 

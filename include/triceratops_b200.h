@@ -82,6 +82,14 @@ typedef struct {
     int64_t n_limb;       /* evaluated model points with the occultor on the limb            */
     double* lnL_out;      /* optional [N]: per-draw lnL (no prior), -inf where masked         */
     uint8_t* mask_out;    /* optional [N]: the geometric mask                                 */
+    /* best draws, i.e. the head of (-lnL).argsort() (marginal_likelihoods.py:152-153), selected
+     * on the GPU: up to top_cap entries with finite lnL, best first, ties by ascending index.
+     * Leave top_cap = 0 to skip.  (Device-pointer calls return them unsorted.)                */
+    int64_t top_cap;      /* in: capacity of top_idx / top_lnL                                */
+    int64_t n_top;        /* out: entries written (= min(top_cap, n_evaluated))               */
+    int64_t n_evaluated;  /* out: draws with a finite lnL (valid when top_cap > 0)            */
+    int64_t* top_idx;     /* out [top_cap]: draw indices                                      */
+    double* top_lnL;      /* out [top_cap]: their lnL                                         */
 } tri_result;
 
 /* Bind this process to one GPU, create the stream, build and upload the orbit table.  */
@@ -116,6 +124,10 @@ int tri_lnl_eb(int64_t n, const double* R_EB, const double* EB_fluxratio, const 
                const double* u2, const double* ecc, const double* argp,
                const double* companion_fluxratio, int32_t companion_is_host, int32_t twin,
                double* out);
+
+/* Per-draw lnL of branch 0/1 of the most recent tri_eval_* call, copied to a host buffer of N
+ * doubles (the array stays on the device until the next call). */
+int tri_fetch_lnl(int32_t branch, double* out, int64_t N);
 
 /* _log_mean_exp (_numerics.py:12-51) of a host array on the GPU; fills lnZ, m, s, n_*. */
 int tri_log_mean_exp(const double* logw, int64_t n, tri_result* out);

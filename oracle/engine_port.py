@@ -52,7 +52,8 @@ class OracleEngine:
                    float(exptime), int(nsamples))
 
     def eval_tp(self, N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
-                extra_mask=None, companion_is_host=False, want_lnL=True, want_mask=False):
+                extra_mask=None, companion_is_host=False, want_lnL=True, want_mask=False,
+                n_best=0):
         t, f, s, exptime, ns = self.lc
         rp, P, inc, ecc, argp, mtot, rhost, u1, u2, cfr = [
             _full(x, N) for x in (rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr)]
@@ -77,7 +78,7 @@ class OracleEngine:
 
     def eval_eb(self, N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr,
                 lnprior=None, extra_mask=None, companion_is_host=False, want_lnL=True,
-                want_mask=False):
+                want_mask=False, n_best=0):
         t, f, s, exptime, ns = self.lc
         reb, ebfr, q, P, inc, ecc, argp, mtot, rhost, u1, u2, cfr = [
             _full(x, N) for x in (reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr)]

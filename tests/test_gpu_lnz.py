@@ -150,3 +150,66 @@ def test_gpu_log_mean_exp_random(gpu_engine):
     lnw[rng.random(lnw.size) < 0.9] = -np.inf
     got, _ = gpu_engine.log_mean_exp(lnw)
     assert abs(got - _log_mean_exp(lnw, N_total=lnw.size)) < 1e-9
+
+
+def _host_best(lnL, k):
+    """Head of a stable sort of -lnL over the finite entries (ties by ascending index)."""
+    idx = np.flatnonzero(np.isfinite(lnL))
+    order = np.lexsort((idx, -lnL[idx]))
+    return idx[order][:k]
+
+
+@pytest.mark.parametrize("k", [1, 100, 1000])
+def test_device_topk_equals_host_sort(gpu_engine, toi465_lc, k):
+    t, f, s = toi465_lc
+    gpu_engine.set_lightcurve(t, f, s, 0.00139, 20)
+    N = 200_000
+    rng = np.random.default_rng(8)
+    args = (N, rng.uniform(0.5, 20, N), 3.836169, np.degrees(np.arccos(rng.random(N))),
+            rng.beta(0.867, 3.03, N), rng.uniform(0, 360, N), 0.811, 0.84738, 0.43, 0.2, 0.0)
+    r = gpu_engine.eval_tp(*args, want_lnL=True, n_best=k)
+    want = _host_best(r.lnL, k)
+    assert r.n_evaluated == np.isfinite(r.lnL).sum()
+    assert np.array_equal(r.top_idx, want)
+    assert np.array_equal(r.top_lnL, r.lnL[want])
+    assert np.array_equal(gpu_engine.fetch_lnl(0, N), r.lnL)
+
+
+def test_device_topk_ties_and_short_lists(gpu_engine, toi465_lc):
+    """Blocks of identical draws give bit-identical lnL: ties must come out in index order; with
+    fewer finite draws than requested the list is simply shorter."""
+    t, f, s = toi465_lc
+    gpu_engine.set_lightcurve(t, f, s, 0.00139, 20)
+    rng = np.random.default_rng(9)
+    base = 37
+    rp = np.repeat(rng.uniform(1, 15, base), 300)
+    inc = np.repeat(rng.uniform(87.5, 90, base), 300)
+    ecc = np.repeat(rng.uniform(0, 0.3, base), 300)
+    argp = np.repeat(rng.uniform(0, 360, base), 300)
+    N = rp.size
+    r = gpu_engine.eval_tp(N, rp, 3.836169, inc, ecc, argp, 0.811, 0.84738, 0.43, 0.2, 0.0,
+                           want_lnL=True, n_best=100)
+    assert len(np.unique(r.lnL[np.isfinite(r.lnL)])) <= base
+    assert np.array_equal(r.top_idx, _host_best(r.lnL, 100))
+    # only 5 transiting draws among face-on ones
+    inc2 = np.full(N, 5.0)
+    inc2[[3, 77, 1000, 5000, 11000]] = 89.5
+    r = gpu_engine.eval_tp(N, rp, 3.836169, inc2, np.zeros(N), argp, 0.811, 0.84738, 0.43, 0.2,
+                           0.0, want_lnL=True, n_best=100)
+    assert r.n_evaluated == 5 and len(r.top_idx) == 5
+    assert np.array_equal(r.top_idx, _host_best(r.lnL, 100))
+
+
+def test_eb_branches_have_their_own_best_lists(gpu_engine, kepler10b_lc):
+    t, f, s = kepler10b_lc
+    gpu_engine.set_lightcurve(t, f, s, 0.0204, 20)
+    N = 60_000
+    rng = np.random.default_rng(10)
+    q = rng.uniform(0.1, 1.0, N)
+    r0, r1 = gpu_engine.eval_eb(N, 0.1 + 0.9 * q, 0.3 * q ** 3 + 1e-4, q, 0.837,
+                                np.degrees(np.arccos(rng.random(N))), rng.random(N) ** 5,
+                                rng.uniform(0, 360, N), 1.0 + q, 1.0, 0.4, 0.26, 0.05,
+                                want_lnL=True, n_best=100)
+    for r in (r0, r1):
+        assert np.array_equal(r.top_idx, _host_best(r.lnL, 100))
+    assert np.all(q[r0.top_idx] < 0.95) and np.all(q[r1.top_idx] >= 0.95)

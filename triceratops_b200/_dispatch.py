@@ -80,15 +80,33 @@ class Branch:
     __slots__ = ("lnZ", "idx", "n_pass", "n_evaluated", "lnL_local", "lo", "hi")
 
 
-def _gather_branch(res, lo, hi, N):
+def _local_best(res, eng, single_rank):
+    """(indices, lnL values, number of draws with finite lnL) of this rank's best draws.
+
+    The CUDA engine selects them on the device (no per-draw read-back).  With fewer than N_BEST
+    finite draws the reference pads its table with zero-weight draws in the order numpy's
+    argsort happens to give the -inf entries; a single rank reproduces that by fetching the
+    array, ranks of a sharded run pad nothing."""
+    top_idx = getattr(res, "top_idx", None)
+    if top_idx is not None:
+        if single_rank and res.n_evaluated < N_BEST and res.N > 0:
+            lnL = eng.fetch_lnl(res.branch, res.N)
+            idx = best_indices(lnL)
+            return idx, lnL[idx], int(res.n_evaluated)
+        return top_idx, res.top_lnL, int(res.n_evaluated)
+    if res.lnL is None or not res.lnL.size:
+        return np.zeros(0, dtype=np.int64), np.zeros(0), 0
+    idx = best_indices(res.lnL)
+    return idx, res.lnL[idx], int(np.isfinite(res.lnL).sum())
+
+
+def _gather_branch(res, lo, hi, N, eng=None):
     """Merge per-rank results: lnZ from (m, s) records, best draws from per-rank candidates."""
     br = Branch()
     br.lo, br.hi = lo, hi
     br.lnL_local = res.lnL
     d = _dist()
-    local_best = best_indices(res.lnL) if res.lnL is not None and res.lnL.size else \
-        np.zeros(0, dtype=np.int64)
-    n_eval = int(np.isfinite(res.lnL).sum()) if res.lnL is not None else 0
+    local_best, local_vals, n_eval = _local_best(res, eng, d is None)
     if d is None:
         br.lnZ = res.lnZ
         br.n_pass = res.n_pass
@@ -100,8 +118,10 @@ def _gather_branch(res, lo, hi, N):
     H = 6
     rec = np.full(H + 2 * N_BEST, np.nan)
     rec[0:H] = (res.m, res.s, res.n_finite, res.n_posinf, res.n_pass, n_eval)
+    fin = np.isfinite(local_vals)          # zero-weight padding is not exchanged
+    local_best, local_vals = local_best[fin], local_vals[fin]
     k = local_best.size
-    rec[H:H + k] = res.lnL[local_best]
+    rec[H:H + k] = local_vals
     rec[H + N_BEST:H + N_BEST + k] = (local_best + lo).astype(np.float64)
     dev = "cuda" if d.get_backend() == "nccl" else "cpu"
     mine = torch.from_numpy(rec).to(dev)
@@ -128,8 +148,8 @@ def run_tp(N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
     res = eng.eval_tp(hi - lo, *[_slice(x, lo, hi) for x in (rp, P_orb, inc, ecc, argp, mtot,
                                                               rhost, u1, u2, cfr)],
                       lnprior=_slice(lnprior, lo, hi), extra_mask=_mask_slice(extra_mask, lo, hi),
-                      companion_is_host=companion_is_host, want_lnL=True)
-    return _gather_branch(res, lo, hi, N)
+                      companion_is_host=companion_is_host, want_lnL=False, n_best=N_BEST)
+    return _gather_branch(res, lo, hi, N, eng)
 
 
 def run_eb(N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
@@ -139,5 +159,5 @@ def run_eb(N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnp
     r0, r1 = eng.eval_eb(hi - lo, *[_slice(x, lo, hi) for x in (reb, ebfr, q, P_orb, inc, ecc,
                                                                  argp, mtot, rhost, u1, u2, cfr)],
                          lnprior=_slice(lnprior, lo, hi), extra_mask=_mask_slice(extra_mask, lo, hi),
-                         companion_is_host=companion_is_host, want_lnL=True)
-    return _gather_branch(r0, lo, hi, N), _gather_branch(r1, lo, hi, N)
+                         companion_is_host=companion_is_host, want_lnL=False, n_best=N_BEST)
+    return _gather_branch(r0, lo, hi, N, eng), _gather_branch(r1, lo, hi, N, eng)

@@ -78,6 +78,10 @@ struct Ctx {
     LsePartial* d_lse_out = nullptr;           // [2]
     LsePartial* h_lse_out = nullptr;           // pinned [2]
     unsigned long long* h_counters = nullptr;  // pinned [8]
+    TopkState* d_topk = nullptr;               // [2]
+    TopkState* h_topk = nullptr;               // pinned [2]
+    const double* last_lnl[2] = {nullptr, nullptr};   // device lnL arrays of the last eval
+    int64_t last_N = 0;
 };
 
 Ctx g;
@@ -180,6 +184,24 @@ int launch_lnl(LnlArgs& A, cudaStream_t s) {
     return TRI_OK;
 }
 
+// top-K of lnl on the device into (d_idx, d_val); the state record of `slot` receives n_out
+int launch_topk(const double* lnl, int64_t N, int64_t cap, int slot, int64_t* d_idx,
+                double* d_val, cudaStream_t s) {
+    TopkState* st = g.d_topk + slot;
+    int nb = (int)std::max<int64_t>(1, std::min<int64_t>((N + 4095) / 4096,
+                                                         4 * (int64_t)g.sm_count));
+    topk_init_kernel<<<1, 256, 0, s>>>(st, (unsigned long long)cap);
+    for (int pass = 0; pass < 8; ++pass) {
+        topk_hist_kernel<<<nb, kTopkThreads, 0, s>>>(lnl, N, st, pass);
+        topk_scan_kernel<<<1, 32, 0, s>>>(st, pass);
+    }
+    topk_collect_above_kernel<<<nb, kTopkThreads, 0, s>>>(lnl, N, st, d_idx, d_val, cap);
+    topk_collect_ties_kernel<<<1, 1024, 0, s>>>(lnl, N, st, d_idx, d_val, cap);
+    g.launches += 19;
+    CU(cudaGetLastError());
+    return TRI_OK;
+}
+
 // core of tri_eval_tp*: every pointer in `a` is a device pointer
 int eval_tp_device(const tri_tp_args& a, tri_result* out, cudaStream_t s) {
     const int64_t N = a.N;
@@ -222,6 +244,13 @@ int eval_tp_device(const tri_tp_args& a, tri_result* out, cudaStream_t s) {
     CU(cudaEventRecord(g.ev[2], s));
     rc = launch_lse(S.lnl, to_col(a.lnprior), N, S.partials, g.d_lse_out, s);
     if (rc) return rc;
+    const bool want_top = out->top_cap > 0 && out->top_idx && out->top_lnL;
+    if (want_top) {
+        rc = launch_topk(S.lnl, N, out->top_cap, 0, out->top_idx, out->top_lnL, s);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(g.h_topk, g.d_topk, sizeof(TopkState), cudaMemcpyDeviceToHost, s));
+    }
+    g.last_lnl[0] = S.lnl; g.last_lnl[1] = nullptr; g.last_N = N;
     CU(cudaEventRecord(g.ev[3], s));
     CU(cudaMemcpyAsync(g.h_lse_out, g.d_lse_out, sizeof(LsePartial), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(g.h_counters, g.d_counters, 8 * sizeof(unsigned long long),
@@ -233,6 +262,10 @@ int eval_tp_device(const tri_tp_args& a, tri_result* out, cudaStream_t s) {
     out->n_stamps = (int64_t)g.h_counters[5];
     out->n_interior = (int64_t)g.h_counters[6];
     out->n_limb = (int64_t)g.h_counters[7];
+    out->n_top = want_top ? (int64_t)std::min<unsigned long long>(g.h_topk[0].n_out,
+                                                                 (unsigned long long)out->top_cap)
+                          : 0;
+    out->n_evaluated = want_top ? (int64_t)g.h_topk[0].n_finite : -1;
     return TRI_OK;
 }
 
@@ -284,6 +317,18 @@ int eval_eb_device(const tri_eb_args& a, tri_result out[2], cudaStream_t s) {
     rc = launch_lse(S.lnl_twin, to_col(a.lnprior), N, S.partials + S.n_partials,
                     g.d_lse_out + 1, s);
     if (rc) return rc;
+    bool want_top[2];
+    for (int b = 0; b < 2; ++b) {
+        want_top[b] = out[b].top_cap > 0 && out[b].top_idx && out[b].top_lnL;
+        if (want_top[b]) {
+            rc = launch_topk(b ? S.lnl_twin : S.lnl, N, out[b].top_cap, b, out[b].top_idx,
+                             out[b].top_lnL, s);
+            if (rc) return rc;
+        }
+    }
+    if (want_top[0] || want_top[1])
+        CU(cudaMemcpyAsync(g.h_topk, g.d_topk, 2 * sizeof(TopkState), cudaMemcpyDeviceToHost, s));
+    g.last_lnl[0] = S.lnl; g.last_lnl[1] = S.lnl_twin; g.last_N = N;
     CU(cudaEventRecord(g.ev[3], s));
     CU(cudaMemcpyAsync(g.h_lse_out, g.d_lse_out, 2 * sizeof(LsePartial), cudaMemcpyDeviceToHost,
                        s));
@@ -299,8 +344,24 @@ int eval_eb_device(const tri_eb_args& a, tri_result out[2], cudaStream_t s) {
         out[b].n_stamps = (int64_t)g.h_counters[5];
         out[b].n_interior = (int64_t)g.h_counters[6];
         out[b].n_limb = (int64_t)g.h_counters[7];
+        out[b].n_top = want_top[b]
+            ? (int64_t)std::min<unsigned long long>(g.h_topk[b].n_out,
+                                                    (unsigned long long)out[b].top_cap)
+            : 0;
+        out[b].n_evaluated = want_top[b] ? (int64_t)g.h_topk[b].n_finite : -1;
     }
     return TRI_OK;
+}
+
+// best first, ties by ascending index: the order of a stable sort of -lnL
+void sort_candidates(int64_t n, int64_t* idx, double* val) {
+    std::vector<std::pair<double, int64_t>> v((size_t)n);
+    for (int64_t i = 0; i < n; ++i) v[(size_t)i] = {val[i], idx[i]};
+    std::sort(v.begin(), v.end(), [](const std::pair<double, int64_t>& x,
+                                     const std::pair<double, int64_t>& y) {
+        return x.first > y.first || (x.first == y.first && x.second < y.second);
+    });
+    for (int64_t i = 0; i < n; ++i) { val[i] = v[(size_t)i].first; idx[i] = v[(size_t)i].second; }
 }
 
 int check_cols(int64_t N, std::initializer_list<const tri_col*> req) {
@@ -353,6 +414,8 @@ int tri_init(int device) {
     CU(cudaMalloc(&g.d_lse_out, 2 * sizeof(LsePartial)));
     CU(cudaMallocHost(&g.h_lse_out, 2 * sizeof(LsePartial)));
     CU(cudaMallocHost(&g.h_counters, 8 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&g.d_topk, 2 * sizeof(TopkState)));
+    CU(cudaMallocHost(&g.h_topk, 2 * sizeof(TopkState)));
     // occupancy of the persistent light-curve kernel
     int bps = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lnl_kernel, kLnlThreads, 0));
@@ -375,6 +438,8 @@ int tri_shutdown(void) {
     cudaFree(g.d_lse_out);
     cudaFreeHost(g.h_lse_out);
     cudaFreeHost(g.h_counters);
+    cudaFree(g.d_topk);
+    cudaFreeHost(g.h_topk);
     if (g.scratch.base) cudaFree(g.scratch.base);
     if (g.staging.base) cudaFree(g.staging.base);
     for (auto& ev : g.ev) cudaEventDestroy(ev);
@@ -460,7 +525,7 @@ int tri_eval_tp_dev(const tri_tp_args* a, tri_result* out, void* stream) {
     if (a->N == 0) {
         LsePartial z{-INFINITY, 0.0, 0, 0};
         finish_result(z, 0, out);
-        out->n_pass = out->n_stamps = out->n_interior = out->n_limb = 0;
+        out->n_pass = out->n_stamps = out->n_interior = out->n_limb = out->n_top = 0;
         return TRI_OK;
     }
     return eval_tp_device(*a, out, stream ? (cudaStream_t)stream : g.stream);
@@ -478,7 +543,7 @@ int tri_eval_eb_dev(const tri_eb_args* a, tri_result out[2], void* stream) {
         LsePartial z{-INFINITY, 0.0, 0, 0};
         for (int b = 0; b < 2; ++b) {
             finish_result(z, 0, &out[b]);
-            out[b].n_pass = out[b].n_stamps = out[b].n_interior = out[b].n_limb = 0;
+            out[b].n_pass = out[b].n_stamps = out[b].n_interior = out[b].n_limb = out[b].n_top = 0;
         }
         return TRI_OK;
     }
@@ -497,7 +562,8 @@ int tri_eval_tp(const tri_tp_args* a, tri_result* out) {
     const int64_t N = a->N;
     cudaStream_t s = g.stream;
     g.staging.reset();
-    rc = g.staging.reserve((size_t)N * 8 * 13 + (size_t)N * 2 + 8192);
+    rc = g.staging.reserve((size_t)N * 8 * 13 + (size_t)N * 2 + 8192
+                           + (size_t)std::max<int64_t>(out->top_cap, 0) * 16);
     if (rc) return rc;
     tri_tp_args d = *a;
     Col c;
@@ -515,15 +581,29 @@ int tri_eval_tp(const tri_tp_args* a, tri_result* out) {
     tri_result r = *out;
     double* h_lnl = out->lnL_out;
     uint8_t* h_mask = out->mask_out;
+    int64_t* h_tidx = out->top_idx;
+    double* h_tval = out->top_lnL;
+    const bool top = out->top_cap > 0 && h_tidx && h_tval;
     r.lnL_out = h_lnl ? g.staging.take<double>(N) : nullptr;
     r.mask_out = h_mask ? g.staging.take<uint8_t>(N) : nullptr;
+    r.top_cap = top ? out->top_cap : 0;
+    r.top_idx = top ? g.staging.take<int64_t>(out->top_cap) : nullptr;
+    r.top_lnL = top ? g.staging.take<double>(out->top_cap) : nullptr;
     rc = eval_tp_device(d, &r, s);
     if (rc) return rc;
     if (h_lnl) CU(cudaMemcpyAsync(h_lnl, r.lnL_out, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
     if (h_mask) CU(cudaMemcpyAsync(h_mask, r.mask_out, (size_t)N, cudaMemcpyDeviceToHost, s));
+    if (top && r.n_top > 0) {
+        CU(cudaMemcpyAsync(h_tidx, r.top_idx, (size_t)r.n_top * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(h_tval, r.top_lnL, (size_t)r.n_top * 8, cudaMemcpyDeviceToHost, s));
+    }
     CU(cudaStreamSynchronize(s));
+    if (top) sort_candidates(r.n_top, h_tidx, h_tval);
     r.lnL_out = h_lnl;
     r.mask_out = h_mask;
+    r.top_cap = out->top_cap;
+    r.top_idx = h_tidx;
+    r.top_lnL = h_tval;
     *out = r;
     return TRI_OK;
 }
@@ -540,7 +620,9 @@ int tri_eval_eb(const tri_eb_args* a, tri_result out[2]) {
     const int64_t N = a->N;
     cudaStream_t s = g.stream;
     g.staging.reset();
-    rc = g.staging.reserve((size_t)N * 8 * 16 + (size_t)N * 3 + 8192);
+    rc = g.staging.reserve((size_t)N * 8 * 16 + (size_t)N * 3 + 8192
+                           + (size_t)std::max<int64_t>(out[0].top_cap, 0) * 16
+                           + (size_t)std::max<int64_t>(out[1].top_cap, 0) * 16);
     if (rc) return rc;
     tri_eb_args d = *a;
     Col c;
@@ -555,9 +637,16 @@ int tri_eval_eb(const tri_eb_args* a, tri_result out[2]) {
     tri_result r[2] = {out[0], out[1]};
     double* h_lnl[2] = {out[0].lnL_out, out[1].lnL_out};
     uint8_t* h_mask[2] = {out[0].mask_out, out[1].mask_out};
+    int64_t* h_tidx[2] = {out[0].top_idx, out[1].top_idx};
+    double* h_tval[2] = {out[0].top_lnL, out[1].top_lnL};
+    bool top[2];
     for (int b = 0; b < 2; ++b) {
+        top[b] = out[b].top_cap > 0 && h_tidx[b] && h_tval[b];
         r[b].lnL_out = h_lnl[b] ? g.staging.take<double>(N) : nullptr;
         r[b].mask_out = h_mask[b] ? g.staging.take<uint8_t>(N) : nullptr;
+        r[b].top_cap = top[b] ? out[b].top_cap : 0;
+        r[b].top_idx = top[b] ? g.staging.take<int64_t>(out[b].top_cap) : nullptr;
+        r[b].top_lnL = top[b] ? g.staging.take<double>(out[b].top_cap) : nullptr;
     }
     rc = eval_eb_device(d, r, s);
     if (rc) return rc;
@@ -566,11 +655,21 @@ int tri_eval_eb(const tri_eb_args* a, tri_result out[2]) {
             CU(cudaMemcpyAsync(h_lnl[b], r[b].lnL_out, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
         if (h_mask[b])
             CU(cudaMemcpyAsync(h_mask[b], r[b].mask_out, (size_t)N, cudaMemcpyDeviceToHost, s));
+        if (top[b] && r[b].n_top > 0) {
+            CU(cudaMemcpyAsync(h_tidx[b], r[b].top_idx, (size_t)r[b].n_top * 8,
+                               cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(h_tval[b], r[b].top_lnL, (size_t)r[b].n_top * 8,
+                               cudaMemcpyDeviceToHost, s));
+        }
     }
     CU(cudaStreamSynchronize(s));
     for (int b = 0; b < 2; ++b) {
+        if (top[b]) sort_candidates(r[b].n_top, h_tidx[b], h_tval[b]);
         r[b].lnL_out = h_lnl[b];
         r[b].mask_out = h_mask[b];
+        r[b].top_cap = out[b].top_cap;
+        r[b].top_idx = h_tidx[b];
+        r[b].top_lnL = h_tval[b];
         out[b] = r[b];
     }
     return TRI_OK;
@@ -636,6 +735,17 @@ int tri_lnl_eb(int64_t n, const double* R_EB, const double* EB_fluxratio, const 
                int32_t is_host, int32_t twin, double* out) {
     return lnl_seam(1, n, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
                     is_host, twin, out);
+}
+
+int tri_fetch_lnl(int32_t branch, double* out, int64_t N) {
+    int rc = need_ready(false);
+    if (rc) return rc;
+    if (branch < 0 || branch > 1 || !out) return fail(TRI_EINVAL, "bad argument");
+    if (!g.last_lnl[branch] || N != g.last_N)
+        return fail(TRI_ESTATE, "no lnL array of that size from the last tri_eval_* call");
+    CU(cudaSetDevice(g.device));
+    CU(cudaMemcpy(out, g.last_lnl[branch], (size_t)N * 8, cudaMemcpyDeviceToHost));
+    return TRI_OK;
 }
 
 int tri_log_mean_exp(const double* logw, int64_t n, tri_result* out) {

@@ -431,6 +431,138 @@ __global__ void lse_final_kernel(const LsePartial* partials, int n, LsePartial* 
     *out = a;
 }
 
+// ---- best draws: top-K of lnL on the device (reference marginal_likelihoods.py:152-153) --------
+// Radix select on the order-preserving integer image of the doubles: eight 8-bit passes find the
+// exact K-th largest finite value T; everything above T is appended by the whole grid, ties at
+// T are taken in index order by one block, so the selection equals a stable sort by
+// (-lnL, index).  NaN and -inf never qualify.
+struct TopkState {
+    unsigned long long prefix, mask;   // key bits fixed so far
+    unsigned long long k_remaining;    // rank still to resolve inside the current bucket
+    unsigned long long n_finite;       // finite entries seen in pass 0
+    unsigned long long n_out;          // entries written to the output
+    unsigned long long n_ties;         // tie slots to fill with keys == prefix
+    unsigned int hist[256];
+};
+
+__device__ __forceinline__ unsigned long long topk_key(double x) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);   // larger double -> larger key
+}
+
+__device__ __forceinline__ bool topk_valid(double x) { return isfinite(x); }
+
+constexpr int kTopkThreads = 256;
+
+__global__ void topk_init_kernel(TopkState* st, unsigned long long k) {
+    if (threadIdx.x < 256) st->hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        st->prefix = 0; st->mask = 0; st->k_remaining = k; st->n_finite = 0; st->n_out = 0;
+        st->n_ties = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kTopkThreads)
+topk_hist_kernel(const double* lnl, int64_t N, TopkState* st, int pass) {
+    __shared__ unsigned int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long prefix = st->prefix, mask = st->mask;
+    const int shift = 56 - 8 * pass;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double x = lnl[i];
+        if (!topk_valid(x)) continue;
+        unsigned long long key = topk_key(x);
+        if ((key & mask) == prefix) atomicAdd(&h[(key >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void topk_scan_kernel(TopkState* st, int pass) {
+    if (threadIdx.x != 0) return;
+    const int shift = 56 - 8 * pass;
+    unsigned long long total = 0;
+    for (int b = 0; b < 256; ++b) total += st->hist[b];
+    if (pass == 0) {
+        st->n_finite = total;
+        if (st->k_remaining > total) st->k_remaining = total;   // fewer finite entries than K
+    }
+    unsigned long long need = st->k_remaining, above = 0;
+    int bucket = 0;
+    for (int b = 255; b >= 0; --b) {
+        unsigned long long c = st->hist[b];
+        if (above + c >= need && c > 0) { bucket = b; break; }
+        above += c;
+    }
+    if (need == 0) bucket = 255;
+    st->prefix |= (unsigned long long)bucket << shift;
+    st->mask |= 0xffull << shift;
+    st->k_remaining = need - above;     // rank inside the chosen bucket
+    if (pass == 7) st->n_ties = st->k_remaining;   // how many entries equal to T are wanted
+    for (int b = 0; b < 256; ++b) st->hist[b] = 0;
+}
+
+// entries strictly above the threshold: order does not matter (sorted afterwards)
+__global__ void __launch_bounds__(kTopkThreads)
+topk_collect_above_kernel(const double* lnl, int64_t N, TopkState* st, int64_t* out_idx,
+                          double* out_val, int64_t cap) {
+    if (st->n_finite == 0) return;
+    const unsigned long long T = st->prefix;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double x = lnl[i];
+        if (!topk_valid(x) || topk_key(x) <= T) continue;
+        unsigned long long pos = atomicAdd(&st->n_out, 1ull);
+        if ((int64_t)pos < cap) { out_idx[pos] = i; out_val[pos] = x; }
+    }
+}
+
+// entries equal to the threshold, lowest indices first (one block walks the array in order)
+__global__ void __launch_bounds__(1024)
+topk_collect_ties_kernel(const double* lnl, int64_t N, TopkState* st, int64_t* out_idx,
+                         double* out_val, int64_t cap) {
+    __shared__ unsigned int warp_cnt[32];
+    __shared__ unsigned long long base_sh;
+    __shared__ long long want_sh;
+    if (st->n_finite == 0) return;
+    const unsigned long long T = st->prefix;
+    if (threadIdx.x == 0) { base_sh = st->n_out; want_sh = (long long)st->n_ties; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int64_t start = 0; start < N; start += blockDim.x) {
+        long long want = want_sh;
+        if (want <= 0) break;
+        int64_t i = start + threadIdx.x;
+        bool hit = false;
+        double x = 0.0;
+        if (i < N) { x = lnl[i]; hit = topk_valid(x) && topk_key(x) == T; }
+        unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_cnt[wid] = __popc(bal);
+        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            unsigned c = warp_cnt[w];
+            if (w < wid) before += c;
+            total += c;
+        }
+        unsigned rank = before + __popc(bal & ((1u << lane) - 1u));
+        if (hit && (long long)rank < want) {
+            unsigned long long pos = base_sh + rank;
+            if ((int64_t)pos < cap) { out_idx[pos] = i; out_val[pos] = x; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned take = total < (unsigned long long)want ? total : (unsigned)want;
+            base_sh += take;
+            want_sh = want - take;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st->n_out = base_sh;
+}
+
 // ---- FP64 issue-rate probe (roofline denominator measured on the box) -----------------------
 __global__ void dfma_peak_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;

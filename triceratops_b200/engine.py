@@ -29,14 +29,21 @@ def get_engine(device=None):
 class BranchResult:
     """One scenario branch: lnZ pieces + optional per-draw arrays."""
     __slots__ = ("lnZ", "m", "s", "n_finite", "n_posinf", "n_pass", "n_stamps", "n_interior",
-                 "n_limb", "lnL", "mask", "N")
+                 "n_limb", "lnL", "mask", "N", "top_idx", "top_lnL", "n_evaluated", "branch")
 
-    def __init__(self, r, N, lnL, mask):
+    def __init__(self, r, N, lnL, mask, top=None, branch=0):
         self.lnZ, self.m, self.s = r.lnZ, r.m, r.s
         self.n_finite, self.n_posinf = r.n_finite, r.n_posinf
         self.n_pass, self.n_stamps = r.n_pass, r.n_stamps
         self.n_interior, self.n_limb = r.n_interior, r.n_limb
         self.lnL, self.mask, self.N = lnL, mask, N
+        self.branch = branch
+        if top is not None:
+            self.top_idx, self.top_lnL = top[0][:r.n_top], top[1][:r.n_top]
+            self.n_evaluated = r.n_evaluated
+        else:
+            self.top_idx = self.top_lnL = None
+            self.n_evaluated = None
 
 
 def combine_lse(parts, N_total):
@@ -104,17 +111,29 @@ class Engine:
         self._keep.append(a)
         return a.ctypes.data
 
-    def _result(self, N, want_lnL, want_mask):
+    def _result(self, N, want_lnL, want_mask, n_best=0):
         r = tri_result()
         lnL = np.empty(N) if want_lnL else None
         mask = np.empty(N, dtype=np.uint8) if want_mask else None
         r.lnL_out = lnL.ctypes.data if want_lnL else None
         r.mask_out = mask.ctypes.data if want_mask else None
-        return r, lnL, mask
+        top = None
+        if n_best > 0:
+            top = (np.zeros(n_best, dtype=np.int64), np.full(n_best, -np.inf))
+            r.top_cap = n_best
+            r.top_idx, r.top_lnL = top[0].ctypes.data, top[1].ctypes.data
+        return r, lnL, mask, top
+
+    def fetch_lnl(self, branch, N):
+        """Per-draw lnL of the most recent eval_tp / eval_eb call (kept on the device)."""
+        out = np.empty(int(N))
+        _cabi.check(self.lib.tri_fetch_lnl(int(branch), _cabi.dptr(out), int(N)))
+        return out
 
     # ------------------------------------------------------------------ L2 seam
     def eval_tp(self, N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
-                extra_mask=None, companion_is_host=False, want_lnL=True, want_mask=False):
+                extra_mask=None, companion_is_host=False, want_lnL=True, want_mask=False,
+                n_best=0):
         N = int(N)
         self._keep = []
         a = tri_tp_args()
@@ -125,14 +144,14 @@ class Engine:
             setattr(a, name, self._col(val, N))
         a.extra_mask = self._mask(extra_mask, N)
         a.companion_is_host = int(bool(companion_is_host))
-        r, lnL, mask = self._result(N, want_lnL, want_mask)
+        r, lnL, mask, top = self._result(N, want_lnL, want_mask, n_best)
         _cabi.check(self.lib.tri_eval_tp(ctypes.byref(a), ctypes.byref(r)))
         self._keep = []
-        return BranchResult(r, N, lnL, mask.astype(bool) if mask is not None else None)
+        return BranchResult(r, N, lnL, mask.astype(bool) if mask is not None else None, top, 0)
 
     def eval_eb(self, N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr,
                 lnprior=None, extra_mask=None, companion_is_host=False, want_lnL=True,
-                want_mask=False):
+                want_mask=False, n_best=0):
         N = int(N)
         self._keep = []
         a = tri_eb_args()
@@ -146,13 +165,14 @@ class Engine:
         rr = (tri_result * 2)()
         outs = []
         for b in range(2):
-            r, lnL, mask = self._result(N, want_lnL, want_mask)
+            r, lnL, mask, top = self._result(N, want_lnL, want_mask, n_best)
             rr[b] = r
-            outs.append((lnL, mask))
+            outs.append((lnL, mask, top))
         _cabi.check(self.lib.tri_eval_eb(ctypes.byref(a), rr))
         self._keep = []
         return tuple(BranchResult(rr[b], N, outs[b][0],
-                                  outs[b][1].astype(bool) if outs[b][1] is not None else None)
+                                  outs[b][1].astype(bool) if outs[b][1] is not None else None,
+                                  outs[b][2], b)
                      for b in range(2))
 
     # ------------------------------------------------------------------ L1 seam
