@@ -442,6 +442,7 @@ struct TopkState {
     unsigned long long n_finite;       // finite entries seen in pass 0
     unsigned long long n_out;          // entries written to the output
     unsigned long long n_ties;         // tie slots to fill with keys == prefix
+    unsigned long long n_equal;        // entries whose key == prefix
     unsigned int hist[256];
 };
 
@@ -458,7 +459,7 @@ __global__ void topk_init_kernel(TopkState* st, unsigned long long k) {
     if (threadIdx.x < 256) st->hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         st->prefix = 0; st->mask = 0; st->k_remaining = k; st->n_finite = 0; st->n_out = 0;
-        st->n_ties = 0;
+        st->n_ties = 0; st->n_equal = 0;
     }
 }
 
@@ -489,31 +490,38 @@ __global__ void topk_scan_kernel(TopkState* st, int pass) {
         st->n_finite = total;
         if (st->k_remaining > total) st->k_remaining = total;   // fewer finite entries than K
     }
-    unsigned long long need = st->k_remaining, above = 0;
+    unsigned long long need = st->k_remaining, above = 0, in_bucket = 0;
     int bucket = 0;
     for (int b = 255; b >= 0; --b) {
         unsigned long long c = st->hist[b];
-        if (above + c >= need && c > 0) { bucket = b; break; }
+        if (above + c >= need && c > 0) { bucket = b; in_bucket = c; break; }
         above += c;
     }
     if (need == 0) bucket = 255;
     st->prefix |= (unsigned long long)bucket << shift;
     st->mask |= 0xffull << shift;
     st->k_remaining = need - above;     // rank inside the chosen bucket
-    if (pass == 7) st->n_ties = st->k_remaining;   // how many entries equal to T are wanted
+    if (pass == 7) {
+        st->n_ties = st->k_remaining;   // how many entries equal to T are wanted ...
+        st->n_equal = in_bucket;        // ... out of this many
+    }
     for (int b = 0; b < 256; ++b) st->hist[b] = 0;
 }
 
-// entries strictly above the threshold: order does not matter (sorted afterwards)
+// entries strictly above the threshold (and the ones equal to it when all of them are wanted,
+// the usual case of a unique K-th value): order does not matter, they are sorted afterwards
 __global__ void __launch_bounds__(kTopkThreads)
 topk_collect_above_kernel(const double* lnl, int64_t N, TopkState* st, int64_t* out_idx,
                           double* out_val, int64_t cap) {
     if (st->n_finite == 0) return;
     const unsigned long long T = st->prefix;
+    const bool all_ties = st->n_equal <= st->n_ties;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
          i += (int64_t)gridDim.x * blockDim.x) {
         double x = lnl[i];
-        if (!topk_valid(x) || topk_key(x) <= T) continue;
+        if (!topk_valid(x)) continue;
+        unsigned long long key = topk_key(x);
+        if (key < T || (key == T && !all_ties)) continue;
         unsigned long long pos = atomicAdd(&st->n_out, 1ull);
         if ((int64_t)pos < cap) { out_idx[pos] = i; out_val[pos] = x; }
     }
@@ -526,7 +534,7 @@ topk_collect_ties_kernel(const double* lnl, int64_t N, TopkState* st, int64_t* o
     __shared__ unsigned int warp_cnt[32];
     __shared__ unsigned long long base_sh;
     __shared__ long long want_sh;
-    if (st->n_finite == 0) return;
+    if (st->n_finite == 0 || st->n_equal <= st->n_ties) return;   // nothing left to order
     const unsigned long long T = st->prefix;
     if (threadIdx.x == 0) { base_sh = st->n_out; want_sh = (long long)st->n_ties; }
     __syncthreads();
