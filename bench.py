@@ -358,6 +358,9 @@ def run_ours(args):
         "model_points_per_s": pts_all / lnl_s, "model_points_executed_per_s": pts_exec / lnl_s,
         "slots_per_point": {"orbit": SLOTS_ORBIT, "interior": SLOTS_INTERIOR,
                             "limb": SLOTS_LIMB, "per_stamp": SLOTS_STAMP},
+        "work": {"draws_surviving_masks": stat["n_pass"], "stamps_in_windows": stat["n_stamps"],
+                 "points_interior": stat["n_interior"], "points_limb": stat["n_limb"],
+                 "points_reference_evaluates": pts_all},
         "param_stream_GBs": param_bytes / (ms_total * 1e-3) / 1e9,
         "hbm_peak_GBs": _measured_peaks().get("hbm_gbs"),
         "traffic": None,

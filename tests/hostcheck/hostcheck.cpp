@@ -146,11 +146,18 @@ void hc_lnl(int eb, int64_t npts, const double* time_sorted, const double* flux_
             if (stats) stats[1]++;
         }
         double chi = 0.0;
+        const bool probe = nsamples > 1 && !o.table_clamped;
+        const double skip_beyond =
+            1.0 + k + max_projected_speed(o, a_rs) * (0.5 * exptime) + 1e-9;
         for (int j = jlo; j < jhi; j++) {
             double t = lc.time[j], acc = 0.0;
-            for (int is = 1; is <= nsamples; ++is) {
-                double toff = exptime * ((is - 0.5) * inv_ns - 0.5);
+            for (int is = probe ? 0 : 1; is <= nsamples; ++is) {
+                double toff = is ? exptime * ((is - 0.5) * inv_ns - 0.5) : 0.0;
                 double z = z_at(o, g_tab, t + toff);
+                if (is == 0) {
+                    if (std::fabs(z) > skip_beyond) { acc = (double)nsamples; if (stats) stats[2]++; break; }
+                    continue;
+                }
                 acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
             }
             double m = dilute(D, acc / nsamples);

@@ -43,7 +43,7 @@ def _lnl(H, eb, lc, exptime, g, a, P, host, twin, window):
         body, g["EB_fluxratio"], P, g["inc"], a, g["R_s"], g["u1"], g["u2"], g["ecc"], g["argp"],
         g["cfr"])]
     out = np.empty(body.size)
-    st = np.zeros(2, dtype=np.int64)
+    st = np.zeros(3, dtype=np.int64)
     H.hc_lnl(eb, t.size, _p(t), _p(f), s, exptime, 20, body.size, *[_p(c) for c in cols],
              int(host), int(twin), int(window), _p(out), st.ctypes.data_as(I64))
     return out, st

@@ -300,6 +300,10 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                 jlo = 0;
                 jhi = 25;
             }
+            // centre probe (see max_projected_speed): only worth it with supersampling
+            const bool probe = primary && ns > 1 && !o.table_clamped;
+            const double skip_beyond =
+                1.0 + k + max_projected_speed(o, a_rs) * (0.5 * exptime) + 1e-9;
             double red = primary ? 0.0 : INFINITY;
             // lane <-> time stamp, serial over sub-exposures
 #pragma unroll 1
@@ -310,9 +314,13 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                                              : ((j == 24) ? 0.05 : -0.05 + j * ((0.05 - -0.05) / 24.0));
                     double acc = 0.0;
 #pragma unroll 1
-                    for (int is = 1; is <= ns; ++is) {
-                        const double toff = exptime * ((is - 0.5) * inv_ns - 0.5);
+                    for (int is = probe ? 0 : 1; is <= ns; ++is) {
+                        const double toff = is ? exptime * ((is - 0.5) * inv_ns - 0.5) : 0.0;
                         const double z = z_at(o, A.tab, t + toff);
+                        if (is == 0) {   // stamp centre: is the whole exposure out of transit?
+                            if (fabs(z) > skip_beyond) { acc = (double)ns; break; }
+                            continue;
+                        }
                         acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
                         // work classes of SURVEY.md 8(d): interior (z <= 1-k) / limb-crossing
                         if (primary && z >= 0.0 && z <= 1.0 + k && !(k >= 1.0 && z <= k - 1.0)) {

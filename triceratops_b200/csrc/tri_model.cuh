@@ -427,6 +427,21 @@ TRI_HD bool transit_window(const Orbit& o, const OrbitTable& T, double a_rs, dou
     return true;
 }
 
+// Bound on |z(t1) - z(t2)| / |t1 - t2| [stellar radii per day] for the interpolated orbit: the
+// projected separation cannot change faster than the body moves, |dr/df| * df/dt, with
+// |dr/df| <= a(1+e) sqrt(1 + e^2/(1-e^2)) on the ellipse and df/dt <= n (1+e')^2/(1-e'^2)^1.5
+// where e' covers the next row of the (e, M) table.  Loose for eccentric orbits, always safe.
+// A time stamp whose centre has |z| > 1 + k + speed * exptime/2 has every sub-exposure out of
+// transit, so its model is exactly 1 and the sub-exposures need not be evaluated.
+TRI_HD double max_projected_speed(const Orbit& o, double a_rs) {
+    double e = o.e;
+    double e1 = fmin(e + 0.004, 0.96);
+    double om = 1.0 - e1 * e1;
+    double dfdt = o.n_rate * (1.0 + e1) * (1.0 + e1) / (om * sqrt(om));
+    double drdf = a_rs * (1.0 + e) * sqrt(1.0 + e * e / (1.0 - e * e));
+    return 1.1 * dfdt * drdf;
+}
+
 // first index with time[j] >= x
 TRI_HD int lower_bound(const double* t, int n, double x) {
     int lo = 0, hi = n;
