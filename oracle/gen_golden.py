@@ -11,6 +11,8 @@ Fixtures (all seeds via np.random.seed, as the reference uses numpy's global RNG
   l1_<lc>.npz       lnL_TP_p / lnL_EB_p / lnL_EB_twin_p inputs and outputs (likelihoods.py:443-587)
   lnz_toi465.npz    the ten lnZ_* functions (marginal_likelihoods.py) incl. contrast-curve variants
   lnz_kepler10b.npz lnZ_TTP / lnZ_TEB with 30-min exposure supersampling, mission="Kepler"
+  lnz_nearby.npz    lnZ_NTP_unknown / NEB_unknown / NTP_evolved / NEB_evolved (defined by the
+                    reference, never called by it: marginal_likelihoods.py:2365-3178)
   calc_probs.npz    target.calc_probs (triceratops.py:673-1485) on the 18-row configuration
   model.npz         eval_quad / separation values of the restated model itself
 PARITY UNPINNED with respect to real pytransit (see oracle/quadmodel.py).
@@ -71,6 +73,27 @@ def lnz_calls(star, N, tri, cc, lc, mission="TESS", exptime=0.00139):
     return calls
 
 
+def nearby_calls(N, tri, lc):
+    t, f, s = lc
+    P = TOI465["P"]
+    return {
+        "NTPu": lambda m: m.lnZ_NTP_unknown(t, f, s, P, 13.0, tri, N, True),
+        "NEBu": lambda m: m.lnZ_NEB_unknown(t, f, s, P, 13.0, tri, N, True),
+        "NTPe": lambda m: m.lnZ_NTP_evolved(t, f, s, P, 2.5, 5100.0, 0.0, N, True),
+        "NEBe": lambda m: m.lnZ_NEB_evolved(t, f, s, P, 2.5, 5100.0, 0.0, N, True),
+    }
+
+
+def gen_nearby(ref, tri):
+    lc = load_lc("TOI465_01_lightcurve.csv")
+    out = {"N": np.array(N_LNZ), "seed": np.array(SEED)}
+    for name, fn in nearby_calls(N_LNZ, tri, lc).items():
+        np.random.seed(SEED)
+        flatten(name, fn(ref.ml), out)
+    np.savez_compressed(os.path.join(GOLD, "lnz_nearby.npz"), **out)
+    print("lnz_nearby.npz", [(k, float(v)) for k, v in out.items() if k.endswith("lnZ")])
+
+
 def flatten(prefix, res, out):
     rs = res if isinstance(res, tuple) else (res,)
     for b, r in enumerate(rs):
@@ -102,7 +125,11 @@ def transiting_draws(rng, n, star, rsun=6.957e10, rearth=6.3781e8):
 def main():
     ref = refhost.load()
     tri = os.path.join(GOLD, "trilegal_synth.csv")
+    if len(sys.argv) > 1 and sys.argv[1] == "nearby":
+        gen_nearby(ref, tri)
+        return
     synth.trilegal_table(tri, n=2500)
+    gen_nearby(ref, tri)
     cc = os.path.join(GOLD, "TOI465_01_contrastcurve.csv")
 
     # ---- samplers / priors / relations ------------------------------------------------------

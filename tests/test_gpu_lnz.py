@@ -5,7 +5,7 @@ draws (masks bit-exact, per-draw lnL to 1e-9)."""
 import numpy as np
 import pytest
 
-from conftest import KEP10, TOI465, check_against_golden, lnz_calls
+from conftest import KEP10, TOI465, check_against_golden, lnz_calls, nearby_calls
 
 import triceratops_b200.marginal_likelihoods as ml
 
@@ -213,3 +213,20 @@ def test_eb_branches_have_their_own_best_lists(gpu_engine, kepler10b_lc):
     for r in (r0, r1):
         assert np.array_equal(r.top_idx, _host_best(r.lnL, 100))
     assert np.all(q[r0.top_idx] < 0.95) and np.all(q[r1.top_idx] >= 0.95)
+
+
+@pytest.mark.parametrize("name", ["NTPu", "NEBu", "NTPe", "NEBe"])
+def test_unknown_and_evolved_nearby_star_functions(name, gpu_engine, golden, toi465_lc, trilegal_file):
+    """lnZ_NTP_unknown / NEB_unknown / NTP_evolved / NEB_evolved (marginal_likelihoods.py:2365-3178)."""
+    g = golden("lnz_nearby.npz")
+    calls = nearby_calls(int(g["N"]), trilegal_file, toi465_lc)
+    np.random.seed(int(g["seed"]))
+    check_against_golden(name, calls[name](ml), g, lnz_atol=1e-6, arr_rtol=1e-9)
+
+
+def test_unknown_star_without_similar_trilegal_stars(gpu_engine, toi465_lc, trilegal_file):
+    t, f, s = toi465_lc
+    res = ml.lnZ_NTP_unknown(t, f, s, 3.8, 40.0, trilegal_file, 100, True)
+    assert res["lnZ"] == -np.inf and "b" not in res and res["M_s"] == 0
+    res = ml.lnZ_NEB_unknown(t, f, s, 3.8, 40.0, trilegal_file, 100, True)
+    assert isinstance(res, dict) and res["lnZ"] == -np.inf and res["b"] == 0

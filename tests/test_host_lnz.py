@@ -5,7 +5,7 @@ isolates the host logic; the same comparisons run on the real engine in test_gpu
 import numpy as np
 import pytest
 
-from conftest import KEP10, TOI465, check_against_golden, lnz_calls
+from conftest import KEP10, TOI465, check_against_golden, lnz_calls, nearby_calls
 
 import triceratops_b200.marginal_likelihoods as ml
 
@@ -101,3 +101,20 @@ def test_target_requires_a_stars_table():
         target(1, sectors=np.array([1]))
     with pytest.raises(ValueError):
         target(1, mission="Hubble")
+
+
+@pytest.mark.parametrize("name", ["NTPu", "NEBu", "NTPe", "NEBe"])
+def test_unknown_and_evolved_nearby_star_functions(name, oracle_engine, golden, toi465_lc, trilegal_file):
+    """lnZ_NTP_unknown / NEB_unknown / NTP_evolved / NEB_evolved (marginal_likelihoods.py:2365-3178)."""
+    g = golden("lnz_nearby.npz")
+    calls = nearby_calls(int(g["N"]), trilegal_file, toi465_lc)
+    np.random.seed(int(g["seed"]))
+    check_against_golden(name, calls[name](ml), g, lnz_atol=1e-9, arr_rtol=1e-12)
+
+
+def test_unknown_star_without_similar_trilegal_stars(oracle_engine, toi465_lc, trilegal_file):
+    t, f, s = toi465_lc
+    res = ml.lnZ_NTP_unknown(t, f, s, 3.8, 40.0, trilegal_file, 100, True)
+    assert res["lnZ"] == -np.inf and "b" not in res and res["M_s"] == 0
+    res = ml.lnZ_NEB_unknown(t, f, s, 3.8, 40.0, trilegal_file, 100, True)
+    assert isinstance(res, dict) and res["lnZ"] == -np.inf and res["b"] == 0

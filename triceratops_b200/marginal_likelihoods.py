@@ -33,7 +33,8 @@ np.seterr(divide='ignore')
 N_SAMPLES = 100
 
 __all__ = ["lnZ_TTP", "lnZ_TEB", "lnZ_PTP", "lnZ_PEB", "lnZ_STP", "lnZ_SEB", "lnZ_DTP",
-           "lnZ_DEB", "lnZ_BTP", "lnZ_BEB"]
+           "lnZ_DEB", "lnZ_BTP", "lnZ_BEB",
+           "lnZ_NTP_unknown", "lnZ_NEB_unknown", "lnZ_NTP_evolved", "lnZ_NEB_evolved"]
 
 
 # ------------------------------------------------------------------------------ shared pieces
@@ -512,3 +513,125 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     return _run_eb(N, host_masses, host_radii, u1s_comp[idxs], u2s_comp[idxs], P,
                    host_masses + masses, incs, qs, eccs, argps, masses, radii, fluxratios, cfr,
                    lnprior, extra, True)
+
+
+# ------------------------------------------------- nearby stars of unknown / evolved nature
+# The reference defines these four but never calls them (marginal_likelihoods.py:2365-3178);
+# they reuse the same two kernels.
+
+
+class _PossibleHosts:
+    """TRILEGAL stars within one magnitude of a nearby star of unknown properties (:2402-2415)."""
+
+    def __init__(self, trilegal_fname, Tmag, mission):
+        (Tmags, masses, loggs, Teffs, Zs, _, _, _) = trilegal_results(trilegal_fname, Tmag)
+        near = (Tmag - 1 < Tmags) & (Tmags < Tmag + 1)
+        self.masses, self.loggs, self.Teffs, self.Zs = (masses[near], loggs[near], Teffs[near],
+                                                        Zs[near])
+        self.radii = np.sqrt(G * self.masses * Msun / 10 ** self.loggs) / Rsun
+        self.n = int(near.sum())
+        self.u1s, self.u2s = grid_for(mission).nearest_each(self.Teffs, self.loggs, self.Zs)
+
+
+_EMPTY_KEYS = ('M_s', 'R_s', 'u1', 'u2', 'P_orb', 'inc', 'b', 'R_p', 'ecc', 'argp', 'M_EB',
+               'R_EB', 'fluxratio_EB', 'fluxratio_comp')
+
+
+def _no_hosts(with_b):
+    # what the reference returns when no TRILEGAL star is similar enough (:2438-2454, :2648-2665)
+    res = {k: 0 for k in _EMPTY_KEYS if with_b or k != 'b'}
+    res['lnZ'] = -np.inf
+    return res
+
+
+def lnZ_NTP_unknown(time: np.ndarray, flux: np.ndarray, sigma: float,
+                    P_orb: float, Tmag: float, trilegal_fname: str,
+                    N: int = 1000000, parallel: bool = False,
+                    mission: str = "TESS", flatpriors: bool = False,
+                    exptime: float = 0.00139, nsamples: int = 20):
+    """Planet on a nearby star of unknown properties, host drawn from the TRILEGAL stars of
+    similar brightness (marginal_likelihoods.py:2365-2551)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    hosts = _PossibleHosts(trilegal_fname, Tmag, mission)
+    if hosts.n == 0:
+        return _no_hosts(with_b=False)
+    idxs = np.random.randint(0, hosts.n, N)
+    host_masses = hosts.masses[idxs]
+    rps, incs, eccs, argps = _draw_planet(N, host_masses, flatpriors, P_mean)
+    extra = (hosts.loggs[idxs] >= 3.5) & (hosts.Teffs[idxs] <= 10000)
+    return _run_tp(N, host_masses, hosts.radii[idxs], hosts.u1s[idxs], hosts.u2s[idxs], P,
+                   host_masses, rps, incs, eccs, argps, 0.0, None, extra, False)
+
+
+def lnZ_NEB_unknown(time: np.ndarray, flux: np.ndarray, sigma: float,
+                    P_orb: float, Tmag: float, trilegal_fname: str,
+                    N: int = 1000000, parallel: bool = False,
+                    mission: str = "TESS", flatpriors: bool = False,
+                    exptime: float = 0.00139, nsamples: int = 20):
+    """EB on a nearby star of unknown properties (marginal_likelihoods.py:2554-2829)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    incs, qs, eccs, argps = _draw_binary(N, 1.0, P_mean)       # sample_q with M_s = 1.0, :2593
+    hosts = _PossibleHosts(trilegal_fname, Tmag, mission)
+    if hosts.n == 0:
+        return _no_hosts(with_b=True)                           # a single dict, as :2665
+    idxs = np.random.randint(0, hosts.n, N)
+    host_masses, host_radii = hosts.masses[idxs], hosts.radii[idxs]
+    masses = qs * host_masses
+    radii, _ = stellar_relations(masses, host_radii, hosts.Teffs[idxs])
+    f = flux_relation(masses)
+    fluxratios = f / (f + flux_relation(host_masses))
+    extra = (hosts.loggs[idxs] >= 3.5) & (hosts.Teffs[idxs] <= 10000)
+    return _run_eb(N, host_masses, host_radii, hosts.u1s[idxs], hosts.u2s[idxs], P,
+                   host_masses + masses, incs, qs, eccs, argps, masses, radii, fluxratios, 0.0,
+                   None, extra, False)
+
+
+def _subgiant_mass(R_s):
+    # M_s = (10**logg)*(R_s*Rsun)**2 / G / Msun with logg = 3.0     (:2877-2878)
+    logg = 3.0
+    return logg, (10 ** logg) * (R_s * Rsun) ** 2 / G / Msun
+
+
+def lnZ_NTP_evolved(time: np.ndarray, flux: np.ndarray, sigma: float,
+                    P_orb: float, R_s: float, Teff: float, Z: float,
+                    N: int = 1000000, parallel: bool = False,
+                    mission: str = "TESS", flatpriors: bool = False,
+                    exptime: float = 0.00139, nsamples: int = 20):
+    """Planet on a nearby subgiant (logg = 3) of radius R_s (marginal_likelihoods.py:2832-2966)."""
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    logg, M_s = _subgiant_mass(R_s)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, logg)
+    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
+    return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, 0.0, None, None, False)
+
+
+def lnZ_NEB_evolved(time: np.ndarray, flux: np.ndarray, sigma: float,
+                    P_orb: float, R_s: float, Teff: float, Z: float,
+                    N: int = 1000000, parallel: bool = False,
+                    mission: str = "TESS", flatpriors: bool = False,
+                    exptime: float = 0.00139, nsamples: int = 20):
+    """EB on a nearby subgiant (marginal_likelihoods.py:2969-3178).
+
+    Reference quirk kept: the q >= 0.95 branch models a twin of radius R_s (it passes the scalar
+    R_s as R_EB, :3100, and uses 2 R_s in Ptra_twin, :3052) while reporting R_EB = R_s; the two
+    branches therefore see different companion radii and are evaluated in two engine calls.
+    """
+    N = int(N)
+    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    P, P_mean = _periods(P_orb, N)
+    logg, M_s = _subgiant_mass(R_s)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, logg)
+    incs, qs, eccs, argps = _draw_binary(N, 1.0, P_mean)
+    masses = qs * M_s
+    radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
+    fluxratios = _fluxratio(masses, M_s)
+    common = (N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses)
+    res, _ = _run_eb(*common, radii, fluxratios, 0.0, None, None, False)
+    _, res_twin = _run_eb(*common, np.full(N, float(R_s)), fluxratios, 0.0, None, None, False)
+    return res, res_twin
