@@ -92,11 +92,8 @@ class _Recorder:
         return self._dummy(N), self._dummy(N)
 
 
-def build_workload(N, seed):
-    """Run calc_probs' host side once (prior draws, stellar relations, priors) and record the
-    12 engine calls of the 18-row configuration."""
+def make_target():
     from oracle import synth
-    from triceratops_b200 import _dispatch
     from triceratops_b200.triceratops import target
     lc = np.loadtxt(os.path.join(GOLD, "TOI465_01_lightcurve.csv"), delimiter=",")
     t, f, s = lc[:, 0].copy(), lc[:, 1].copy(), float(np.mean(lc[:, 2]))
@@ -104,6 +101,27 @@ def build_workload(N, seed):
                               TOI465["M"], TOI465["R"], TOI465["Teff"], TOI465["plx"])
     tgt = target(TOI465["ID"], stars=stars,
                  trilegal_fname=os.path.join(GOLD, "trilegal_synth.csv"))
+    return tgt, t, f, s, lc
+
+
+def calc_probs_wall(N, seed):
+    """The user-facing call, untimed extras: one full target.calc_probs on the real engine
+    (host prior draws + 12 engine calls + best-draw tables).  Under torchrun the draws of each
+    scenario are sharded over the ranks by the package itself."""
+    tgt, t, f, s, _ = make_target()
+    np.random.seed(seed)
+    t0 = time.perf_counter()
+    tgt.calc_probs(t, f, s, TOI465["P"],
+                   contrast_curve_file=os.path.join(GOLD, "TOI465_01_contrastcurve.csv"),
+                   filt="K", N=N, parallel=True, verbose=0)
+    return time.perf_counter() - t0, float(tgt.FPP), float(tgt.NFPP)
+
+
+def build_workload(N, seed):
+    """Run calc_probs' host side once (prior draws, stellar relations, priors) and record the
+    12 engine calls of the 18-row configuration."""
+    from triceratops_b200 import _dispatch
+    tgt, t, f, s, lc = make_target()
     rec = _Recorder()
     saved = _dispatch._engine_factory
     _dispatch._engine_factory = lambda: rec
@@ -389,6 +407,12 @@ def run_ours(args):
         "host_prior_draws_s": host_prep_s,
         "lnZ_check": [float(x) for x in lnZ[:3]],
     }
+    # outside every timed region: the public call a user makes, end to end
+    wall, fpp, nfpp = calc_probs_wall(N, SEED)
+    out["calc_probs_call"] = {"wall_s": wall, "N_total": N, "FPP": fpp, "NFPP": nfpp,
+                              "note": "target.calc_probs incl. host prior draws (numpy RNG, "
+                                      "sequential by construction); draws sharded over %d "
+                                      "rank(s)" % world}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_leg(calls, npts, 4 * args.cpu_draws, steps=1, warmup=0)
     if rank == 0:

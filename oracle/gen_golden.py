@@ -31,7 +31,8 @@ from oracle import quadmodel, refhost, synth  # noqa: E402
 
 TOI465 = dict(P=3.836169, M=0.811, R=0.84738, Teff=4936.0, plx=8.16366,
               T=10.7307, J=9.906, H=9.473, K=9.339)
-KEP10 = dict(P=0.837, M=1.017, R=1.08974, Teff=5706.0, plx=5.36185)
+KEP10 = dict(P=0.837, M=1.017, R=1.08974, Teff=5706.0, plx=5.36185,
+             T=10.4, J=9.889, H=9.563, K=9.496)
 N_LNZ = 3000
 SEED = 11
 
@@ -94,6 +95,19 @@ def gen_nearby(ref, tri):
     print("lnz_nearby.npz", [(k, float(v)) for k, v in out.items() if k.endswith("lnZ")])
 
 
+def gen_kepler(ref, tri):
+    """Config 3: Kepler-10b, 29.4-min exposures (exptime 0.0204 d, 20 sub-exposures),
+    mission="Kepler" limb darkening, every scenario."""
+    cc = os.path.join(GOLD, "TOI465_01_contrastcurve.csv")
+    lc = load_lc("Kepler10b_lightcurve.csv")
+    out = {"N": np.array(N_LNZ), "seed": np.array(SEED)}
+    for name, fn in lnz_calls(KEP10, N_LNZ, tri, cc, lc, mission="Kepler", exptime=0.0204).items():
+        np.random.seed(SEED)
+        flatten(name, fn(ref.ml), out)
+        print("  lnZ kepler", name, [float(out[k]) for k in out if k.endswith("lnZ") and k.startswith(name + "/")])
+    np.savez_compressed(os.path.join(GOLD, "lnz_kepler10b.npz"), **out)
+
+
 def flatten(prefix, res, out):
     rs = res if isinstance(res, tuple) else (res,)
     for b, r in enumerate(rs):
@@ -127,6 +141,9 @@ def main():
     tri = os.path.join(GOLD, "trilegal_synth.csv")
     if len(sys.argv) > 1 and sys.argv[1] == "nearby":
         gen_nearby(ref, tri)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "kepler":
+        gen_kepler(ref, tri)
         return
     synth.trilegal_table(tri, n=2500)
     gen_nearby(ref, tri)
@@ -200,13 +217,7 @@ def main():
         flatten(name, fn(ref.ml), out)
         print("  lnZ", name, [float(out[k]) for k in out if k.startswith(name + "/") and k.endswith("lnZ")])
     np.savez_compressed(os.path.join(GOLD, "lnz_toi465.npz"), **out)
-    lc = load_lc("Kepler10b_lightcurve.csv")
-    out = {"N": np.array(N_LNZ), "seed": np.array(SEED)}
-    for name, fn in lnz_calls(KEP10, N_LNZ, None, None, lc, mission="Kepler", exptime=0.0204).items():
-        np.random.seed(SEED)
-        flatten(name, fn(ref.ml), out)
-        print("  lnZ kepler", name, [float(out[k]) for k in out if k.endswith("lnZ") and k.startswith(name)])
-    np.savez_compressed(os.path.join(GOLD, "lnz_kepler10b.npz"), **out)
+    gen_kepler(ref, tri)
 
     # ---- calc_probs -----------------------------------------------------------------------------
     t, f, s = load_lc("TOI465_01_lightcurve.csv")

@@ -17,7 +17,8 @@ def pytest_configure(config):
 
 TOI465 = dict(P=3.836169, M=0.811, R=0.84738, Teff=4936.0, plx=8.16366,
               T=10.7307, J=9.906, H=9.473, K=9.339)
-KEP10 = dict(P=0.837, M=1.017, R=1.08974, Teff=5706.0, plx=5.36185)
+KEP10 = dict(P=0.837, M=1.017, R=1.08974, Teff=5706.0, plx=5.36185,
+             T=10.4, J=9.889, H=9.563, K=9.496)
 
 
 def load_lc(name):

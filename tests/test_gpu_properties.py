@@ -86,3 +86,73 @@ def test_light_curve_order_does_not_matter(big, gpu_engine, toi465_lc):
     gpu_engine.set_lightcurve(t, f, s, 0.00139, 20)
     fin = np.isfinite(r.lnL)
     np.testing.assert_allclose(r.lnL[fin], whole.lnL[:50000][fin], rtol=1e-13)
+
+
+# ---------------------------------------------------------------- BASELINE config 4 shapes
+def _config4_lightcurve():
+    """20 000 two-minute stamps on [-0.5, 0.5] d, P = 10 d, injected
+    k = 0.05, a/R* = 15, b = 0.3 transit + N(0, 1e-3) noise."""
+    from oracle import coracle
+    t = np.linspace(-0.5, 0.5, 20000)
+    truth = coracle.model(t, 0.05, 10.0, 15.0, np.arccos(0.3 / 15.0), 0.0, np.pi / 2, 0.4, 0.2,
+                          0.00139, 20)
+    return t, truth + np.random.default_rng(1234).normal(0, 1e-3, t.size), 1e-3
+
+
+def test_config4_long_light_curve_against_oracle(gpu_engine):
+    """20 000-stamp light curve (no shared-memory staging, 15 % of stamps inside windows):
+    fused TP and EB kernels against the oracle port on 3000 draws."""
+    import _oracle_engine
+    t, f, s = _config4_lightcurve()
+    gpu_engine.set_lightcurve(t, f, s, 0.00139, 20)
+    ora = _oracle_engine.OracleEngine()
+    ora.set_lightcurve(t, f, s, 0.00139, 20)
+    N = 3000
+    rng = np.random.default_rng(2)
+    inc = np.degrees(np.arccos(rng.random(N) * 0.12))
+    ecc, argp = rng.beta(0.867, 3.03, N), rng.uniform(0, 360, N)
+    a = (N, rng.uniform(0.5, 20, N), 10.0, inc, ecc, argp, 1.0, 1.0, 0.4, 0.2, 0.0)
+    g, o = gpu_engine.eval_tp(*a, want_mask=True), ora.eval_tp(*a)
+    assert np.array_equal(g.mask, o.mask) and g.n_pass > 300
+    fin = np.isfinite(o.lnL)
+    np.testing.assert_allclose(g.lnL[fin], o.lnL[fin], rtol=1e-9)
+    assert abs(g.lnZ - o.lnZ) < 1e-6
+    assert g.n_stamps < 0.5 * g.n_pass * t.size          # the windows really skip stamps
+    q = rng.uniform(0.1, 1.0, N)
+    a = (N, 0.1 + 0.9 * q, 0.3 * q ** 3 + 1e-4, q, 10.0, inc, ecc, argp, 1.0 + q, 1.0, 0.4, 0.2,
+         0.0)
+    for gg, oo in zip(gpu_engine.eval_eb(*a, want_mask=True), ora.eval_eb(*a)):
+        assert np.array_equal(gg.mask, oo.mask)
+        fin = np.isfinite(oo.lnL)
+        assert np.array_equal(np.isfinite(gg.lnL), fin)
+        np.testing.assert_allclose(gg.lnL[fin], oo.lnL[fin], rtol=1e-9)
+
+
+def test_ten_million_draws_equal_ten_shards(gpu_engine, toi465_lc):
+    """N = 1e7 (the north-star draw count) in one call versus ten 1e6 shards merged with the
+    (max, scaled-sum) combine; per-draw results must not depend on the sharding."""
+    t, f, s = toi465_lc
+    gpu_engine.set_lightcurve(t, f, s, 0.00139, 20)
+    n = 10_000_000
+    rng = np.random.default_rng(3)
+    rp = rng.uniform(0.5, 20, n)
+    inc = np.degrees(np.arccos(rng.random(n)))
+    ecc = rng.beta(0.867, 3.03, n)
+    argp = rng.uniform(0, 360, n)
+    tail = (TOI465["M"], TOI465["R"], 0.4338, 0.2008, 0.0)
+    whole = gpu_engine.eval_tp(n, rp, TOI465["P"], inc, ecc, argp, *tail, want_lnL=False,
+                               n_best=100)
+    assert 0.08 * n < whole.n_pass < 0.14 * n
+    parts, best = [], []
+    for r in range(10):
+        sl = slice(r * 1_000_000, (r + 1) * 1_000_000)
+        res = gpu_engine.eval_tp(1_000_000, rp[sl], TOI465["P"], inc[sl], ecc[sl], argp[sl],
+                                 *tail, want_lnL=False, n_best=100)
+        parts.append((res.m, res.s, res.n_finite, res.n_posinf))
+        best.append((res.top_lnL, res.top_idx + sl.start))
+    assert abs(combine_lse(parts, n) - whole.lnZ) < 1e-9
+    vals = np.concatenate([b[0] for b in best])
+    idx = np.concatenate([b[1] for b in best])
+    order = np.lexsort((idx, -vals))[:100]
+    assert np.array_equal(idx[order], whole.top_idx)
+    assert np.array_equal(vals[order], whole.top_lnL)

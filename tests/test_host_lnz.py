@@ -22,11 +22,12 @@ def test_lnz_functions_reproduce_reference(name, oracle_engine, golden, toi465_l
     check_against_golden(name, calls[name](ml), g, lnz_atol=1e-9, arr_rtol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["TTP", "TEB"])
-def test_kepler_long_cadence(name, oracle_engine, golden, kepler10b_lc):
+@pytest.mark.parametrize("name", NAMES)
+def test_kepler_long_cadence(name, oracle_engine, golden, kepler10b_lc, trilegal_file, contrast_file):
+    """BASELINE config 3: Kepler-10b, 30-min exposure supersampling, every scenario."""
     g = golden("lnz_kepler10b.npz")
-    calls = lnz_calls(KEP10, int(g["N"]), None, None, kepler10b_lc, mission="Kepler",
-                      exptime=0.0204)
+    calls = lnz_calls(KEP10, int(g["N"]), trilegal_file, contrast_file, kepler10b_lc,
+                      mission="Kepler", exptime=0.0204)
     np.random.seed(int(g["seed"]))
     check_against_golden(name, calls[name](ml), g, lnz_atol=1e-9, arr_rtol=1e-12)
 
