@@ -381,7 +381,9 @@ def run_ours(args):
                  "points_reference_evaluates": pts_all},
         "param_stream_GBs": param_bytes / (ms_total * 1e-3) / 1e9,
         "hbm_peak_GBs": _measured_peaks().get("hbm_gbs"),
-        "traffic": None,
+        "traffic": _profiled_traffic(),
+        "traffic_source": "profiles/r01_traffic.json (dram bytes read+write per launch, one ncu "
+                          "--set full capture at N = 1e6)",
     }
 
     value = units_per_step * world * args.steps / (ms_total * 1e-3)
@@ -419,6 +421,14 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _profiled_traffic():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[
+            "traffic_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def _measured_peaks():
