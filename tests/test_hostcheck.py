@@ -59,7 +59,7 @@ def test_occultation_and_separation_match_oracle(hc, golden):
     np.testing.assert_allclose(got[contact], g["flux"][contact], rtol=0, atol=5e-13)
     zz = np.array([hc.hc_z(*x) for x in zip(g["t"], g["p"], g["a"], g["inc"], g["e"], g["w"])])
     # the cancellation in 1 - sin^2(w+f) sin^2 i amplifies rounding by (a/R*)^2 / z
-    tol = 4e-16 * g["a"] ** 2 / np.maximum(np.abs(g["zsep"]), 1e-3) + 1e-14
+    tol = 1e-15 * g["a"] ** 2 / np.maximum(np.abs(g["zsep"]), 1e-3) + 1e-14
     assert np.all(np.abs(zz - g["zsep"]) <= tol * np.maximum(1.0, np.abs(g["zsep"])))
 
 

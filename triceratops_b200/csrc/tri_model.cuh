@@ -79,6 +79,122 @@ TRI_HD double fast_sqrt(double x) {
 #endif
 }
 
+// ---- polynomial tables in constant memory ------------------------------------------------------
+// Literal double constants cost two uniform-register moves each on sm_100a; adjacent entries of
+// a __constant__ table are fetched two at a time (LDCU.128).  The hot loop evaluates ~50
+// coefficients per model point, so the tables below (and hand-written sincos / log kernels
+// that use them instead of the CUDA library routines' embedded literals) remove ~10 % of the
+// issued instructions.  On the host (tests/hostcheck) the same tables are plain arrays.
+#define TRI_TABLE(name, n, ...)                                  \
+    static const double name##_host[n] = {__VA_ARGS__};           \
+    TRI_DEVICE_TABLE(name, n, __VA_ARGS__)
+#if defined(__CUDACC__)
+#define TRI_DEVICE_TABLE(name, n, ...) __constant__ double name##_dev[n] = {__VA_ARGS__};
+#else
+#define TRI_DEVICE_TABLE(name, n, ...)
+#endif
+#if defined(__CUDA_ARCH__)
+#define TRI_T(name) name##_dev
+#else
+#define TRI_T(name) name##_host
+#endif
+
+// sin/cos on [-pi/4, pi/4] (fdlibm __kernel_sin / __kernel_cos minimax coefficients) and the
+// two-term Cody-Waite split of pi/2
+TRI_TABLE(kTrig, 16,
+          6.36619772367581382433e-01,   /* 0  2/pi      */
+          1.57079632679489655800e+00,   /* 1  pi/2 high */
+          6.12323399573676603587e-17,   /* 2  pi/2 low  */
+          -1.66666666666666324348e-01,  /* 3  S1 */
+          8.33333333332248946124e-03,   /* 4  S2 */
+          -1.98412698298579493134e-04,  /* 5  S3 */
+          2.75573137070700676789e-06,   /* 6  S4 */
+          -2.50507602534068634195e-08,  /* 7  S5 */
+          1.58969099521155010221e-10,   /* 8  S6 */
+          4.16666666666666019037e-02,   /* 9  C1 */
+          -1.38888888888741095749e-03,  /* 10 C2 */
+          2.48015872894767294178e-05,   /* 11 C3 */
+          -2.75573143513906633035e-07,  /* 12 C4 */
+          2.08757232129817482790e-09,   /* 13 C5 */
+          -1.13596475577881948265e-11,  /* 14 C6 */
+          0.0)
+
+// log(x) = k ln2 + log(1+f), fdlibm __ieee754_log coefficients
+TRI_TABLE(kLog, 10,
+          6.93147180369123816490e-01,   /* 0 ln2 high */
+          1.90821492927058770002e-10,   /* 1 ln2 low  */
+          6.666666666666735130e-01,     /* 2 Lg1 */
+          3.999999999940941908e-01,     /* 3 Lg2 */
+          2.857142874366239149e-01,     /* 4 Lg3 */
+          2.222219843214978396e-01,     /* 5 Lg4 */
+          1.818357216161805012e-01,     /* 6 Lg5 */
+          1.531383769920937332e-01,     /* 7 Lg6 */
+          1.479819860511658591e-01,     /* 8 Lg7 */
+          0.0)
+
+// Hastings K / E polynomials (A&S 17.3.34, 17.3.36): K = (a0..a4)(m1) - (b0..b4)(m1) ln m1,
+// E = 1 + (c1..c4)(m1) - (d1..d4)(m1) ln m1
+TRI_TABLE(kEll, 18,
+          1.38629436112, 0.09666344259, 0.03590092383, 0.03742563713, 0.01451196212,
+          0.5, 0.12498593597, 0.06880248576, 0.03328355346, 0.00441787012,
+          0.44325141463, 0.0626060122, 0.04757383546, 0.01736506451,
+          0.2499836831, 0.09200180037, 0.04069697526, 0.00526449639)
+
+// sin and cos of an angle of a few radians at most (true anomalies): quadrant reduction with a
+// two-term pi/2, then the two polynomials; ~1 ulp, no huge-argument path (|x| < 1e5 assumed).
+TRI_HD void sincos_small(double x, double& s, double& c) {
+    const double* T = TRI_T(kTrig);
+    double q = rint(x * T[0]);
+    double r = fma(-q, T[1], x);
+    r = fma(-q, T[2], r);
+    double z = r * r;
+    double sp = T[4] + z * (T[5] + z * (T[6] + z * (T[7] + z * T[8])));
+    sp = fma(r * z, fma(z, sp, T[3]), r);                    // r + r^3 (S1 + z (...))
+    double cp = T[9] + z * (T[10] + z * (T[11] + z * (T[12] + z * (T[13] + z * T[14]))));
+    cp = fma(z * z, cp, fma(-0.5, z, 1.0));                  // 1 - z/2 + z^2 (C1 + ...)
+    int n = (int)q;
+    double ss = (n & 1) ? cp : sp;
+    double cc = (n & 1) ? sp : cp;
+    s = (n & 2) ? -ss : ss;
+    c = ((n + 1) & 2) ? -cc : cc;
+}
+
+// natural logarithm of a normal positive double (0 -> -inf, negative / NaN -> NaN)
+TRI_HD double log_pos(double x) {
+    if (!(x > 0.0)) return x == 0.0 ? -INFINITY : NAN;
+    const double* T = TRI_T(kLog);
+#if defined(__CUDA_ARCH__)
+    int hx = __double2hiint(x);
+    int lx = __double2loint(x);
+#else
+    union { double d; unsigned long long u; } cv;
+    cv.d = x;
+    int hx = (int)(cv.u >> 32);
+    int lx = (int)(cv.u & 0xffffffffu);
+#endif
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    int i = (hx + 0x95f64) & 0x100000;        // mantissa above sqrt(2): halve it, bump k
+    hx |= (i ^ 0x3ff00000);
+    k += (i >> 20);
+#if defined(__CUDA_ARCH__)
+    double m = __hiloint2double(hx, lx);
+#else
+    cv.u = ((unsigned long long)(unsigned)hx << 32) | (unsigned)lx;
+    double m = cv.d;
+#endif
+    double f = m - 1.0;
+    double sq = f * fast_rcp(2.0 + f);
+    double dk = (double)k;
+    double z = sq * sq;
+    double w = z * z;
+    double t1 = w * (T[3] + w * (T[5] + w * T[7]));
+    double t2 = z * (T[2] + w * (T[4] + w * (T[6] + w * T[8])));
+    double R = t2 + t1;
+    double hfsq = 0.5 * f * f;
+    return dk * T[0] - ((hfsq - (sq * (hfsq + R) + dk * T[1])) - f);
+}
+
 constexpr int kTableNe = 256;
 constexpr int kTableNm = 512;
 constexpr double kTableMaxE = 0.95;
@@ -179,7 +295,7 @@ TRI_HD double mean_anomaly(const Orbit& o, double t) {
 
 TRI_HD double z_from_ta(const Orbit& o, double ta) {
     double st, ct;
-    sincos(ta, &st, &ct);
+    sincos_small(ta, st, ct);
     double swt = o.sinw * ct + o.cosw * st;  // sin(w + f)
     double z = o.a1me2 * fast_rcp(1.0 + o.e * ct) * fast_sqrt(1.0 - swt * swt * o.sini2);
     return swt < 0.0 ? -z : z;
@@ -193,15 +309,12 @@ TRI_HD double z_at(const Orbit& o, const OrbitTable& T, double t) {
 // K and E from the complementary parameter m1 = 1 - q^2; they share its logarithm
 // (Hastings, A&S 17.3.34 / 17.3.36).
 TRI_HD void ellke_m1(double m1, double& Kk, double& Ek) {
-    double lg = log(m1);
-    double ek1 = 1.38629436112 + m1 * (0.09666344259 + m1 * (0.03590092383
-               + m1 * (0.03742563713 + m1 * 0.01451196212)));
-    double ek2 = 0.5 + m1 * (0.12498593597 + m1 * (0.06880248576
-               + m1 * (0.03328355346 + m1 * 0.00441787012)));
-    double ee1 = 1.0 + m1 * (0.44325141463 + m1 * (0.0626060122
-               + m1 * (0.04757383546 + m1 * 0.01736506451)));
-    double ee2 = m1 * (0.2499836831 + m1 * (0.09200180037 + m1 * (0.04069697526
-               + m1 * 0.00526449639)));
+    const double* T = TRI_T(kEll);
+    double lg = log_pos(m1);
+    double ek1 = T[0] + m1 * (T[1] + m1 * (T[2] + m1 * (T[3] + m1 * T[4])));
+    double ek2 = T[5] + m1 * (T[6] + m1 * (T[7] + m1 * (T[8] + m1 * T[9])));
+    double ee1 = 1.0 + m1 * (T[10] + m1 * (T[11] + m1 * (T[12] + m1 * T[13])));
+    double ee2 = m1 * (T[14] + m1 * (T[15] + m1 * (T[16] + m1 * T[17])));
     Kk = ek1 - ek2 * lg;
     Ek = ee1 - ee2 * lg;
 }
@@ -376,7 +489,7 @@ struct Window {
 
 TRI_HD bool in_arc(const Orbit& o, double ta, double cmax) {
     double st, ct;
-    sincos(ta, &st, &ct);
+    sincos_small(ta, st, ct);
     double swt = o.sinw * ct + o.cosw * st;
     double cwt = o.cosw * ct - o.sinw * st;
     return swt > 0.0 && fabs(cwt) <= cmax;
