@@ -163,6 +163,11 @@ TRI_HD void sincos_small(double x, double& s, double& c) {
 TRI_HD double log_pos(double x) {
     if (!(x > 0.0)) return x == 0.0 ? -INFINITY : NAN;
     const double* T = TRI_T(kLog);
+    int k0 = 0;
+    if (x < 2.2250738585072014e-308) {   // subnormal: rescale by 2^54
+        x *= 18014398509481984.0;
+        k0 = -54;
+    }
 #if defined(__CUDA_ARCH__)
     int hx = __double2hiint(x);
     int lx = __double2loint(x);
@@ -172,7 +177,7 @@ TRI_HD double log_pos(double x) {
     int hx = (int)(cv.u >> 32);
     int lx = (int)(cv.u & 0xffffffffu);
 #endif
-    int k = (hx >> 20) - 1023;
+    int k = (hx >> 20) - 1023 + k0;
     hx &= 0x000fffff;
     int i = (hx + 0x95f64) & 0x100000;        // mantissa above sqrt(2): halve it, bump k
     hx |= (i ^ 0x3ff00000);
