@@ -125,6 +125,23 @@ int tri_lnl_eb(int64_t n, const double* R_EB, const double* EB_fluxratio, const 
                const double* companion_fluxratio, int32_t companion_is_host, int32_t twin,
                double* out);
 
+/* Model light curves on the time stamps of the current light curve (whose flux and sigma are
+ * then irrelevant): simulate_TP_transit_p (likelihoods.py:302-358) and simulate_EB_transit_p
+ * (:361-439).  flux_out is [n][npts] row-major in the caller's stamp order, after dilution;
+ * secdepth_out (optional) is [n].  scalar_rule = 1 applies the radius-ratio rules of the scalar
+ * simulate_EB_transit (:121-123, :137: |k-1| < 1e-6 and secondary k = 1/k) instead of the
+ * vectorised ones (:406, :417-418).  Meant for handfuls of draws (best-fit curves, plot_fits):
+ * n * npts is limited to 2^28. */
+int tri_simulate_tp(int64_t n, const double* R_p, const double* P_orb, const double* inc,
+                    const double* a, const double* R_s, const double* u1, const double* u2,
+                    const double* ecc, const double* argp, const double* companion_fluxratio,
+                    int32_t companion_is_host, double* flux_out);
+int tri_simulate_eb(int64_t n, const double* R_EB, const double* EB_fluxratio,
+                    const double* P_orb, const double* inc, const double* a, const double* R_s,
+                    const double* u1, const double* u2, const double* ecc, const double* argp,
+                    const double* companion_fluxratio, int32_t companion_is_host,
+                    int32_t scalar_rule, double* flux_out, double* secdepth_out);
+
 /* Per-draw lnL of branch 0/1 of the most recent tri_eval_* call, copied to a host buffer of N
  * doubles (the array stays on the device until the next call). */
 int tri_fetch_lnl(int32_t branch, double* out, int64_t N);

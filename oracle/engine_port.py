@@ -110,6 +110,62 @@ class OracleEngine:
             out.append(_lse_record(lnL if lnprior is None else lnL + _full(lnprior, N), N, res))
         return tuple(out)
 
+    # ---- simulate seam (likelihoods.py:302-439 and the scalar :27-160), via the C model ----
+    def _rows(self, npts, k, P, a_cm, R_s, inc, ecc, w_deg, u1, u2, exptime, ns):
+        t = self.lc[0]
+        out = np.empty((len(k), npts))
+        for i in range(len(k)):
+            out[i] = coracle.model(t, k[i], P[i], a_cm[i] / (R_s[i] * Rsun), inc[i] * (pi / 180.),
+                                   ecc[i], w_deg[i] * (pi / 180.), u1[i], u2[i], exptime, ns)
+        return out
+
+    def simulate_tp(self, npts, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
+                    companion_is_host):
+        _, _, _, exptime, ns = self.lc
+        n = np.size(R_p)
+        R_p, P, inc, a, R_s, u1, u2, ecc, argp, cfr = [
+            _full(x, n) for x in (R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr)]
+        flux = self._rows(npts, R_p * Rearth / (R_s * Rsun), P, a, R_s, inc, ecc, 90 - argp, u1,
+                          u2, exptime, ns)
+        F_comp = (cfr / (1 - cfr)).reshape(-1, 1)
+        D = 1 / F_comp if companion_is_host else F_comp / 1
+        return (flux + D) / (1 + D)
+
+    def simulate_eb(self, npts, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
+                    companion_is_host, scalar_rule=False):
+        _, _, _, exptime, ns = self.lc
+        n = np.size(R_EB)
+        R_EB, fr, P, inc, a, R_s, u1, u2, ecc, argp, cfr = [
+            _full(x, n) for x in (R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr)]
+        k = R_EB / R_s
+        if scalar_rule:
+            k[np.abs(k - 1.0) < 1e-6] *= 0.999
+            ks = 1 / k
+        else:
+            k[(k - 1.0) < 1e-6] *= 0.999
+            ks = R_s / R_EB
+            ks[(ks - 1.0) < 1e-6] *= 0.999
+        flux = self._rows(npts, k, P, a, R_s, inc, ecc, 90 - argp, u1, u2, exptime, ns)
+        tsec = np.linspace(-0.05, 0.05, 25)
+        sec = np.empty(n)
+        for i in range(n):
+            sec[i] = coracle.model(tsec, ks[i], P[i], a[i] / (R_s[i] * Rsun), inc[i] * (pi / 180.),
+                                   ecc[i], (90 - argp[i] + 180) * (pi / 180.), u1[i], u2[i],
+                                   0.0, 1).min()
+        F_comp = (cfr / (1 - cfr)).reshape(-1, 1)
+        F_EB = (fr / (1 - fr)).reshape(-1, 1)
+        sec = sec.reshape(-1, 1)
+        if companion_is_host:
+            flux = (flux + F_EB / F_comp) / (1 + F_EB / F_comp)
+            sec = (sec + F_comp / F_EB) / (1 + F_comp / F_EB)
+            D = 1 / (F_comp + F_EB)
+        else:
+            flux = (flux + F_EB / 1) / (1 + F_EB / 1)
+            sec = (sec + 1 / F_EB) / (1 + 1 / F_EB)
+            D = F_comp / (1 + F_EB)
+        flux = (flux + D) / (1 + D)
+        return flux, (1 - (sec + D) / (1 + D))[:, 0]
+
     def lnl_tp(self, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr, companion_is_host):
         t, f, s, exptime, ns = self.lc
         return coracle.lnL_TP_p(t, f, s, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,

@@ -13,6 +13,7 @@ Fixtures (all seeds via np.random.seed, as the reference uses numpy's global RNG
   lnz_kepler10b.npz lnZ_TTP / lnZ_TEB with 30-min exposure supersampling, mission="Kepler"
   lnz_nearby.npz    lnZ_NTP_unknown / NEB_unknown / NTP_evolved / NEB_evolved (defined by the
                     reference, never called by it: marginal_likelihoods.py:2365-3178)
+  simulate.npz      simulate_TP/EB_transit_p and the scalar simulate_TP/EB_transit (likelihoods.py)
   calc_probs.npz    target.calc_probs (triceratops.py:673-1485) on the 18-row configuration
   model.npz         eval_quad / separation values of the restated model itself
 PARITY UNPINNED with respect to real pytransit (see oracle/quadmodel.py).
@@ -95,6 +96,40 @@ def gen_nearby(ref, tri):
     print("lnz_nearby.npz", [(k, float(v)) for k, v in out.items() if k.endswith("lnZ")])
 
 
+def gen_simulate(ref):
+    t, _, _ = load_lc("TOI465_01_lightcurve.csv")
+    t = np.ascontiguousarray(t[::6])
+    d = transiting_draws(np.random.default_rng(31), 12, TOI465)
+    d["R_EB"][:3] = d["R_s"][:3] * np.array([1.0, 1.0 + 5e-7, 1.3])   # the radius-ratio rules
+    out = dict(d)
+    out["time"] = t
+    c = lambda k: d[k].copy()  # noqa: E731
+    for host in (0, 1):
+        out["tp_p/%d" % host] = ref.lk.simulate_TP_transit_p(
+            t, c("R_p"), c("P_orb"), c("inc"), c("a"), c("R_s"), c("u1"), c("u2"), c("ecc"),
+            c("argp"), c("cfr"), bool(host), 0.00139, 20)
+        fl, sd = ref.lk.simulate_EB_transit_p(
+            t, c("R_EB"), c("EB_fluxratio"), c("P_orb"), c("inc"), c("a") * 1.2, c("R_s"),
+            c("u1"), c("u2"), c("ecc"), c("argp"), c("cfr"), bool(host), 0.00139, 20)
+        out["eb_p/%d" % host], out["eb_p_sec/%d" % host] = fl, sd
+        tp1, eb1, sd1 = [], [], []
+        for i in range(5):
+            tp1.append(ref.lk.simulate_TP_transit(
+                t, d["R_p"][i], d["P_orb"][i], d["inc"][i], d["a"][i], d["R_s"][i], d["u1"][i],
+                d["u2"][i], d["ecc"][i], d["argp"][i], d["cfr"][i], bool(host), 0.00139, 20))
+            f1, s1 = ref.lk.simulate_EB_transit(
+                t, d["R_EB"][i], d["EB_fluxratio"][i], d["P_orb"][i], d["inc"][i],
+                d["a"][i] * 1.2, d["R_s"][i], d["u1"][i], d["u2"][i], d["ecc"][i], d["argp"][i],
+                d["cfr"][i], bool(host), 0.00139, 20)
+            eb1.append(f1)
+            sd1.append(s1)
+        out["tp_s/%d" % host] = np.array(tp1)
+        out["eb_s/%d" % host] = np.array(eb1)
+        out["eb_s_sec/%d" % host] = np.array(sd1)
+    np.savez_compressed(os.path.join(GOLD, "simulate.npz"), **out)
+    print("simulate.npz")
+
+
 def gen_kepler(ref, tri):
     """Config 3: Kepler-10b, 29.4-min exposures (exptime 0.0204 d, 20 sub-exposures),
     mission="Kepler" limb darkening, every scenario."""
@@ -142,11 +177,15 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "nearby":
         gen_nearby(ref, tri)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "simulate":
+        gen_simulate(ref)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "kepler":
         gen_kepler(ref, tri)
         return
     synth.trilegal_table(tri, n=2500)
     gen_nearby(ref, tri)
+    gen_simulate(ref)
     cc = os.path.join(GOLD, "TOI465_01_contrastcurve.csv")
 
     # ---- samplers / priors / relations ------------------------------------------------------

@@ -54,6 +54,7 @@ class tri_result(ctypes.Structure):
 # every symbol include/triceratops_b200.h declares
 EXPORTS = ("tri_init", "tri_shutdown", "tri_last_error", "tri_set_lightcurve", "tri_eval_tp",
            "tri_eval_eb", "tri_eval_tp_dev", "tri_eval_eb_dev", "tri_lnl_tp", "tri_lnl_eb",
+           "tri_simulate_tp", "tri_simulate_eb",
            "tri_fetch_lnl", "tri_log_mean_exp", "tri_last_timing", "tri_fp64_peak", "tri_sm_count")
 
 _lib = None
@@ -90,6 +91,10 @@ def load():
     L.tri_lnl_tp.argtypes = [ctypes.c_int64] + [c_double_p] * 10 + [ctypes.c_int32, c_double_p]
     L.tri_lnl_eb.argtypes = ([ctypes.c_int64] + [c_double_p] * 11
                              + [ctypes.c_int32, ctypes.c_int32, c_double_p])
+    L.tri_simulate_tp.argtypes = [ctypes.c_int64] + [c_double_p] * 10 + [ctypes.c_int32,
+                                                                        c_double_p]
+    L.tri_simulate_eb.argtypes = ([ctypes.c_int64] + [c_double_p] * 11
+                                  + [ctypes.c_int32, ctypes.c_int32, c_double_p, c_double_p])
     L.tri_fetch_lnl.argtypes = [ctypes.c_int32, c_double_p, ctypes.c_int64]
     L.tri_log_mean_exp.argtypes = [c_double_p, ctypes.c_int64, ctypes.POINTER(tri_result)]
     L.tri_last_timing.argtypes = [c_double_p, c_double_p, c_double_p,

@@ -70,6 +70,7 @@ struct Ctx {
     // light curve
     bool have_lc = false;
     double *d_time = nullptr, *d_flux = nullptr, *d_prefix = nullptr;
+    int* d_perm = nullptr;   // sorted stamp -> caller's stamp
     size_t lc_cap = 0;
     LightCurve lc{};
     Arena scratch;   // kernel scratch (a, p, lnl, items, partials)
@@ -434,6 +435,7 @@ int tri_shutdown(void) {
     cudaFree(g.d_time);
     cudaFree(g.d_flux);
     cudaFree(g.d_prefix);
+    cudaFree(g.d_perm);
     cudaFree(g.d_counters);
     cudaFree(g.d_lse_out);
     cudaFreeHost(g.h_lse_out);
@@ -484,9 +486,11 @@ int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, dou
     CU(cudaSetDevice(g.device));
     CU(cudaStreamSynchronize(g.stream));
     if ((size_t)npts > g.lc_cap) {
-        cudaFree(g.d_time); cudaFree(g.d_flux); cudaFree(g.d_prefix);
+        cudaFree(g.d_time); cudaFree(g.d_flux); cudaFree(g.d_prefix); cudaFree(g.d_perm);
         g.d_time = g.d_flux = g.d_prefix = nullptr;
+        g.d_perm = nullptr;
         g.lc_cap = 0;
+        CU(cudaMalloc(&g.d_perm, npts * sizeof(int)));
         CU(cudaMalloc(&g.d_time, npts * sizeof(double)));
         CU(cudaMalloc(&g.d_flux, npts * sizeof(double)));
         CU(cudaMalloc(&g.d_prefix, (npts + 1) * sizeof(double)));
@@ -495,6 +499,11 @@ int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, dou
     CU(cudaMemcpy(g.d_time, t.data(), npts * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g.d_flux, f.data(), npts * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g.d_prefix, pre.data(), (npts + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        std::vector<int> perm(npts);
+        for (int64_t j = 0; j < npts; j++) perm[j] = (int)order[j];
+        CU(cudaMemcpy(g.d_perm, perm.data(), npts * sizeof(int), cudaMemcpyHostToDevice));
+    }
     g.lc.time = g.d_time; g.lc.flux = g.d_flux; g.lc.prefix = g.d_prefix;
     g.lc.npts = (int)npts; g.lc.nsamples = nsamples; g.lc.sigma = sigma; g.lc.exptime = exptime;
     g.lc.tmin = t.front(); g.lc.tmax = t.back();
@@ -678,18 +687,22 @@ int tri_eval_eb(const tri_eb_args* a, tri_result out[2]) {
 static int lnl_seam(int eb, int64_t n, const double* body, const double* ebfr, const double* P,
                     const double* inc, const double* a, const double* R_s, const double* u1,
                     const double* u2, const double* ecc, const double* argp, const double* cfr,
-                    int32_t is_host, int32_t twin, double* out) {
+                    int32_t is_host, int32_t twin, double* out, double* model_out = nullptr,
+                    double* secdepth_out = nullptr, int scalar_rule = 0) {
     int rc = need_ready(true);
     if (rc) return rc;
     if (n < 0) return fail(TRI_EINVAL, "n must be >= 0");
     if (n == 0) return TRI_OK;
-    if (!body || !P || !inc || !a || !R_s || !u1 || !u2 || !ecc || !argp || !cfr || !out ||
-        (eb && !ebfr))
+    if (!body || !P || !inc || !a || !R_s || !u1 || !u2 || !ecc || !argp || !cfr ||
+        (!out && !model_out) || (eb && !ebfr))
         return fail(TRI_EINVAL, "NULL array");
+    const size_t npts = (size_t)g.lc.npts;
+    if (model_out && (size_t)n * npts > ((size_t)1 << 28))
+        return fail(TRI_EINVAL, "model matrix too large (n * npts > 2^28): simulate fewer draws");
     CU(cudaSetDevice(g.device));
     cudaStream_t s = g.stream;
     g.staging.reset();
-    rc = g.staging.reserve((size_t)n * 8 * 13 + 8192);
+    rc = g.staging.reserve((size_t)n * 8 * 14 + 8192 + (model_out ? (size_t)n * npts * 8 : 0));
     if (rc) return rc;
     LnlArgs A{};
     A.lc = g.lc; A.tab = g.tab; A.eb = eb; A.companion_is_host = is_host; A.raw = 1;
@@ -705,17 +718,25 @@ static int lnl_seam(int eb, int64_t n, const double* body, const double* ebfr, c
     UP(argp, argp) UP(cfr, cfr)
 #undef UP
     double* d_out = g.staging.take<double>(n);
+    double* d_model = model_out ? g.staging.take<double>((size_t)n * npts) : nullptr;
+    double* d_sec = secdepth_out ? g.staging.take<double>(n) : nullptr;
     g.launches = 0;
     CU(cudaMemsetAsync(g.d_counters, 0, 8 * sizeof(unsigned long long), s));
     A.items = nullptr; A.count = n; A.count_dev = nullptr; A.next = g.d_counters + 2;
     A.out = d_out; A.out_twin = nullptr; A.counters = g.d_counters + 4;
+    A.model_out = d_model; A.secdepth_out = d_sec; A.perm = g.d_perm;
+    A.scalar_rule = scalar_rule;
     CU(cudaEventRecord(g.ev[0], s));
     CU(cudaEventRecord(g.ev[1], s));
     rc = launch_lnl(A, s);
     if (rc) return rc;
     CU(cudaEventRecord(g.ev[2], s));
     CU(cudaEventRecord(g.ev[3], s));
-    CU(cudaMemcpyAsync(out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    if (out) CU(cudaMemcpyAsync(out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    if (model_out)
+        CU(cudaMemcpyAsync(model_out, d_model, (size_t)n * npts * 8, cudaMemcpyDeviceToHost, s));
+    if (secdepth_out)
+        CU(cudaMemcpyAsync(secdepth_out, d_sec, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     g.timing_valid = true;
     return TRI_OK;
@@ -735,6 +756,26 @@ int tri_lnl_eb(int64_t n, const double* R_EB, const double* EB_fluxratio, const 
                int32_t is_host, int32_t twin, double* out) {
     return lnl_seam(1, n, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
                     is_host, twin, out);
+}
+
+int tri_simulate_tp(int64_t n, const double* R_p, const double* P_orb, const double* inc,
+                    const double* a, const double* R_s, const double* u1, const double* u2,
+                    const double* ecc, const double* argp, const double* cfr, int32_t is_host,
+                    double* flux_out) {
+    if (!flux_out) return fail(TRI_EINVAL, "flux_out is NULL");
+    return lnl_seam(0, n, R_p, nullptr, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr, is_host, 1,
+                    nullptr, flux_out, nullptr);
+}
+
+int tri_simulate_eb(int64_t n, const double* R_EB, const double* EB_fluxratio,
+                    const double* P_orb, const double* inc, const double* a, const double* R_s,
+                    const double* u1, const double* u2, const double* ecc, const double* argp,
+                    const double* cfr, int32_t is_host, int32_t scalar_rule, double* flux_out,
+                    double* secdepth_out) {
+    if (!flux_out) return fail(TRI_EINVAL, "flux_out is NULL");
+    // twin = 1: the secondary-depth cut belongs to lnL_EB_p, not to the simulation
+    return lnl_seam(1, n, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
+                    is_host, 1, nullptr, flux_out, secdepth_out, scalar_rule ? 1 : 0);
 }
 
 int tri_fetch_lnl(int32_t branch, double* out, int64_t N) {

@@ -169,6 +169,12 @@ struct LnlArgs {
     double* out_twin;        // lnL of the twin branch (fused EB only)
     unsigned long long* counters;  // optional [4]: model points evaluated, time stamps in
                                    // windows, interior-case points, limb/edge-case points
+    // simulate mode (simulate_TP_transit_p / simulate_EB_transit_p, likelihoods.py:302-439):
+    double* model_out;       // optional [count][npts] diluted model flux, caller's stamp order
+    double* secdepth_out;    // optional [count] secondary-eclipse depth (EB-type)
+    const int* perm;         // sorted stamp j -> caller's stamp index
+    int scalar_rule;         // 1: radius-ratio rules of the scalar simulate_EB_transit
+                             // (likelihoods.py:121-123, :137) instead of the vectorised ones
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -249,10 +255,15 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
             const double reb = A.body.at(i);
             const double fr = A.ebfr.at(i);
             F_EB = fr / (1.0 - fr);
-            k_pri = reb / rhost;                                   // :405-406
-            if ((k_pri - 1.0) < 1e-6) k_pri *= 0.999;
-            k_sec = rhost / reb;                                   // :417-418
-            if ((k_sec - 1.0) < 1e-6) k_sec *= 0.999;
+            k_pri = reb / rhost;
+            if (!A.scalar_rule) {
+                if ((k_pri - 1.0) < 1e-6) k_pri *= 0.999;          // :405-406 (no abs: every k <= 1)
+                k_sec = rhost / reb;                               // :417-418
+                if ((k_sec - 1.0) < 1e-6) k_sec *= 0.999;
+            } else {
+                if (fabs(k_pri - 1.0) < 1e-6) k_pri *= 0.999;      // :121-123
+                k_sec = 1.0 / k_pri;                               // :137
+            }
             D.two_stage = true;
             if (A.companion_is_host) {                              // :427-432
                 D.d1 = F_EB / F_comp;
@@ -296,6 +307,11 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                     jhi = lower_bound(lc.time, lc.npts, win.t_hi + half);
                     if (jhi < jlo) jhi = jlo;
                 }
+                if (A.model_out) {   // outside the window the model is exactly 1
+                    double* row = A.model_out + (size_t)w * lc.npts;
+                    for (int j = lane; j < lc.npts; j += 32)
+                        if (j < jlo || j >= jhi) row[A.perm[j]] = 1.0;
+                }
             } else {
                 jlo = 0;
                 jhi = 25;
@@ -329,7 +345,9 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                     }
                     const double m = acc / ns;
                     if (primary) {
-                        const double r = lc.flux[j] - dilute(D, m);
+                        const double md = dilute(D, m);
+                        if (A.model_out) A.model_out[(size_t)w * lc.npts + A.perm[j]] = md;
+                        const double r = lc.flux[j] - md;
                         red = fma(r, r, red);
                     } else {
                         red = fmin(red, m);
@@ -341,6 +359,7 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                 if (A.companion_is_host) sec = (sec + F_comp / F_EB) / (1.0 + F_comp / F_EB);
                 else sec = (sec + 1.0 / F_EB) / (1.0 + 1.0 / F_EB);
                 const double sd = 1.0 - (sec + D.d2) / (1.0 + D.d2);
+                if (A.secdepth_out && lane == 0) A.secdepth_out[w] = sd;
                 cut = !twin && !(sd < 1.5 * sigma);                 // :535-538
                 if (cut) break;
             } else {

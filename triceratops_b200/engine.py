@@ -195,6 +195,31 @@ class Engine:
                                         _cabi.dptr(out)))
         return out
 
+    # ------------------------------------------------------------------ simulate seam
+    def simulate_tp(self, npts, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
+                    companion_is_host):
+        n = int(np.size(R_p))
+        cols = [self._full(x, n) for x in (R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr)]
+        out = np.empty((n, int(npts)))
+        if n:
+            _cabi.check(self.lib.tri_simulate_tp(n, *[_cabi.dptr(c) for c in cols],
+                                                 int(bool(companion_is_host)), _cabi.dptr(out)))
+        return out
+
+    def simulate_eb(self, npts, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
+                    companion_is_host, scalar_rule=False):
+        n = int(np.size(R_EB))
+        cols = [self._full(x, n) for x in (R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc,
+                                           argp, cfr)]
+        out = np.empty((n, int(npts)))
+        sec = np.empty(n)
+        if n:
+            _cabi.check(self.lib.tri_simulate_eb(n, *[_cabi.dptr(c) for c in cols],
+                                                 int(bool(companion_is_host)),
+                                                 int(bool(scalar_rule)), _cabi.dptr(out),
+                                                 _cabi.dptr(sec)))
+        return out, sec
+
     @staticmethod
     def _full(x, n):
         a = np.asarray(x, dtype=np.float64)
