@@ -1,0 +1,50 @@
+"""Batch front-end: a job runs through the drop-in calc_probs; under a process group the job
+list (not the draws) is what gets distributed."""
+import numpy as np
+import pytest
+
+from conftest import TOI465
+
+
+def _job(toi465_lc, trilegal_file, seed=3, N=400):
+    from oracle import synth
+    t, f, s = toi465_lc
+    stars = synth.stars_table(77, TOI465["T"], TOI465["J"], TOI465["H"], TOI465["K"],
+                              TOI465["M"], TOI465["R"], TOI465["Teff"], TOI465["plx"],
+                              n_neighbours=0)
+    return dict(ID=77, stars=stars, trilegal_fname=trilegal_file, time=t, flux=f, flux_err=s,
+                P_orb=TOI465["P"], seed=seed, calc_probs=dict(N=N))
+
+
+def test_run_job_matches_direct_calc_probs(oracle_engine, toi465_lc, trilegal_file):
+    from triceratops_b200.batch import run_job
+    from triceratops_b200.triceratops import target
+    job = _job(toi465_lc, trilegal_file)
+    res = run_job(job)
+    tgt = target(77, stars=job["stars"], trilegal_fname=trilegal_file)
+    np.random.seed(3)
+    tgt.calc_probs(job["time"], job["flux"], job["flux_err"], job["P_orb"], N=400, parallel=True,
+                   verbose=0)
+    assert res["FPP"] == float(tgt.FPP) and res["NFPP"] == float(tgt.NFPP)
+    assert np.array_equal(res["lnZ"], tgt.lnZ) and len(res["probs"]["scenario"]) == 15
+
+
+def test_no_sharding_context_disables_the_rank_split():
+    from triceratops_b200 import _dispatch
+    with _dispatch.no_sharding():
+        assert _dispatch._dist() is None
+        assert _dispatch.shard_bounds(10) == (0, 10)
+    assert _dispatch._sharding is True
+
+
+@pytest.mark.gpu
+def test_vet_many_spawns_workers_and_keeps_job_order(gpu_engine, toi465_lc, trilegal_file):
+    from triceratops_b200.batch import run_job, vet_many
+    jobs = [_job(toi465_lc, trilegal_file, seed=s, N=20000) for s in (1, 2, 3)]
+    for i, j in enumerate(jobs):
+        j["ID"] = 100 + i
+        j["stars"] = j["stars"].assign(ID=[100 + i])
+    res = vet_many(jobs, n_gpus=1, workers_per_gpu=2)
+    assert [r["ID"] for r in res] == [100, 101, 102]
+    again = run_job(jobs[1])                     # same seed, this process: same answer
+    np.testing.assert_allclose(res[1]["lnZ"], again["lnZ"], rtol=1e-12)

@@ -24,7 +24,25 @@ def get_engine():
     return _engine_factory()
 
 
+_sharding = True
+
+
+class no_sharding:
+    """Context manager: evaluate every draw on this rank even inside a process group (used when
+    whole targets, not draws, are distributed over the ranks -- batch.vet_many)."""
+
+    def __enter__(self):
+        global _sharding
+        self._prev, _sharding = _sharding, False
+
+    def __exit__(self, *exc):
+        global _sharding
+        _sharding = self._prev
+
+
 def _dist():
+    if not _sharding:
+        return None
     try:
         import torch.distributed as dist
     except Exception:  # pragma: no cover
