@@ -104,17 +104,26 @@ def make_target():
     return tgt, t, f, s, lc
 
 
-def calc_probs_wall(N, seed):
+def calc_probs_wall(N, seed, sampler="host"):
     """The user-facing call, untimed extras: one full target.calc_probs on the real engine
-    (host prior draws + 12 engine calls + best-draw tables).  Under torchrun the draws of each
-    scenario are sharded over the ranks by the package itself."""
+    (prior draws + 12 engine calls + best-draw tables).  sampler="host": numpy draws in the
+    reference's order (parity mode); "device": draws generated in HBM (opt-in).  Under torchrun
+    the draws of each scenario are sharded over the ranks by the package itself."""
+    import triceratops_b200
     tgt, t, f, s, _ = make_target()
-    np.random.seed(seed)
-    t0 = time.perf_counter()
-    tgt.calc_probs(t, f, s, TOI465["P"],
-                   contrast_curve_file=os.path.join(GOLD, "TOI465_01_contrastcurve.csv"),
-                   filt="K", N=N, parallel=True, verbose=0)
-    return time.perf_counter() - t0, float(tgt.FPP), float(tgt.NFPP)
+    best = None
+    try:
+        triceratops_b200.set_sampler(sampler, seed=seed)
+        for _ in range(2 if sampler == "device" else 1):    # first device call warms torch up
+            np.random.seed(seed)
+            t0 = time.perf_counter()
+            tgt.calc_probs(t, f, s, TOI465["P"],
+                           contrast_curve_file=os.path.join(GOLD, "TOI465_01_contrastcurve.csv"),
+                           filt="K", N=N, parallel=True, verbose=0)
+            best = time.perf_counter() - t0
+    finally:
+        triceratops_b200.set_sampler("host")
+    return best, float(tgt.FPP), float(tgt.NFPP)
 
 
 def build_workload(N, seed):
@@ -415,6 +424,11 @@ def run_ours(args):
                               "note": "target.calc_probs incl. host prior draws (numpy RNG, "
                                       "sequential by construction); draws sharded over %d "
                                       "rank(s)" % world}
+    wall, fpp, nfpp = calc_probs_wall(N, SEED, sampler="device")
+    out["calc_probs_call_device_sampler"] = {
+        "wall_s": wall, "N_total": N, "FPP": fpp, "NFPP": nfpp,
+        "note": "opt-in mode: prior draws generated on the GPU (statistically equivalent, not "
+                "the reference's numpy stream)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_leg(calls, npts, 4 * args.cpu_draws, steps=1, warmup=0)
     if rank == 0:

@@ -110,6 +110,36 @@ class OracleEngine:
             out.append(_lse_record(lnL if lnprior is None else lnL + _full(lnprior, N), N, res))
         return tuple(out)
 
+    # ---- device-sampler entry points: torch (CPU) tensors in, numpy evaluation ----
+    @staticmethod
+    def _np(x):
+        try:
+            import torch
+            if torch.is_tensor(x):
+                return x.detach().cpu().numpy()
+        except Exception:
+            pass
+        return x
+
+    def _with_top(self, res, n_best):
+        fin = np.flatnonzero(np.isfinite(res.lnL))
+        order = fin[np.lexsort((fin, -res.lnL[fin]))][:n_best]
+        res.top_idx, res.top_lnL = order, res.lnL[order]
+        res.n_evaluated, res.branch = int(fin.size), 0
+        return res
+
+    def eval_tp_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
+        c = {k: self._np(v) for k, v in cols.items()}
+        res = self.eval_tp(N, extra_mask=self._np(extra_mask),
+                           companion_is_host=companion_is_host, **c)
+        return self._with_top(res, n_best)
+
+    def eval_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
+        c = {k: self._np(v) for k, v in cols.items()}
+        r0, r1 = self.eval_eb(N, extra_mask=self._np(extra_mask),
+                              companion_is_host=companion_is_host, **c)
+        return self._with_top(r0, n_best), self._with_top(r1, n_best)
+
     # ---- simulate seam (likelihoods.py:302-439 and the scalar :27-160), via the C model ----
     def _rows(self, npts, k, P, a_cm, R_s, inc, ecc, w_deg, u1, u2, exptime, ns):
         t = self.lc[0]

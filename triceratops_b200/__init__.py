@@ -58,3 +58,21 @@ def unpatch():
     while _saved:
         mod, name, fn = _saved.pop()
         setattr(mod, name, fn)
+
+
+def set_sampler(mode="host", seed=None):
+    """Where the prior draws are made.
+
+    "host" (default): numpy's global RNG in the reference's call order -- a given np.random.seed
+        reproduces the reference's draws bit for bit (the parity mode).
+    "device": draws are generated in HBM (torch Philox) and never visit the host; statistically
+        equivalent results, ~10x less wall time per calc_probs (device_sampler.py).  `seed`
+        makes the device streams reproducible.
+    """
+    from . import marginal_likelihoods
+    if mode not in ("host", "device"):
+        raise ValueError("mode must be 'host' or 'device'")
+    marginal_likelihoods._SAMPLER["mode"] = mode
+    if mode == "device":
+        from . import device_sampler
+        device_sampler.seed(seed)

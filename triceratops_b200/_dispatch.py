@@ -179,3 +179,63 @@ def run_eb(N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnp
                          lnprior=_slice(lnprior, lo, hi), extra_mask=_mask_slice(extra_mask, lo, hi),
                          companion_is_host=companion_is_host, want_lnL=False, n_best=N_BEST)
     return _gather_branch(r0, lo, hi, N, eng), _gather_branch(r1, lo, hi, N, eng)
+
+
+# ---- device-sampler mode: every rank owns its own draws --------------------------------------
+class LocalBranch:
+    """This rank's share of a branch: evidence record and its best LOCAL draws."""
+    __slots__ = ("res", "idx", "vals", "N")
+
+
+def gather_local(res, N, eng=None):
+    lb = LocalBranch()
+    lb.res, lb.N = res, N
+    idx, vals, _ = _local_best(res, eng, False)
+    fin = np.isfinite(vals)
+    lb.idx, lb.vals = np.asarray(idx)[fin], np.asarray(vals)[fin]
+    return lb
+
+
+def merge_tables(lb, table, keys):
+    """Combine per-rank evidence records and best-draw ROWS (the draws themselves live on the
+    rank that made them).  `table`: dict key -> array over lb.idx.  Returns
+    (lnZ, n_pass, n_evaluated, merged table padded to N_BEST rows)."""
+    res = lb.res
+    n_eval = int(res.n_evaluated) if res.n_evaluated is not None else int(len(lb.idx))
+    rows = np.stack([np.asarray(table[k], dtype=np.float64) for k in keys], axis=1) \
+        if len(lb.idx) else np.zeros((0, len(keys)))
+    vals = lb.vals
+    d = _dist()
+    if d is None:
+        lnZ, n_pass = res.lnZ, int(res.n_pass)
+    else:
+        import torch
+        world = d.get_world_size()
+        W = 6 + N_BEST * (1 + len(keys))
+        rec = np.full(W, np.nan)
+        rec[0:6] = (res.m, res.s, res.n_finite, res.n_posinf, res.n_pass, n_eval)
+        k = len(vals)
+        rec[6:6 + k] = vals
+        rec[6 + N_BEST:6 + N_BEST + k * len(keys)] = rows.ravel()
+        dev = "cuda" if d.get_backend() == "nccl" else "cpu"
+        mine = torch.from_numpy(rec).to(dev)
+        allrec = torch.empty(world * W, dtype=torch.float64, device=dev)
+        d.all_gather_into_tensor(allrec, mine)
+        allrec = allrec.cpu().numpy().reshape(world, W)
+        lnZ = _engine_mod.combine_lse([(r[0], r[1], int(r[2]), int(r[3])) for r in allrec], lb.N)
+        n_pass = int(sum(r[4] for r in allrec))
+        n_eval = int(sum(r[5] for r in allrec))
+        vs, rs = [], []
+        for r in allrec:
+            v = r[6:6 + N_BEST]
+            ok = ~np.isnan(v)
+            vs.append(v[ok])
+            rs.append(r[6 + N_BEST:6 + N_BEST + int(ok.sum()) * len(keys)].reshape(-1, len(keys)))
+        vals, rows = np.concatenate(vs), np.concatenate(rs)
+    order = np.argsort(-vals, kind="stable")[:N_BEST]
+    rows = rows[order]
+    if len(rows) < N_BEST:
+        # zero-weight padding rows so that the table always has N_BEST entries
+        pad = rows[-1:] if len(rows) else np.zeros((1, len(keys)))
+        rows = np.concatenate([rows, np.repeat(pad, N_BEST - len(rows), axis=0)])
+    return lnZ, n_pass, n_eval, {k: rows[:, i].copy() for i, k in enumerate(keys)}

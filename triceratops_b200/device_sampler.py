@@ -1,0 +1,436 @@
+"""The ten `lnZ_*` scenarios with the prior draws generated on the device (opt-in).
+
+Same scenario definitions as `marginal_likelihoods.py` (reference
+marginal_likelihoods.py:39-2362) -- same priors, same derived quantities, same wiring into the
+two kernels -- but every per-draw column is produced in HBM by `device_priors.py` and handed to
+`tri_eval_tp_dev` / `tri_eval_eb_dev` by pointer.  The results are statistically, not bitwise,
+equivalent to the host-sampler mode (different random streams); see device_priors.py.
+
+Enable with `triceratops_b200.set_sampler("device", seed=...)`.  Under a process group every
+rank draws its own N/G draws (independent streams), so nothing but the evidence records and
+best-draw candidates is exchanged.
+"""
+import math
+
+import numpy as np
+import torch
+from pandas import read_csv
+
+from . import _dispatch
+from . import device_priors as dp
+from ._constants import G, Msun, Rsun, pi
+from ._ldc import grid_for
+from .funcs import file_to_contrast_curve, trilegal_results
+
+N_SAMPLES = 100
+_state = {"seed": None, "calls": 0}
+
+
+def seed(value):
+    _state["seed"] = value
+    _state["calls"] = 0
+
+
+def _device():
+    eng = _dispatch.get_engine()
+    d = getattr(eng, "device", 0)
+    if d is None or d < 0 or not torch.cuda.is_available():
+        return torch.device("cpu")       # oracle stand-in (tests)
+    return torch.device("cuda", d)
+
+
+def _begin(time, flux, sigma, exptime, nsamples, N):
+    """Upload the light curve, seed this call's stream, return (device, local draw count)."""
+    eng = _dispatch.get_engine()
+    eng.set_lightcurve(time, flux, sigma, exptime, nsamples)
+    dev = _device()
+    lo, hi = _dispatch.shard_bounds(N)
+    if _state["seed"] is not None:
+        rank = 0
+        d = _dispatch._dist()
+        if d is not None:
+            rank = d.get_rank()
+        s = (int(_state["seed"]) * 1000003 + _state["calls"] * 7919 + rank) % (2 ** 63 - 1)
+        torch.manual_seed(s)
+        if dev.type == "cuda":
+            torch.cuda.manual_seed(s)
+    _state["calls"] += 1
+    return eng, dev, hi - lo
+
+
+def _periods(P_orb, n, dev):
+    if type(P_orb) not in [float, int]:
+        P = P_orb[0] + (P_orb[-1] - P_orb[0]) * dp.rand(n, dev)
+        return P, float(0.5 * (P_orb[0] + P_orb[-1]))
+    return float(P_orb), float(P_orb)
+
+
+def _logg(M, R):
+    return math.log10(G * (M * Msun) / (R * Rsun) ** 2)
+
+
+def _draw_planet(n, host_masses, flatpriors, P_mean, dev):
+    rps = dp.sample_rp(dp.rand(n, dev), host_masses, flatpriors)
+    incs = dp.sample_inc(dp.rand(n, dev))
+    eccs = dp.sample_ecc(n, True, P_mean, dev)
+    argps = dp.sample_w(dp.rand(n, dev))
+    return rps, incs, eccs, argps
+
+
+def _draw_binary(n, M_s, P_mean, dev):
+    incs = dp.sample_inc(dp.rand(n, dev))
+    qs = dp.sample_q(dp.rand(n, dev), M_s)
+    eccs = dp.sample_ecc(n, False, P_mean, dev)
+    argps = dp.sample_w(dp.rand(n, dev))
+    return incs, qs, eccs, argps
+
+
+def _companion_q(n, M_s, molusc_file, dev):
+    if molusc_file is None:
+        return dp.sample_q_companion(dp.rand(n, dev), M_s)
+    df = read_csv(molusc_file)
+    sma = df["semi-major axis(AU)"].values
+    e = df["eccentricity"].values
+    q = np.array(df[sma * (1 - e) > 10]["mass ratio"].values, dtype=float)
+    q[q < 0.1 / M_s] = 0.1 / M_s
+    return dp._t(np.pad(q, (0, n - len(q)))[:n], dev)
+
+
+def _fluxratio(masses, M_s, filt="TESS"):
+    f = dp.flux_relation(masses, filt)
+    return f / (f + dp.flux_relation_scalar(M_s, filt))
+
+
+def _bound_prior(prior_fn, M_s, plx, n, dev, molusc_file, contrast_curve_file, fr_tess, fr_cc_fn):
+    if molusc_file is not None:
+        return None
+    if contrast_curve_file is None:
+        dm = 2.5 * torch.log10(fr_tess)
+        sep, con = dp._t([2.2], dev), dp._t([1.0], dev)
+    else:
+        dm = 2.5 * torch.log10(fr_cc_fn())
+        s_, c_ = file_to_contrast_curve(contrast_curve_file)
+        sep, con = dp._t(s_, dev), dp._t(c_, dev)
+    return dp.clip_prior(prior_fn(M_s, plx, torch.abs(dm), sep, con), dm)
+
+
+class _Background:
+    def __init__(self, trilegal_fname, Tmag, Jmag, Hmag, Kmag, dev):
+        (Tm, masses, loggs, Teffs, Zs, Jm, Hm, Km) = trilegal_results(trilegal_fname, Tmag)
+        self.N_comp = Tm.shape[0]
+        self.delta = {"T": Tmag - Tm, "J": Jmag - Jm, "H": Hmag - Hm, "K": Kmag - Km}
+        self.h_masses, self.h_loggs, self.h_Teffs, self.h_Zs = masses, loggs, Teffs, Zs
+        self.dev = dev
+        self.masses, self.loggs, self.Teffs = (dp._t(masses, dev), dp._t(loggs, dev),
+                                               dp._t(Teffs, dev))
+        self.fluxratios = dp._t(self._fr("T"), dev)
+
+    def _fr(self, band):
+        d = self.delta[band]
+        return 10 ** (d / 2.5) / (1 + 10 ** (d / 2.5))
+
+    def band_key(self, filt):
+        return filt if filt in ("J", "H", "K") else "T"
+
+    def dmag(self, filt):
+        return dp._t(self.delta[self.band_key(filt)], self.dev)
+
+    def fluxratios_in(self, filt):
+        return dp._t(self._fr(self.band_key(filt)), self.dev)
+
+    def radii(self):
+        return dp._t(np.sqrt(G * self.h_masses * Msun / 10 ** self.h_loggs) / Rsun, self.dev)
+
+    def ldc(self, mission):
+        u1, u2 = grid_for(mission).nearest_each(self.h_Teffs, self.h_loggs, self.h_Zs)
+        return dp._t(u1, self.dev), dp._t(u2, self.dev)
+
+
+def _background_prior(bg, n, dev, contrast_curve_file, dmag_tess, dmag_cc):
+    if contrast_curve_file is None:
+        c = math.log((bg.N_comp / 0.1) * (1 / 3600) ** 2 * 2.2 ** 2)
+        return dp.clip_prior(torch.full((n,), c, dtype=dp.F64, device=dev), dmag_tess)
+    s_, c_ = file_to_contrast_curve(contrast_curve_file)
+    lnprior = dp.lnprior_background(bg.N_comp, torch.abs(dmag_cc), dp._t(s_, dev), dp._t(c_, dev))
+    return dp.clip_prior(lnprior, dmag_cc)
+
+
+# ------------------------------------------------------------------------------- result tables
+def _take(x, idx, dev):
+    if torch.is_tensor(x):
+        return x[idx].cpu().numpy()
+    return np.full(len(idx), x)
+
+
+def _semi_major_axis(mtot, P):
+    return ((G * mtot * Msun) / (4 * pi ** 2) * (P * 86400) ** 2) ** (1 / 3)
+
+
+_KEYS = ('M_s', 'R_s', 'u1', 'u2', 'P_orb', 'inc', 'b', 'R_p', 'ecc', 'argp', 'M_EB', 'R_EB',
+         'fluxratio_EB', 'fluxratio_comp')
+
+
+def _table(lb, dev, twin, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cfr, rps=None,
+           masses=None, radii=None, fluxratios=None):
+    """Result dictionary (reference marginal_likelihoods.py:155-171) from this rank's best local
+    draws, merged across ranks."""
+    from .marginal_likelihoods import ScenarioResult
+    idx = torch.as_tensor(np.asarray(lb.idx, dtype=np.int64), device=dev)
+    g = lambda x: _take(x, idx, dev)  # noqa: E731
+    n = len(lb.idx)
+    P_i = g(P) * (2 if twin else 1)
+    a_i = _semi_major_axis(g(mtot), P_i)
+    ecc, argp, inc, Rh = g(eccs), g(argps), g(incs), g(R_host)
+    r = a_i * (1 - ecc ** 2) / (1 + ecc * np.sin(argp * np.pi / 180))
+    zeros = np.zeros(n)
+    local = {
+        'M_s': g(M_host), 'R_s': Rh, 'u1': g(u1), 'u2': g(u2), 'P_orb': P_i, 'inc': inc,
+        'b': r * np.cos(inc * pi / 180) / (Rh * Rsun),
+        'R_p': g(rps) if rps is not None else zeros, 'ecc': ecc, 'argp': argp,
+        'M_EB': g(masses) if masses is not None else zeros,
+        'R_EB': g(radii) if radii is not None else zeros,
+        'fluxratio_EB': g(fluxratios) if fluxratios is not None else zeros,
+        'fluxratio_comp': g(cfr) if torch.is_tensor(cfr) else zeros,
+    }
+    lnZ, n_pass, n_eval, merged = _dispatch.merge_tables(lb, local, _KEYS)
+    merged['lnZ'] = lnZ
+    out = ScenarioResult(merged)
+    out.n_pass, out.n_evaluated = n_pass, n_eval
+    return out
+
+
+def _run_tp(eng, dev, n, N, M_host, R_host, u1, u2, P, mtot, rps, incs, eccs, argps, cfr, lnprior,
+            extra_mask, is_host):
+    res = eng.eval_tp_tensors(n, dict(rp=rps, P_orb=P, inc=incs, ecc=eccs, argp=argps, mtot=mtot,
+                                      rhost=R_host, u1=u1, u2=u2, cfr=cfr, lnprior=lnprior),
+                              extra_mask, is_host, N_SAMPLES)
+    lb = _dispatch.gather_local(res, N, eng)
+    return _table(lb, dev, False, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cfr, rps=rps)
+
+
+def _run_eb(eng, dev, n, N, M_host, R_host, u1, u2, P, mtot, incs, qs, eccs, argps, masses, radii,
+            fluxratios, cfr, lnprior, extra_mask, is_host):
+    r0, r1 = eng.eval_eb_tensors(n, dict(reb=radii, ebfr=fluxratios, q=qs, P_orb=P, inc=incs,
+                                         ecc=eccs, argp=argps, mtot=mtot, rhost=R_host, u1=u1,
+                                         u2=u2, cfr=cfr, lnprior=lnprior),
+                                 extra_mask, is_host, N_SAMPLES)
+    common = (M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cfr)
+    kw = dict(masses=masses, radii=radii, fluxratios=fluxratios)
+    return (_table(_dispatch.gather_local(r0, N, eng), dev, False, *common, **kw),
+            _table(_dispatch.gather_local(r1, N, eng), dev, True, *common, **kw))
+
+
+# ------------------------------------------------------------------------------- scenarios
+def lnZ_TTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, N=1000000, parallel=False,
+            mission="TESS", flatpriors=False, exptime=0.00139, nsamples=20):
+    eng, dev, n = _begin(time, flux, sigma, exptime, nsamples, int(N))
+    P, P_mean = _periods(P_orb, n, dev)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    rps, incs, eccs, argps = _draw_planet(n, M_s, flatpriors, P_mean, dev)
+    return _run_tp(eng, dev, n, int(N), M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, 0.0,
+                   None, None, False)
+
+
+def lnZ_TEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, N=1000000, parallel=False,
+            mission="TESS", flatpriors=False, exptime=0.00139, nsamples=20):
+    eng, dev, n = _begin(time, flux, sigma, exptime, nsamples, int(N))
+    P, P_mean = _periods(P_orb, n, dev)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    incs, qs, eccs, argps = _draw_binary(n, M_s, P_mean, dev)
+    masses = qs * M_s
+    radii, _ = dp.stellar_relations(masses, R_s, Teff)
+    fluxratios = _fluxratio(masses, M_s)
+    return _run_eb(eng, dev, n, int(N), M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps,
+                   masses, radii, fluxratios, 0.0, None, None, False)
+
+
+def lnZ_PTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file=None,
+            filt="TESS", N=1000000, parallel=False, mission="TESS", flatpriors=False,
+            exptime=0.00139, nsamples=20, molusc_file=None):
+    eng, dev, n = _begin(time, flux, sigma, exptime, nsamples, int(N))
+    P, P_mean = _periods(P_orb, n, dev)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    qs_comp = _companion_q(n, M_s, molusc_file, dev)
+    masses_comp = qs_comp * M_s
+    cfr = _fluxratio(masses_comp, M_s)
+
+    def cc_term():
+        fr = _fluxratio(masses_comp, M_s, filt)
+        return fr / (1 - fr)
+
+    lnprior = _bound_prior(dp.lnprior_bound_TP, M_s, plx, n, dev, molusc_file,
+                           contrast_curve_file, cfr / (1 - cfr), cc_term)
+    rps, incs, eccs, argps = _draw_planet(n, M_s, flatpriors, P_mean, dev)
+    return _run_tp(eng, dev, n, int(N), M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, cfr,
+                   lnprior, qs_comp != 0.0, False)
+
+
+def lnZ_PEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file=None,
+            filt="TESS", N=1000000, parallel=False, mission="TESS", flatpriors=False,
+            exptime=0.00139, nsamples=20, molusc_file=None):
+    eng, dev, n = _begin(time, flux, sigma, exptime, nsamples, int(N))
+    P, P_mean = _periods(P_orb, n, dev)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    incs, qs, eccs, argps = _draw_binary(n, M_s, P_mean, dev)
+    qs_comp = _companion_q(n, M_s, molusc_file, dev)
+    masses = qs * M_s
+    radii, _ = dp.stellar_relations(masses, R_s, Teff)
+    fluxratios = _fluxratio(masses, M_s)
+    masses_comp = qs_comp * M_s
+    cfr = _fluxratio(masses_comp, M_s)
+
+    def cc_term():
+        fr = _fluxratio(masses_comp, M_s, filt)
+        return fr / (1 - fr)
+
+    lnprior = _bound_prior(dp.lnprior_bound_EB, M_s, plx, n, dev, molusc_file,
+                           contrast_curve_file, cfr / (1 - cfr), cc_term)
+    return _run_eb(eng, dev, n, int(N), M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps,
+                   masses, radii, fluxratios, cfr, lnprior, qs_comp != 0.0, False)
+
+
+def _companion_stars(n, M_s, R_s, Teff, Z, mission, qs_comp, Teff_cap):
+    masses_comp = qs_comp * M_s
+    radii_comp, Teffs_comp = dp.stellar_relations(masses_comp, R_s, Teff)
+    loggs_comp = torch.log10(G * (masses_comp * Msun) / (radii_comp * Rsun) ** 2)
+    cfr = _fluxratio(masses_comp, M_s)
+    u1s, u2s = dp.ldc_at_Z_rounded(grid_for(mission), Z, Teffs_comp, loggs_comp, Teff_cap)
+    return masses_comp, radii_comp, Teffs_comp, cfr, u1s, u2s
+
+
+def lnZ_STP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file=None,
+            filt="TESS", N=1000000, parallel=False, mission="TESS", flatpriors=False,
+            exptime=0.00139, nsamples=20, molusc_file=None):
+    eng, dev, n = _begin(time, flux, sigma, exptime, nsamples, int(N))
+    P, P_mean = _periods(P_orb, n, dev)
+    qs_comp = _companion_q(n, M_s, molusc_file, dev)
+    masses_comp, radii_comp, _, cfr, u1s, u2s = _companion_stars(n, M_s, R_s, Teff, Z, mission,
+                                                                 qs_comp, 10000)
+
+    def cc_term():
+        fr = _fluxratio(masses_comp, M_s, filt)
+        return fr / (1 - fr)
+
+    lnprior = _bound_prior(dp.lnprior_bound_TP, M_s, plx, n, dev, molusc_file,
+                           contrast_curve_file, cfr / (1 - cfr), cc_term)
+    rps, incs, eccs, argps = _draw_planet(n, masses_comp, flatpriors, P_mean, dev)
+    return _run_tp(eng, dev, n, int(N), masses_comp, radii_comp, u1s, u2s, P, masses_comp, rps,
+                   incs, eccs, argps, cfr, lnprior, qs_comp != 0.0, True)
+
+
+def lnZ_SEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file=None,
+            filt="TESS", N=1000000, parallel=False, mission="TESS", flatpriors=False,
+            exptime=0.00139, nsamples=20, molusc_file=None):
+    eng, dev, n = _begin(time, flux, sigma, exptime, nsamples, int(N))
+    P, P_mean = _periods(P_orb, n, dev)
+    incs, qs, eccs, argps = _draw_binary(n, M_s, P_mean, dev)
+    qs_comp = _companion_q(n, M_s, molusc_file, dev)
+    masses_comp, radii_comp, Teffs_comp, cfr, u1s, u2s = _companion_stars(
+        n, M_s, R_s, Teff, Z, mission, qs_comp, 13000)
+    masses = qs * masses_comp
+    radii, _ = dp.stellar_relations(masses, radii_comp, Teffs_comp)
+    fluxratios = _fluxratio(masses, M_s)
+
+    def cc_term():
+        fr = _fluxratio(masses, M_s, filt)
+        frc = _fluxratio(masses_comp, M_s, filt)
+        return (frc / (1 - frc)) + (fr / (1 - fr))
+
+    lnprior = _bound_prior(dp.lnprior_bound_EB, M_s, plx, n, dev, molusc_file,
+                           contrast_curve_file,
+                           (cfr / (1 - cfr)) + (fluxratios / (1 - fluxratios)), cc_term)
+    return _run_eb(eng, dev, n, int(N), masses_comp, radii_comp, u1s, u2s, P,
+                   masses_comp + masses, incs, qs, eccs, argps, masses, radii, fluxratios, cfr,
+                   lnprior, qs_comp != 0.0, True)
+
+
+def _randint(lo, hi, n, dev):
+    return torch.randint(lo, hi, (n,), device=dev)
+
+
+def lnZ_DTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, Tmag, Jmag, Hmag, Kmag, trilegal_fname,
+            contrast_curve_file=None, filt="TESS", N=1000000, parallel=False, mission="TESS",
+            flatpriors=False, exptime=0.00139, nsamples=20):
+    eng, dev, n = _begin(time, flux, sigma, exptime, nsamples, int(N))
+    P, P_mean = _periods(P_orb, n, dev)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag, dev)
+    idxs = _randint(0, bg.N_comp - 1, n, dev)            # upper bound N_comp-1, as :1463
+    cfr = bg.fluxratios[idxs]
+    lnprior = _background_prior(bg, n, dev, contrast_curve_file,
+                                2.5 * torch.log10(cfr / (1 - cfr)), bg.dmag(filt)[idxs])
+    rps, incs, eccs, argps = _draw_planet(n, M_s, flatpriors, P_mean, dev)
+    return _run_tp(eng, dev, n, int(N), M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, cfr,
+                   lnprior, None, False)
+
+
+def lnZ_DEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, Tmag, Jmag, Hmag, Kmag, trilegal_fname,
+            contrast_curve_file=None, filt="TESS", N=1000000, parallel=False, mission="TESS",
+            flatpriors=False, exptime=0.00139, nsamples=20):
+    eng, dev, n = _begin(time, flux, sigma, exptime, nsamples, int(N))
+    P, P_mean = _periods(P_orb, n, dev)
+    u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    incs, qs, eccs, argps = _draw_binary(n, M_s, P_mean, dev)
+    masses = qs * M_s
+    radii, _ = dp.stellar_relations(masses, R_s, Teff)
+    fluxratios = _fluxratio(masses, M_s)
+    bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag, dev)
+    idxs = _randint(0, bg.N_comp - 1, n, dev)
+    cfr = bg.fluxratios[idxs]
+    lnprior = _background_prior(bg, n, dev, contrast_curve_file,
+                                2.5 * torch.log10(cfr / (1 - cfr)), bg.dmag(filt)[idxs])
+    return _run_eb(eng, dev, n, int(N), M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps,
+                   masses, radii, fluxratios, cfr, lnprior, None, False)
+
+
+def lnZ_BTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Tmag, Jmag, Hmag, Kmag, trilegal_fname,
+            contrast_curve_file=None, filt="TESS", N=1000000, parallel=False, mission="TESS",
+            flatpriors=False, exptime=0.00139, nsamples=20):
+    eng, dev, n = _begin(time, flux, sigma, exptime, nsamples, int(N))
+    P, P_mean = _periods(P_orb, n, dev)
+    bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag, dev)
+    radii_comp = bg.radii()
+    u1c, u2c = bg.ldc(mission)
+    idxs = _randint(0, bg.N_comp, n, dev)
+    cfr = bg.fluxratios[idxs]
+    lnprior = _background_prior(bg, n, dev, contrast_curve_file,
+                                2.5 * torch.log10(cfr / (1 - cfr)), bg.dmag(filt)[idxs])
+    host_masses = bg.masses[idxs]
+    rps, incs, eccs, argps = _draw_planet(n, host_masses, flatpriors, P_mean, dev)
+    extra = (bg.loggs[idxs] >= 3.5) & (bg.Teffs[idxs] <= 10000)
+    return _run_tp(eng, dev, n, int(N), host_masses, radii_comp[idxs], u1c[idxs], u2c[idxs], P,
+                   host_masses, rps, incs, eccs, argps, cfr, lnprior, extra, True)
+
+
+def lnZ_BEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Tmag, Jmag, Hmag, Kmag, trilegal_fname,
+            contrast_curve_file=None, filt="TESS", N=1000000, parallel=False, mission="TESS",
+            flatpriors=False, exptime=0.00139, nsamples=20):
+    eng, dev, n = _begin(time, flux, sigma, exptime, nsamples, int(N))
+    P, P_mean = _periods(P_orb, n, dev)
+    incs, qs, eccs, argps = _draw_binary(n, M_s, P_mean, dev)
+    bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag, dev)
+    radii_comp = bg.radii()
+    u1c, u2c = bg.ldc(mission)
+    idxs = _randint(0, bg.N_comp, n, dev)
+    host_masses, host_radii = bg.masses[idxs], radii_comp[idxs]
+    cfr = bg.fluxratios[idxs]
+    masses = qs * host_masses
+    radii, _ = dp.stellar_relations(masses, host_radii, bg.Teffs[idxs])
+
+    def distance_corrected(band):
+        cfr_band = bg.fluxratios_in(band)[idxs]
+        bound = _fluxratio(host_masses, M_s, band)
+        return _fluxratio(masses, M_s, band) * (cfr_band / bound), cfr_band
+
+    fluxratios, _ = distance_corrected("TESS")
+    if contrast_curve_file is None:
+        dmag = 2.5 * torch.log10((cfr / (1 - cfr)) + (fluxratios / (1 - fluxratios)))
+        lnprior = _background_prior(bg, n, dev, None, dmag, None)
+    else:
+        fr_cc, cfr_cc = distance_corrected(filt if filt in ("J", "H", "K") else "TESS")
+        dmag = 2.5 * torch.log10((cfr_cc / (1 - cfr_cc)) + (fr_cc / (1 - fr_cc)))
+        lnprior = _background_prior(bg, n, dev, contrast_curve_file, None, dmag)
+    extra = (bg.loggs[idxs] >= 3.5) & (bg.Teffs[idxs] <= 10000)
+    return _run_eb(eng, dev, n, int(N), host_masses, host_radii, u1c[idxs], u2c[idxs], P,
+                   host_masses + masses, incs, qs, eccs, argps, masses, radii, fluxratios, cfr,
+                   lnprior, extra, True)

@@ -175,6 +175,88 @@ class Engine:
                                   outs[b][2], b)
                      for b in range(2))
 
+    # ------------------------------------------------------------------ L2 seam, device columns
+    def _tensor_col(self, x, N, keep):
+        """torch CUDA float64 tensor of N values (stride 1) or scalar (stride 0) -> tri_col."""
+        import torch
+        if x is None:
+            return tri_col(None, 0)
+        if torch.is_tensor(x) and x.ndim == 1 and x.numel() == N and N != 1:
+            t = x.contiguous()
+            if t.dtype != torch.float64:
+                t = t.double()
+            stride = 1
+        else:
+            t = torch.as_tensor(x, dtype=torch.float64, device=self._torch_device()).reshape(-1)
+            if t.numel() != 1 and t.numel() != N:
+                raise ValueError("column has %d values, expected %d" % (t.numel(), N))
+            t = t.to(self._torch_device()).contiguous()
+            stride = 0 if t.numel() == 1 and N != 1 else 1
+        keep.append(t)
+        return tri_col(t.data_ptr(), stride)
+
+    def _torch_device(self):
+        import torch
+        return torch.device("cuda", self.device)
+
+    def _tensor_result(self, N, n_best, keep):
+        import torch
+        r = tri_result()
+        ti = torch.zeros(max(n_best, 1), dtype=torch.int64, device=self._torch_device())
+        tv = torch.full((max(n_best, 1),), -math.inf, dtype=torch.float64,
+                        device=self._torch_device())
+        keep += [ti, tv]
+        r.top_cap = n_best
+        r.top_idx, r.top_lnL = ti.data_ptr(), tv.data_ptr()
+        return r, ti, tv
+
+    @staticmethod
+    def _sorted_top(r, ti, tv):
+        """Device-pointer calls return the candidates unsorted: best first, ties by index."""
+        k = int(r.n_top)
+        idx = ti[:k].cpu().numpy()
+        val = tv[:k].cpu().numpy()
+        order = np.lexsort((idx, -val))
+        return idx[order], val[order]
+
+    def _eval_tensors(self, kind, N, cols, extra_mask, companion_is_host, n_best):
+        import torch
+        N = int(N)
+        keep = []
+        a = tri_tp_args() if kind == "tp" else tri_eb_args()
+        a.N = N
+        for name, val in cols.items():
+            setattr(a, name, self._tensor_col(val, N, keep))
+        if extra_mask is not None:
+            m = extra_mask.to(torch.uint8).contiguous()
+            if bool(m.all()):
+                m = None
+            else:
+                keep.append(m)
+                a.extra_mask = m.data_ptr()
+        a.companion_is_host = int(bool(companion_is_host))
+        nb = 1 if kind == "tp" else 2
+        rr = (tri_result * nb)()
+        tops = []
+        for b in range(nb):
+            rr[b], ti, tv = self._tensor_result(N, n_best, keep)
+            tops.append((ti, tv))
+        stream = torch.cuda.current_stream(self._torch_device()).cuda_stream
+        fn = self.lib.tri_eval_tp_dev if kind == "tp" else self.lib.tri_eval_eb_dev
+        _cabi.check(fn(ctypes.byref(a), rr, ctypes.c_void_p(stream)))
+        out = []
+        for b in range(nb):
+            out.append(BranchResult(rr[b], N, None, None, self._sorted_top(rr[b], *tops[b]), b))
+        return out
+
+    def eval_tp_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
+        """tri_eval_tp_dev on torch CUDA tensors (columns: rp, P_orb, inc, ecc, argp, mtot, rhost,
+        u1, u2, cfr, lnprior; tensors of N values or scalars)."""
+        return self._eval_tensors("tp", N, cols, extra_mask, companion_is_host, n_best)[0]
+
+    def eval_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
+        return tuple(self._eval_tensors("eb", N, cols, extra_mask, companion_is_host, n_best))
+
     # ------------------------------------------------------------------ L1 seam
     def lnl_tp(self, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr, companion_is_host):
         n = int(np.size(R_p))

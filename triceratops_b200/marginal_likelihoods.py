@@ -30,6 +30,12 @@ from .priors import (lnprior_background, lnprior_bound_EB, lnprior_bound_TP, sam
 
 np.seterr(divide='ignore')
 
+_SAMPLER = {"mode": "host"}
+
+
+def _sampler_mode():
+    return _SAMPLER["mode"]
+
 N_SAMPLES = 100
 
 __all__ = ["lnZ_TTP", "lnZ_TEB", "lnZ_PTP", "lnZ_PEB", "lnZ_STP", "lnZ_SEB", "lnZ_DTP",
@@ -224,6 +230,9 @@ def lnZ_TTP(time: np.ndarray, flux: np.ndarray, sigma: float,
             exptime: float = 0.00139, nsamples: int = 20):
     """Transiting planet on the target star (marginal_likelihoods.py:39-172).  Also used for a
     nearby star (NTP) by calc_probs."""
+    if _sampler_mode() == "device":
+        from . import device_sampler
+        return device_sampler.lnZ_TTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
     _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
@@ -247,6 +256,9 @@ def lnZ_TEB(time: np.ndarray, flux: np.ndarray, sigma: float,
             exptime: float = 0.00139, nsamples: int = 20):
     """Eclipsing binary on the target star, periods P and 2P (marginal_likelihoods.py:175-383).
     Also used for a nearby star (NEB, NEBx2P) by calc_probs."""
+    if _sampler_mode() == "device":
+        from . import device_sampler
+        return device_sampler.lnZ_TEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
     _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
@@ -269,6 +281,9 @@ def lnZ_PTP(time: np.ndarray, flux: np.ndarray, sigma: float,
             exptime: float = 0.00139, nsamples: int = 20,
             molusc_file: str = None):
     """Planet on the target, diluted by an unresolved bound companion (:386-586)."""
+    if _sampler_mode() == "device":
+        from . import device_sampler
+        return device_sampler.lnZ_PTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples, molusc_file)
     N = int(N)
     _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
@@ -297,6 +312,9 @@ def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
             exptime: float = 0.00139, nsamples: int = 20,
             molusc_file: str = None):
     """EB on the target, diluted by an unresolved bound companion (:589-866)."""
+    if _sampler_mode() == "device":
+        from . import device_sampler
+        return device_sampler.lnZ_PEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples, molusc_file)
     N = int(N)
     _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
@@ -338,6 +356,9 @@ def lnZ_STP(time: np.ndarray, flux: np.ndarray, sigma: float,
             exptime: float = 0.00139, nsamples: int = 20,
             molusc_file: str = None):
     """Planet on an unresolved bound companion of the target (:869-1077)."""
+    if _sampler_mode() == "device":
+        from . import device_sampler
+        return device_sampler.lnZ_STP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples, molusc_file)
     N = int(N)
     _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
@@ -365,6 +386,9 @@ def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
             exptime: float = 0.00139, nsamples: int = 20,
             molusc_file: str = None):
     """EB on an unresolved bound companion of the target (:1080-1376)."""
+    if _sampler_mode() == "device":
+        from . import device_sampler
+        return device_sampler.lnZ_SEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples, molusc_file)
     N = int(N)
     _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
@@ -400,6 +424,9 @@ def lnZ_DTP(time: np.ndarray, flux: np.ndarray, sigma: float,
             mission: str = "TESS", flatpriors: bool = False,
             exptime: float = 0.00139, nsamples: int = 20):
     """Planet on the target, diluted by a chance-aligned background star (:1379-1568)."""
+    if _sampler_mode() == "device":
+        from . import device_sampler
+        return device_sampler.lnZ_DTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, Tmag, Jmag, Hmag, Kmag, trilegal_fname, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
     _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
@@ -423,6 +450,9 @@ def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
             mission: str = "TESS", flatpriors: bool = False,
             exptime: float = 0.00139, nsamples: int = 20):
     """EB on the target, diluted by a chance-aligned background star (:1571-1837)."""
+    if _sampler_mode() == "device":
+        from . import device_sampler
+        return device_sampler.lnZ_DEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, Tmag, Jmag, Hmag, Kmag, trilegal_fname, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
     _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
@@ -449,6 +479,9 @@ def lnZ_BTP(time: np.ndarray, flux: np.ndarray, sigma: float,
             mission: str = "TESS", flatpriors: bool = False,
             exptime: float = 0.00139, nsamples: int = 20):
     """Planet on a chance-aligned background star (:1840-2035)."""
+    if _sampler_mode() == "device":
+        from . import device_sampler
+        return device_sampler.lnZ_BTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Tmag, Jmag, Hmag, Kmag, trilegal_fname, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
     _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
@@ -475,6 +508,9 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
             mission: str = "TESS", flatpriors: bool = False,
             exptime: float = 0.00139, nsamples: int = 20):
     """EB on a chance-aligned background star (:2038-2362)."""
+    if _sampler_mode() == "device":
+        from . import device_sampler
+        return device_sampler.lnZ_BEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Tmag, Jmag, Hmag, Kmag, trilegal_fname, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
     _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
