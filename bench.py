@@ -391,6 +391,7 @@ def run_ours(args):
         "param_stream_GBs": param_bytes / (ms_total * 1e-3) / 1e9,
         "hbm_peak_GBs": _measured_peaks().get("hbm_gbs"),
         "traffic": _profiled_traffic(),
+        "ncu_fp64_pipe_busy": _profiled("ncu_fp64_pipe_busy_pct"),
         "traffic_source": "profiles/r01_traffic.json (dram bytes read+write per launch, one ncu "
                           "--set full capture at N = 1e6)",
     }
@@ -437,12 +438,16 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def _profiled_traffic():
+def _profiled(key):
+    """Numbers that only a profiler can give (ncu capture summarised under profiles/)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[
-            "traffic_bytes_per_launch"]
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]
     except Exception:
         return None
+
+
+def _profiled_traffic():
+    return _profiled("traffic_bytes_per_launch")
 
 
 def _measured_peaks():
