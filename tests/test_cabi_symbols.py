@@ -55,3 +55,11 @@ def test_engine_raises_without_gpu():
     from triceratops_b200.engine import Engine
     with pytest.raises(_cabi.TriError):
         Engine(0)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: without the built CUDA library the package refuses to load."""
+    monkeypatch.setenv("TRI_B200_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_cabi, "_lib", None)
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _cabi.load()

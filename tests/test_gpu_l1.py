@@ -147,3 +147,23 @@ def test_bad_light_curve_is_rejected(gpu_engine):
         gpu_engine.set_lightcurve(t, np.ones(2), 1e-3, 0.0, 1)
     with pytest.raises(TriError):
         gpu_engine.set_lightcurve(np.zeros(3), np.ones(3), -1.0, 0.0, 1)
+
+
+def test_shutdown_and_reinit(gpu_engine, toi465_lc):
+    """tri_shutdown frees the context; the next call must say so, and tri_init restores it."""
+    import ctypes
+    from triceratops_b200 import _cabi
+    t, f, s = toi465_lc
+    d = draws(np.random.default_rng(12), 50, TOI465)
+    before = lk.lnL_TP_p(t, f, s, *tp_args(d), False)
+    lib = gpu_engine.lib
+    assert lib.tri_shutdown() == 0
+    n = ctypes.c_int32()
+    assert lib.tri_sm_count(ctypes.byref(n)) == _cabi.TRI_ESTATE
+    assert lib.tri_init(gpu_engine.device) == 0
+    gpu_engine._lc_key = None                       # the light curve went with the context
+    after = lk.lnL_TP_p(t, f, s, *tp_args(d), False)
+    assert np.array_equal(before, after)
+    with pytest.raises(RuntimeError):
+        from triceratops_b200.engine import get_engine
+        get_engine(gpu_engine.device + 1)           # one process drives one GPU

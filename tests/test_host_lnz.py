@@ -119,3 +119,20 @@ def test_unknown_star_without_similar_trilegal_stars(oracle_engine, toi465_lc, t
     assert res["lnZ"] == -np.inf and "b" not in res and res["M_s"] == 0
     res = ml.lnZ_NEB_unknown(t, f, s, 3.8, 40.0, trilegal_file, 100, True)
     assert isinstance(res, dict) and res["lnZ"] == -np.inf and res["b"] == 0
+
+
+def test_calc_probs_drops_nan_stamps_like_the_reference(oracle_engine, toi465_lc, trilegal_file):
+    """triceratops.py:709-711: NaN time/flux stamps are removed before anything else."""
+    from oracle import synth
+    from triceratops_b200.triceratops import target
+    t, f, s = toi465_lc
+    stars = synth.stars_table(5, 10.7, 9.9, 9.5, 9.3, 0.811, 0.847, 4936.0, 8.16, n_neighbours=0)
+    keep = ["TP"]
+    drop = [k for k in ("EB", "PTP", "PEB", "STP", "SEB", "DTP", "DEB", "BTP", "BEB")]
+    out = []
+    for tt, ff in ((t, f), (np.append(t, [np.nan, 0.01]), np.append(f, [1.0, np.nan]))):
+        tgt = target(5, stars=stars, trilegal_fname=trilegal_file)
+        np.random.seed(9)
+        tgt.calc_probs(tt, ff, s, 3.836169, N=500, parallel=True, drop_scenario=drop, verbose=0)
+        out.append(tgt.lnZ[0])
+    assert np.isfinite(out[0]) and out[0] == out[1]
