@@ -93,7 +93,7 @@ class _Recorder:
 
 
 def make_target():
-    from oracle import synth
+    from triceratops_b200 import synthetic as synth
     from triceratops_b200.triceratops import target
     lc = np.loadtxt(os.path.join(GOLD, "TOI465_01_lightcurve.csv"), delimiter=",")
     t, f, s = lc[:, 0].copy(), lc[:, 1].copy(), float(np.mean(lc[:, 2]))

@@ -28,7 +28,8 @@ ROOT = os.path.dirname(HERE)
 GOLD = os.path.join(ROOT, "tests", "golden")
 sys.path.insert(0, ROOT)
 
-from oracle import quadmodel, refhost, synth  # noqa: E402
+from oracle import quadmodel, refhost  # noqa: E402
+from triceratops_b200 import synthetic as synth  # noqa: E402
 
 TOI465 = dict(P=3.836169, M=0.811, R=0.84738, Teff=4936.0, plx=8.16366,
               T=10.7307, J=9.906, H=9.473, K=9.339)

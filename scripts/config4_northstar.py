@@ -33,11 +33,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import triceratops_b200
-    from oracle import coracle, synth
+    from triceratops_b200 import synthetic as synth
+    from triceratops_b200._constants import Rearth, Rsun
+    from triceratops_b200.likelihoods import simulate_TP_transit
     from triceratops_b200.triceratops import target
     t = np.linspace(-0.5, 0.5, 20000)
-    f = coracle.model(t, 0.05, 10.0, 15.0, np.arccos(0.3 / 15.0), 0.0, np.pi / 2, 0.4, 0.2,
-                      0.00139, 20) + np.random.default_rng(1234).normal(0, 1e-3, t.size)
+    # injected planet: k = 0.05, a/R* = 15, b = 0.3, circular, u = (0.4, 0.2), P = 10 d
+    f = simulate_TP_transit(t, 0.05 * Rsun / Rearth, 10.0, np.degrees(np.arccos(0.3 / 15.0)),
+                            15.0 * Rsun, 1.0, 0.4, 0.2, 0.0, 0.0)
+    f = f + np.random.default_rng(1234).normal(0, 1e-3, t.size)
     stars = synth.stars_table(1, 10.0, 9.2, 8.9, 8.8, 1.0, 1.0, 5750.0, 10.0)
     gold = os.path.join(ROOT, "tests", "golden")
     tgt = target(1, stars=stars, trilegal_fname=os.path.join(gold, "trilegal_synth.csv"))

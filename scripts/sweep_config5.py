@@ -3,7 +3,7 @@
     python scripts/sweep_config5.py --tois 64 --draws 1000000 --workers-per-gpu 8
 
 Each synthetic TOI: seeded stellar parameters, a 200-stamp folded light curve with an injected
-planet transit (CPU oracle model, generation only) plus white noise, a stars table with the
+planet transit (the engine's own simulate_TP_transit) plus white noise, a stars table with the
 target alone, the shared synthetic TRILEGAL population.  Prints one JSON line with the sweep
 throughput (TOIs/s and samples*points/s).
 """
@@ -20,7 +20,9 @@ sys.path.insert(0, ROOT)
 
 
 def make_jobs(n, draws, seed=5):
-    from oracle import coracle, synth
+    from triceratops_b200 import synthetic as synth
+    from triceratops_b200._constants import Rearth, Rsun
+    from triceratops_b200.likelihoods import simulate_TP_transit
     rng = np.random.default_rng(seed)
     tri = os.path.join(ROOT, "tests", "golden", "trilegal_synth.csv")
     jobs = []
@@ -34,8 +36,9 @@ def make_jobs(n, draws, seed=5):
         b = rng.uniform(0, 0.8)
         t = np.linspace(-0.12, 0.12, 200)
         sig = float(rng.uniform(3e-4, 2e-3))
-        f = coracle.model(t, k, P, a_rs, np.arccos(b / a_rs), 0.0, np.pi / 2, 0.4, 0.25, 0.00139,
-                          20) + rng.normal(0, sig, t.size)
+        f = simulate_TP_transit(t, k * R * Rsun / Rearth, P, np.degrees(np.arccos(b / a_rs)),
+                                a_rs * R * Rsun, R, 0.4, 0.25, 0.0, 0.0) \
+            + rng.normal(0, sig, t.size)
         Tmag = rng.uniform(9, 12)
         stars = synth.stars_table(1000 + i, Tmag, Tmag - 0.8, Tmag - 1.2, Tmag - 1.3, M, R, Teff,
                                   rng.uniform(3, 20), n_neighbours=0)

@@ -7,7 +7,7 @@ from conftest import TOI465
 
 
 def _job(toi465_lc, trilegal_file, seed=3, N=400):
-    from oracle import synth
+    from triceratops_b200 import synthetic as synth
     t, f, s = toi465_lc
     stars = synth.stars_table(77, TOI465["T"], TOI465["J"], TOI465["H"], TOI465["K"],
                               TOI465["M"], TOI465["R"], TOI465["Teff"], TOI465["plx"],

@@ -218,7 +218,7 @@ def test_device_and_host_evidences_agree_within_monte_carlo_scatter(gpu_engine, 
 @pytest.mark.gpu
 def test_device_mode_calc_probs_runs_and_is_reproducible(gpu_engine, toi465_lc, trilegal_file,
                                                          contrast_file):
-    from oracle import synth
+    from triceratops_b200 import synthetic as synth
     from triceratops_b200.triceratops import target
     t, f, s = toi465_lc
     stars = synth.stars_table(270380593, TOI465["T"], TOI465["J"], TOI465["H"], TOI465["K"],

@@ -36,7 +36,7 @@ def test_kepler_long_cadence(name, gpu_engine, golden, kepler10b_lc, trilegal_fi
 
 def test_calc_probs_matches_reference_fixture(gpu_engine, golden, toi465_lc, trilegal_file,
                                               contrast_file):
-    from oracle import synth
+    from triceratops_b200 import synthetic as synth
     from triceratops_b200.triceratops import target
     g = golden("calc_probs.npz")
     t, f, s = toi465_lc

@@ -61,7 +61,7 @@ def test_molusc_padding_masks_missing_companions(oracle_engine, toi465_lc, tmp_p
 
 def test_calc_probs_reproduces_reference(oracle_engine, golden, toi465_lc, trilegal_file,
                                          contrast_file):
-    from oracle import synth
+    from triceratops_b200 import synthetic as synth
     from triceratops_b200.triceratops import target
     g = golden("calc_probs.npz")
     t, f, s = toi465_lc
@@ -83,7 +83,7 @@ def test_calc_probs_reproduces_reference(oracle_engine, golden, toi465_lc, trile
 
 
 def test_calc_probs_drop_scenario_and_degenerate_warning(oracle_engine, toi465_lc, trilegal_file):
-    from oracle import synth
+    from triceratops_b200 import synthetic as synth
     from triceratops_b200.triceratops import target
     t, f, s = toi465_lc
     stars = synth.stars_table(1, 10.7, 9.9, 9.5, 9.3, 0.811, 0.847, 4936.0, 8.16, n_neighbours=0)
@@ -123,7 +123,7 @@ def test_unknown_star_without_similar_trilegal_stars(oracle_engine, toi465_lc, t
 
 def test_calc_probs_drops_nan_stamps_like_the_reference(oracle_engine, toi465_lc, trilegal_file):
     """triceratops.py:709-711: NaN time/flux stamps are removed before anything else."""
-    from oracle import synth
+    from triceratops_b200 import synthetic as synth
     from triceratops_b200.triceratops import target
     t, f, s = toi465_lc
     stars = synth.stars_table(5, 10.7, 9.9, 9.5, 9.3, 0.811, 0.847, 4936.0, 8.16, n_neighbours=0)

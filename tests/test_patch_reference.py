@@ -13,7 +13,7 @@ pytestmark = pytest.mark.skipif(not refhost.available(), reason="reference tree 
 def test_patch_lnz_level_routes_reference_calc_probs(oracle_engine, golden, toi465_lc,
                                                      trilegal_file, contrast_file):
     import triceratops_b200
-    from oracle import synth
+    from triceratops_b200 import synthetic as synth
     ref = refhost.load()
     g = golden("calc_probs.npz")
     t, f, s = toi465_lc

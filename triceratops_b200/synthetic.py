@@ -1,6 +1,7 @@
-"""ORACLE/TEST infrastructure: seeded synthetic inputs that stand in for the reference's network
-queries (TRILEGAL population table, stars table) -- SURVEY.md section 8d configs 2-4.  No
-MAST/Gaia/TRILEGAL access exists offline, so these tables are generated, not downloaded."""
+"""Seeded synthetic inputs that stand in for the reference's network queries: a TRILEGAL-like
+background-population table and a TIC-like stars table.
+There is no MAST/Gaia/TRILEGAL access offline, so benchmarks, tests and examples generate these
+tables instead of downloading them.  No compute lives here."""
 import numpy as np
 import pandas as pd
 
