@@ -5,16 +5,18 @@ scenario table layout (15 target-star rows + 3 per nearby star with tdepth > 0),
 (`probs`, `lnZ`, `FPP`, `NFPP`, `FPP_degenerate`, `star_num`, `u1`, `u2`, `fluxratio_EB`,
 `fluxratio_comp`) and warnings.
 
-The rest of the reference's `target` class -- TIC/Gaia/TessCut queries in __init__, plotting,
-aperture bookkeeping, calc_depths -- is outside this package's scope (SURVEY.md section 2 rows
-8-11): there is no network here, so a `target` is built from a stars table the caller already
-has (the reference's `target.stars` DataFrame, e.g. saved from an online session) and a saved
-TRILEGAL file.
+`calc_depths` (triceratops.py:559-671), which produces the `fluxratio` / `tdepth` columns
+calc_probs reads, is included as host numpy.  The rest of the reference's `target` class --
+TIC/Gaia/TessCut queries in __init__, plotting, star-table bookkeeping -- is outside this
+package's scope: there is no network here, so a `target` is built
+from a stars table the caller already has (the reference's `target.stars` DataFrame, e.g. saved
+from an online session), optionally its `pix_coords`, and a saved TRILEGAL file.
 """
 import warnings
 
 import numpy as np
 from pandas import DataFrame
+from scipy.special import ndtr
 
 from ._numerics import _normalize_probabilities
 from .funcs import renorm_flux
@@ -46,20 +48,29 @@ _TARGET_SCENARIOS = (
 class target:
     def __init__(self, ID: int, sectors=None, search_radius: int = 10, mission: str = "TESS",
                  lightkurve_cache_dir=None, trilegal_fname=None, ra: float = None,
-                 dec: float = None, verify_ssl: bool = True, stars: DataFrame = None):
+                 dec: float = None, verify_ssl: bool = True, stars: DataFrame = None,
+                 pix_coords=None):
         """Offline constructor: same leading arguments as the reference (triceratops.py:42-45)
         plus `stars`, the table the reference would have assembled from TIC (one row per star,
         target first, columns ID, Tmag, Jmag, Hmag, Kmag, ra, dec, mass, rad, Teff, plx,
-        fluxratio, tdepth)."""
+        fluxratio, tdepth).  `pix_coords` (optional, one [n_stars, 2] array of pixel positions
+        per sector, the reference's `target.pix_coords`) enables `calc_depths`."""
         if mission != "TESS" and mission != "Kepler" and mission != "K2":
             raise ValueError("Introduced invalid mission: " + mission)
         if stars is None:
             raise NotImplementedError(
                 "catalogue queries are outside triceratops_b200 (no network): pass the stars "
                 "table as target(..., stars=DataFrame)")
+        stars = stars.copy()
+        if pix_coords is not None:
+            for c in ("fluxratio", "tdepth"):       # filled by calc_depths
+                if c not in stars.columns:
+                    stars[c] = 0.0
         missing = [c for c in _STAR_COLUMNS if c not in stars.columns]
         if missing:
             raise ValueError("stars table lacks columns: " + ", ".join(missing))
+        self.pix_coords = None if pix_coords is None else [np.asarray(p, float)
+                                                           for p in pix_coords]
         self.ID = ID
         self.mission = mission
         self.sectors = sectors
@@ -68,6 +79,51 @@ class target:
         self.stars = stars.reset_index(drop=True)
         self.trilegal_fname = trilegal_fname
         self.trilegal_url = None
+
+    def calc_depths(self, tdepth: float, all_ap_pixels=None):
+        """Flux ratio of every star inside the photometric aperture(s) and the transit depth
+        each would need to cause the observed one (reference triceratops.py:559-671): circular
+        Gaussian PSF of 0.75 px integrated analytically over each aperture pixel, averaged over
+        apertures.  Fills stars["fluxratio"] and stars["tdepth"], the inputs of calc_probs."""
+        if self.pix_coords is None:
+            raise RuntimeError("calc_depths needs pix_coords (pass them to target())")
+        if all_ap_pixels is None:
+            print("No apertures provided, assuming 5x5 centered on target.")
+            all_ap_pixels = []
+            for pc in self.pix_coords:
+                c = np.round(pc[0])
+                all_ap_pixels.append(np.array([
+                    np.repeat(np.arange(c[0] - 2, c[0] + 3, 1), 5),
+                    np.tile(np.arange(c[1] - 2, c[1] + 3, 1), 5)]).T)
+        sigma = 0.75
+        Tmag = self.stars.Tmag.values
+        A = 10 ** ((np.min(Tmag) - Tmag) / 2.5)        # flux relative to the brightest star
+        ratios = np.zeros([len(all_ap_pixels), len(self.stars)])
+        for k, pixels in enumerate(all_ap_pixels):
+            pixels = np.array(pixels)
+            mu = self.pix_coords[k]
+            # separable pixel-box integral: [stars, pixels]
+            gx = (ndtr((pixels[None, :, 0] + 0.5 - mu[:, None, 0]) / sigma)
+                  - ndtr((pixels[None, :, 0] - 0.5 - mu[:, None, 0]) / sigma))
+            gy = (ndtr((pixels[None, :, 1] + 0.5 - mu[:, None, 1]) / sigma)
+                  - ndtr((pixels[None, :, 1] - 0.5 - mu[:, None, 1]) / sigma))
+            rel = np.array([A[i] * np.sum(gx[i] * gy[i]) for i in range(len(A))])
+            ratios[k, :] = rel / np.sum(rel)
+        flux_ratios = np.mean(ratios, axis=0)
+        self.stars["fluxratio"] = flux_ratios
+        tdepths = np.zeros(len(self.stars))
+        nz = flux_ratios != 0
+        tdepths[nz] = 1 - (flux_ratios[nz] - tdepth) / flux_ratios[nz]
+        tdepths[tdepths > 1] = 0
+        self.stars["tdepth"] = tdepths
+        hosts = self.stars[self.stars["tdepth"] > 0]
+        for i, ID in enumerate(hosts["ID"].values):
+            need = ["mass", "rad", "Teff"] + (["plx"] if i == 0 else [])
+            if any(np.isnan(hosts[c].values[i]) for c in need):
+                print("WARNING: " + str(ID) + " is missing stellar properties"
+                      + (" required for validation." if i == 0
+                         else "; Solar values will be assumed."))
+        return
 
     def calc_probs(self, time: np.ndarray, flux_0: np.ndarray,
                    flux_err_0: float, P_orb,
