@@ -7,7 +7,6 @@ Sharding follows SURVEY.md section 8e: every rank makes the same host draws (sam
 evaluates the contiguous slice [r*N/G, (r+1)*N/G), and one all-gather of a 206-double record per
 scenario branch replaces any exchange of per-draw data.
 """
-import math
 
 import numpy as np
 

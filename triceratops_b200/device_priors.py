@@ -27,7 +27,7 @@ import numpy as np
 import torch
 
 from . import funcs
-from ._constants import G, Msun, Rsun, au, pi
+from ._constants import G, Msun, au, pi
 
 F64 = torch.float64
 

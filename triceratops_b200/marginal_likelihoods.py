@@ -22,7 +22,7 @@ import numpy as np
 from pandas import read_csv
 
 from . import _dispatch
-from ._constants import G, Msun, Rearth, Rsun, pi
+from ._constants import G, Msun, Rsun, pi
 from ._ldc import grid_for
 from .funcs import (file_to_contrast_curve, flux_relation, stellar_relations, trilegal_results)
 from .priors import (lnprior_background, lnprior_bound_EB, lnprior_bound_TP, sample_ecc,
