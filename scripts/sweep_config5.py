@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def make_jobs(n, draws, seed=5):
+def make_jobs(n, draws, seed=5, sampler="host"):
     from triceratops_b200 import synthetic as synth
     from triceratops_b200._constants import Rearth, Rsun
     from triceratops_b200.likelihoods import simulate_TP_transit
@@ -43,7 +43,8 @@ def make_jobs(n, draws, seed=5):
         stars = synth.stars_table(1000 + i, Tmag, Tmag - 0.8, Tmag - 1.2, Tmag - 1.3, M, R, Teff,
                                   rng.uniform(3, 20), n_neighbours=0)
         jobs.append(dict(ID=1000 + i, stars=stars, trilegal_fname=tri, time=t, flux=f,
-                         flux_err=sig, P_orb=P, seed=100 + i, calc_probs=dict(N=draws)))
+                         flux_err=sig, P_orb=P, seed=100 + i, sampler=sampler,
+                         calc_probs=dict(N=draws)))
     return jobs
 
 
@@ -53,9 +54,10 @@ def main():
     ap.add_argument("--draws", type=int, default=1_000_000)
     ap.add_argument("--workers-per-gpu", type=int, default=8)
     ap.add_argument("--gpus", type=int, default=None)
+    ap.add_argument("--sampler", choices=("host", "device"), default="host")
     args = ap.parse_args()
     from triceratops_b200.batch import vet_many
-    jobs = make_jobs(args.tois, args.draws)
+    jobs = make_jobs(args.tois, args.draws, sampler=args.sampler)
     t0 = time.perf_counter()
     res = vet_many(jobs, n_gpus=args.gpus, workers_per_gpu=args.workers_per_gpu)
     dt = time.perf_counter() - t0
@@ -65,7 +67,8 @@ def main():
                     "scenario, 15 scenario rows each" % (args.tois, args.draws),
         "wall_s": dt, "tois_per_s": args.tois / dt,
         "samples_points_per_s": rows * args.draws * 200 / dt,
-        "workers_per_gpu": args.workers_per_gpu,
+        "workers_per_gpu": args.workers_per_gpu, "sampler": args.sampler,
+        "n_gpus": args.gpus,
         "mean_job_wall_s": float(np.mean([r["wall_s"] for r in res])),
         "FPP_median": float(np.median([r["FPP"] for r in res])),
     }))

@@ -48,3 +48,21 @@ def test_vet_many_spawns_workers_and_keeps_job_order(gpu_engine, toi465_lc, tril
     assert [r["ID"] for r in res] == [100, 101, 102]
     again = run_job(jobs[1])                     # same seed, this process: same answer
     np.testing.assert_allclose(res[1]["lnZ"], again["lnZ"], rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_device_sampler_jobs_are_reproducible_and_agree_with_host_draws(gpu_engine, toi465_lc,
+                                                                        trilegal_file):
+    """"sampler": "device" draws the priors in HBM: same seed -> same answer, and the scenario
+    evidences agree with the host-drawn ones within Monte-Carlo scatter."""
+    from triceratops_b200 import marginal_likelihoods as ml
+    from triceratops_b200.batch import run_job
+    job = dict(_job(toi465_lc, trilegal_file, seed=11, N=200000), sampler="device")
+    a, b = run_job(job), run_job(job)
+    np.testing.assert_array_equal(a["lnZ"], b["lnZ"])
+    assert ml._SAMPLER["mode"] == "host"         # restored after the job
+    host = run_job(dict(job, sampler="host"))
+    probable = np.asarray(host["probs"]["prob"]) > 1e-2      # the rows that carry the answer
+    assert probable.any() and np.all(np.isfinite(a["lnZ"][probable]))
+    assert np.max(np.abs(a["lnZ"][probable] - host["lnZ"][probable])) < 1.0
+    assert abs(a["FPP"] - host["FPP"]) < 0.1

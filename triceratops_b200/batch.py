@@ -9,7 +9,11 @@ job list over ranks instead (`jobs[rank::world]`).
 
 A job is a dict with the arguments of `target(...)` and `calc_probs(...)`:
     {"ID": 123, "stars": DataFrame, "trilegal_fname": "...", "time": t, "flux": f,
-     "flux_err": sigma, "P_orb": 3.2, "seed": 7, "calc_probs": {"N": 1_000_000, ...}}
+     "flux_err": sigma, "P_orb": 3.2, "seed": 7, "calc_probs": {"N": 1_000_000, ...},
+     "sampler": "host" | "device"}
+"sampler" picks where the prior draws are made for that job (`set_sampler`): "host" (default)
+reproduces the reference's numpy streams for the job's seed; "device" draws in HBM, which removes
+most of the host work and makes the sweep GPU-bound.
 The result per job is {"ID", "FPP", "NFPP", "FPP_degenerate", "lnZ", "probs" (DataFrame as dict),
 "wall_s"}.
 """
@@ -23,6 +27,7 @@ import numpy as np
 def run_job(job):
     """One target through the drop-in `target.calc_probs` on this process's engine."""
     from .triceratops import target
+    from . import set_sampler
     t0 = _time.perf_counter()
     tgt = target(job["ID"], stars=job["stars"], trilegal_fname=job.get("trilegal_fname"),
                  mission=job.get("mission", "TESS"))
@@ -30,8 +35,13 @@ def run_job(job):
         np.random.seed(job["seed"])
     kw = dict(parallel=True, verbose=0)
     kw.update(job.get("calc_probs", {}))
-    tgt.calc_probs(np.asarray(job["time"], float), np.asarray(job["flux"], float),
-                   job["flux_err"], job["P_orb"], **kw)
+    sampler = job.get("sampler", "host")
+    try:
+        set_sampler(sampler, seed=job.get("seed"))
+        tgt.calc_probs(np.asarray(job["time"], float), np.asarray(job["flux"], float),
+                       job["flux_err"], job["P_orb"], **kw)
+    finally:
+        set_sampler("host")
     return {"ID": job["ID"], "FPP": float(tgt.FPP), "NFPP": float(tgt.NFPP),
             "FPP_degenerate": bool(tgt.FPP_degenerate), "lnZ": np.asarray(tgt.lnZ),
             "probs": tgt.probs.to_dict(orient="list"), "wall_s": _time.perf_counter() - t0}
