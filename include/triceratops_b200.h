@@ -27,6 +27,8 @@ extern "C" {
 #define TRI_ESTATE (-3)     /* tri_init / tri_set_lightcurve not called             */
 #define TRI_ENODEVICE (-4)  /* no CUDA device: there is no CPU fallback             */
 
+#define TRI_MAX_INFLIGHT 4  /* evaluations that may be queued before one is waited for */
+
 /* A per-draw column: stride 1 = array of N values, stride 0 = one value used for every draw
  * (the reference broadcasts scalars with np.full(N, x), e.g. marginal_likelihoods.py:125-128). */
 typedef struct {
@@ -77,7 +79,7 @@ typedef struct {
     int64_t n_finite;     /* finite ln-weights                                                */
     int64_t n_posinf;     /* +inf ln-weights                                                  */
     int64_t n_pass;       /* draws that survived the geometric mask of this branch           */
-    int64_t n_stamps;     /* time stamps evaluated inside transit windows (diagnostic)       */
+    int64_t n_stamps;     /* time stamps whose sub-exposures were evaluated (diagnostic)     */
     int64_t n_interior;   /* evaluated model points with the occultor inside the disc        */
     int64_t n_limb;       /* evaluated model points with the occultor on the limb            */
     double* lnL_out;      /* optional [N]: per-draw lnL (no prior), -inf where masked         */
@@ -111,6 +113,25 @@ int tri_eval_eb(const tri_eb_args* args, tri_result out[2]); /* [0]=EB, [1]=EBx2
  * the small result record has been read back. */
 int tri_eval_tp_dev(const tri_tp_args* args, tri_result* out, void* stream);
 int tri_eval_eb_dev(const tri_eb_args* args, tri_result out[2], void* stream);
+
+/* Asynchronous forms of the four calls above (which are submit + wait).  tri_submit_* queues the
+ * column copies (on a copy stream of the library) and the kernels, and returns a ticket without
+ * waiting for the GPU, so that the caller can prepare the next scenario's draws -- or submit
+ * it -- while this one runs: the copies of one call overlap the kernels of the one before, the
+ * way consecutive lnZ_* calls of calc_probs (triceratops.py:750-1440) are independent of each
+ * other.  `want` is the record tri_eval_* would receive (optional output pointers, top_cap);
+ * tri_wait(ticket, out) blocks until that evaluation is complete and fills out[0] (TP-type) or
+ * out[0..1] (EB-type).  Every buffer named by `args` and `want` must stay valid and unmodified
+ * until tri_wait returns; entries of top_idx / top_lnL beyond n_top are unspecified.  At most
+ * TRI_MAX_INFLIGHT tickets may be outstanding (TRI_ESTATE otherwise); tickets may be waited for
+ * in any order, once.  tri_set_lightcurve first lets outstanding evaluations finish. */
+int tri_submit_tp(const tri_tp_args* args, const tri_result* want, int64_t* ticket);
+int tri_submit_eb(const tri_eb_args* args, const tri_result want[2], int64_t* ticket);
+int tri_submit_tp_dev(const tri_tp_args* args, const tri_result* want, void* stream,
+                      int64_t* ticket);
+int tri_submit_eb_dev(const tri_eb_args* args, const tri_result want[2], void* stream,
+                      int64_t* ticket);
+int tri_wait(int64_t ticket, tri_result* out);
 
 /* L1 seam, host buffers: lnL_TP_p (likelihoods.py:443-487), lnL_EB_p (:490-539) and
  * lnL_EB_twin_p (:542-587) on already-masked draws.  out[n] = +0.5 chi^2 (+inf where the

@@ -147,3 +147,41 @@ def check_against_golden(name, res, gold, lnz_atol=1e-6, arr_rtol=1e-9):
             want = want[np.lexsort(want.T[::-1])]
         np.testing.assert_allclose(mine, want, rtol=arr_rtol, atol=0,
                                    err_msg="%s branch %d best-draw table" % (name, b))
+
+
+def draw_tp_columns(N, seed, star=None):
+    """Prior draws of a TP-type scenario as keyword columns of Engine.eval_tp / submit_tp."""
+    from triceratops_b200 import priors
+    star = star or TOI465
+    rng_state = np.random.get_state()
+    np.random.seed(seed)
+    try:
+        rp = priors.sample_rp(np.random.rand(N), np.full(N, star["M"]), False)
+        inc = priors.sample_inc(np.random.rand(N))
+        ecc = priors.sample_ecc(np.random.rand(N), True, star["P"])
+        argp = priors.sample_w(np.random.rand(N))
+    finally:
+        np.random.set_state(rng_state)
+    return dict(rp=rp, P_orb=star["P"], inc=inc, ecc=ecc, argp=argp, mtot=star["M"],
+                rhost=star["R"], u1=0.4338, u2=0.2008, cfr=0.0)
+
+
+def draw_eb_columns(N, seed, star=None):
+    """Prior draws of an EB-type scenario as keyword columns of Engine.eval_eb / submit_eb."""
+    from triceratops_b200 import funcs, priors
+    star = star or TOI465
+    rng_state = np.random.get_state()
+    np.random.seed(seed)
+    try:
+        inc = priors.sample_inc(np.random.rand(N))
+        q = priors.sample_q(np.random.rand(N), star["M"])
+        ecc = priors.sample_ecc(np.random.rand(N), False, star["P"])
+        argp = priors.sample_w(np.random.rand(N))
+    finally:
+        np.random.set_state(rng_state)
+    masses = q * star["M"]
+    radii, _ = funcs.stellar_relations(masses, np.full(N, star["R"]), np.full(N, star["Teff"]))
+    fr = funcs.flux_relation(masses) / (funcs.flux_relation(masses)
+                                        + funcs.flux_relation(np.array([star["M"]])))
+    return dict(reb=radii, ebfr=fr, q=q, P_orb=star["P"], inc=inc, ecc=ecc, argp=argp,
+                mtot=star["M"] + masses, rhost=star["R"], u1=0.4338, u2=0.2008, cfr=0.0)

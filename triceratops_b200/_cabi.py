@@ -14,6 +14,7 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 c_uint8_p = ctypes.POINTER(ctypes.c_uint8)
 
 TRI_OK, TRI_ECUDA, TRI_EINVAL, TRI_ESTATE, TRI_ENODEVICE = 0, -1, -2, -3, -4
+TRI_MAX_INFLIGHT = 4     # include/triceratops_b200.h
 
 
 class TriError(RuntimeError):
@@ -55,7 +56,8 @@ class tri_result(ctypes.Structure):
 EXPORTS = ("tri_init", "tri_shutdown", "tri_last_error", "tri_set_lightcurve", "tri_eval_tp",
            "tri_eval_eb", "tri_eval_tp_dev", "tri_eval_eb_dev", "tri_lnl_tp", "tri_lnl_eb",
            "tri_simulate_tp", "tri_simulate_eb",
-           "tri_fetch_lnl", "tri_log_mean_exp", "tri_last_timing", "tri_fp64_peak", "tri_sm_count")
+           "tri_fetch_lnl", "tri_log_mean_exp", "tri_last_timing", "tri_fp64_peak", "tri_sm_count",
+           "tri_submit_tp", "tri_submit_eb", "tri_submit_tp_dev", "tri_submit_eb_dev", "tri_wait")
 
 _lib = None
 
@@ -88,6 +90,14 @@ def load():
                                   ctypes.c_void_p]
     L.tri_eval_eb_dev.argtypes = [ctypes.POINTER(tri_eb_args), ctypes.POINTER(tri_result),
                                   ctypes.c_void_p]
+    c_i64_p = ctypes.POINTER(ctypes.c_int64)
+    L.tri_submit_tp.argtypes = [ctypes.POINTER(tri_tp_args), ctypes.POINTER(tri_result), c_i64_p]
+    L.tri_submit_eb.argtypes = [ctypes.POINTER(tri_eb_args), ctypes.POINTER(tri_result), c_i64_p]
+    L.tri_submit_tp_dev.argtypes = [ctypes.POINTER(tri_tp_args), ctypes.POINTER(tri_result),
+                                    ctypes.c_void_p, c_i64_p]
+    L.tri_submit_eb_dev.argtypes = [ctypes.POINTER(tri_eb_args), ctypes.POINTER(tri_result),
+                                    ctypes.c_void_p, c_i64_p]
+    L.tri_wait.argtypes = [ctypes.c_int64, ctypes.POINTER(tri_result)]
     L.tri_lnl_tp.argtypes = [ctypes.c_int64] + [c_double_p] * 10 + [ctypes.c_int32, c_double_p]
     L.tri_lnl_eb.argtypes = ([ctypes.c_int64] + [c_double_p] * 11
                              + [ctypes.c_int32, ctypes.c_int32, c_double_p])

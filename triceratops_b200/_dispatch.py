@@ -7,6 +7,7 @@ Sharding follows SURVEY.md section 8e: every rank makes the same host draws (sam
 evaluates the contiguous slice [r*N/G, (r+1)*N/G), and one all-gather of a 206-double record per
 scenario branch replaces any exchange of per-draw data.
 """
+import contextlib
 
 import numpy as np
 
@@ -107,7 +108,8 @@ def _local_best(res, eng, single_rank):
     top_idx = getattr(res, "top_idx", None)
     if top_idx is not None:
         if single_rank and res.n_evaluated < N_BEST and res.N > 0:
-            lnL = eng.fetch_lnl(res.branch, res.N)
+            # (the engine fetched the array when the evaluation completed)
+            lnL = res.lnL if res.lnL is not None else eng.fetch_lnl(res.branch, res.N)
             idx = best_indices(lnL)
             return idx, lnL[idx], int(res.n_evaluated)
         return top_idx, res.top_lnL, int(res.n_evaluated)
@@ -158,26 +160,112 @@ def _gather_branch(res, lo, hi, N, eng=None):
     return br
 
 
-def run_tp(N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
-           extra_mask=None, companion_is_host=False):
-    lo, hi = shard_bounds(N)
-    eng = get_engine()
-    res = eng.eval_tp(hi - lo, *[_slice(x, lo, hi) for x in (rp, P_orb, inc, ecc, argp, mtot,
-                                                              rhost, u1, u2, cfr)],
-                      lnprior=_slice(lnprior, lo, hi), extra_mask=_mask_slice(extra_mask, lo, hi),
-                      companion_is_host=companion_is_host, want_lnL=False, n_best=N_BEST)
-    return _gather_branch(res, lo, hi, N, eng)
+# ---- submit / finish ----------------------------------------------------------------------------
+class _Done:
+    """Pending-like wrapper of an already computed result (engines without a submit API)."""
+
+    def __init__(self, out):
+        self._out = out
+
+    def result(self):
+        return self._out
 
 
-def run_eb(N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
-           extra_mask=None, companion_is_host=False):
+def _submit(eng, name, *args, **kw):
+    fn = getattr(eng, "submit_" + name, None)
+    if fn is not None:
+        return fn(*args, **kw)
+    return _Done(getattr(eng, "eval_" + name)(*args, **kw))
+
+
+class PendingBranches:
+    """A scenario evaluation in flight on this rank.  `finish()` waits for it, merges the ranks'
+    records (the collective, when a process group is up) and returns the Branch (TP-type) or
+    the (EB, EBx2P) pair; it is idempotent."""
+
+    def __init__(self, pending, lo, hi, N, eng):
+        self._pending, self._lo, self._hi, self._N, self._eng = pending, lo, hi, N, eng
+        self._out = None
+
+    def finish(self):
+        if self._out is None:
+            res = self._pending.result()
+            if isinstance(res, tuple):
+                self._out = tuple(_gather_branch(r, self._lo, self._hi, self._N, self._eng)
+                                  for r in res)
+            else:
+                self._out = _gather_branch(res, self._lo, self._hi, self._N, self._eng)
+            self._pending = None
+        return self._out
+
+
+def submit_tp(N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
+              extra_mask=None, companion_is_host=False):
     lo, hi = shard_bounds(N)
     eng = get_engine()
-    r0, r1 = eng.eval_eb(hi - lo, *[_slice(x, lo, hi) for x in (reb, ebfr, q, P_orb, inc, ecc,
-                                                                 argp, mtot, rhost, u1, u2, cfr)],
-                         lnprior=_slice(lnprior, lo, hi), extra_mask=_mask_slice(extra_mask, lo, hi),
-                         companion_is_host=companion_is_host, want_lnL=False, n_best=N_BEST)
-    return _gather_branch(r0, lo, hi, N, eng), _gather_branch(r1, lo, hi, N, eng)
+    p = _submit(eng, "tp", hi - lo, *[_slice(x, lo, hi) for x in (rp, P_orb, inc, ecc, argp, mtot,
+                                                                  rhost, u1, u2, cfr)],
+                lnprior=_slice(lnprior, lo, hi), extra_mask=_mask_slice(extra_mask, lo, hi),
+                companion_is_host=companion_is_host, want_lnL=False, n_best=N_BEST)
+    return PendingBranches(p, lo, hi, N, eng)
+
+
+def submit_eb(N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
+              extra_mask=None, companion_is_host=False):
+    lo, hi = shard_bounds(N)
+    eng = get_engine()
+    p = _submit(eng, "eb", hi - lo, *[_slice(x, lo, hi) for x in (reb, ebfr, q, P_orb, inc, ecc,
+                                                                  argp, mtot, rhost, u1, u2, cfr)],
+                lnprior=_slice(lnprior, lo, hi), extra_mask=_mask_slice(extra_mask, lo, hi),
+                companion_is_host=companion_is_host, want_lnL=False, n_best=N_BEST)
+    return PendingBranches(p, lo, hi, N, eng)
+
+
+def run_tp(*args, **kw):
+    return submit_tp(*args, **kw).finish()
+
+
+def run_eb(*args, **kw):
+    return submit_eb(*args, **kw).finish()
+
+
+# ---- deferred delivery: calc_probs overlaps one scenario's GPU work with the next one's draws ----
+_deferring = False
+
+
+class Deferred:
+    """A scenario result whose evaluation may still be running; `resolve()` returns the
+    reference's result dictionary (and caches it)."""
+
+    def __init__(self, make):
+        self._make, self._out = make, None
+
+    def resolve(self):
+        if self._make is not None:
+            self._out = self._make()
+            self._make = None
+        return self._out
+
+
+@contextlib.contextmanager
+def deferring():
+    """Inside this context the lnZ_* functions return `Deferred` results instead of waiting for
+    the GPU (calc_probs resolves them a few scenarios later, in order).  Everywhere else they
+    return finished dictionaries, like the reference."""
+    global _deferring
+    saved, _deferring = _deferring, True
+    try:
+        yield
+    finally:
+        _deferring = saved
+
+
+def deliver(make):
+    return Deferred(make) if _deferring else make()
+
+
+def resolve(res):
+    return res.resolve() if isinstance(res, Deferred) else res
 
 
 # ---- device-sampler mode: every rank owns its own draws --------------------------------------

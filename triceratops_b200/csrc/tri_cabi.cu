@@ -6,9 +6,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/triceratops_b200.h"
@@ -55,16 +57,113 @@ struct Arena {
     }
 };
 
+// grow-only pinned host arena: pageable caller columns are copied here by a few host threads so
+// that their transfer is a true asynchronous DMA (a cudaMemcpyAsync from pageable memory keeps
+// the calling thread busy for the whole transfer, at a fraction of the PCIe rate)
+struct HostArena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return TRI_OK;
+        if (base) CU(cudaFreeHost(base));
+        base = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8;
+        CU(cudaHostAlloc(&base, want, cudaHostAllocDefault));
+        cap = want;
+        return TRI_OK;
+    }
+    void reset() { used = 0; }
+    char* take(size_t bytes) {
+        size_t off = (used + 255) & ~size_t(255);
+        if (off + bytes > cap) return nullptr;
+        used = off + bytes;
+        return base + off;
+    }
+};
+
+constexpr size_t kPinnedLimit = (size_t)3 << 30;   // per slot; larger calls copy the rest directly
+constexpr size_t kPinnedMinCopy = (size_t)256 << 10;
+
+int host_threads() {
+    static int n = [] {
+        const char* e = std::getenv("TRI_B200_HOST_THREADS");
+        int v = e ? std::atoi(e) : 0;
+        if (v <= 0) v = (int)std::thread::hardware_concurrency() / 2;
+        return std::max(1, std::min(v, 8));
+    }();
+    return n;
+}
+
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    int T = host_threads();
+    if (T <= 1 || bytes < ((size_t)2 << 20)) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    size_t chunk = ((bytes / T) + 4095) & ~size_t(4095);
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) {
+        size_t lo = std::min(bytes, chunk * t), hi = std::min(bytes, chunk * (t + 1));
+        if (hi > lo)
+            th.emplace_back([=] { std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+    }
+    std::memcpy(dst, src, std::min(bytes, chunk));
+    for (auto& x : th) x.join();
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+constexpr int kSlots = TRI_MAX_INFLIGHT;
+
+// One evaluation in flight: its device scratch, its staged columns, and the pinned landing zone
+// of its small result record.  Slot kSlots is the private one of the synchronous helpers
+// (tri_lnl_*, tri_simulate_*, tri_log_mean_exp).
+struct Slot {
+    Arena scratch;   // kernel scratch (a, p, lnl, items, partials)
+    Arena staging;   // device copies of host columns
+    HostArena pinned;   // pinned copies of pageable host columns, on their way to `staging`
+    unsigned long long* d_counters = nullptr;  // [8]
+    unsigned long long* h_counters = nullptr;  // pinned [8]
+    LsePartial* d_lse_out = nullptr;           // [2]
+    LsePartial* h_lse_out = nullptr;           // pinned [2]
+    TopkState* d_topk = nullptr;               // [2]
+    TopkState* h_topk = nullptr;               // pinned [2]
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // geometry | lnl | lse
+    cudaEvent_t copied = nullptr, done = nullptr;
+    int launches = 0;
+    // the call in flight
+    int64_t ticket = 0;   // 0 = free
+    int branches = 0;     // 1 = TP-type, 2 = EB-type
+    int64_t N = 0;
+    bool host = false;    // host-buffer call: best-draw candidates are sorted in tri_wait
+    bool want_top[2] = {false, false};
+    tri_result want[2];   // the caller's records: its pointers go back into the results
+    const double* lnl[2] = {nullptr, nullptr};   // device lnL arrays of the call
+    // host-buffer calls: what tri_wait copies into the caller's (pageable) buffers -- a
+    // cudaMemcpyAsync into pageable memory would make tri_submit_* wait for the kernels
+    int64_t* h_tidx[2] = {nullptr, nullptr};     // pinned landing zone of the candidates
+    double* h_tval[2] = {nullptr, nullptr};
+    int64_t h_top_cap = 0;
+    const double* d_out_lnl[2] = {nullptr, nullptr};    // device copies of lnL_out / mask_out
+    const uint8_t* d_out_mask[2] = {nullptr, nullptr};
+};
+
 struct Ctx {
     bool ready = false;
     int device = -1;
     int sm_count = 0;
     int lnl_blocks_per_sm = 0;
     size_t lnl_smem = 0;   // dynamic shared memory used to stage the light curve (0 = none)
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool timing_valid = false;
-    int launches = 0;
+    cudaStream_t stream = nullptr;        // kernels and result read-back
+    cudaStream_t copy_stream = nullptr;   // host columns -> staging (overlaps the kernels)
     double* d_tae = nullptr;
     OrbitTable tab{};
     // light curve
@@ -73,16 +172,9 @@ struct Ctx {
     int* d_perm = nullptr;   // sorted stamp -> caller's stamp
     size_t lc_cap = 0;
     LightCurve lc{};
-    Arena scratch;   // kernel scratch (a, p, lnl, items, partials)
-    Arena staging;   // device copies of host columns
-    unsigned long long* d_counters = nullptr;  // [8]
-    LsePartial* d_lse_out = nullptr;           // [2]
-    LsePartial* h_lse_out = nullptr;           // pinned [2]
-    unsigned long long* h_counters = nullptr;  // pinned [8]
-    TopkState* d_topk = nullptr;               // [2]
-    TopkState* h_topk = nullptr;               // pinned [2]
-    const double* last_lnl[2] = {nullptr, nullptr};   // device lnL arrays of the last eval
-    int64_t last_N = 0;
+    Slot slots[kSlots + 1];
+    int64_t next_ticket = 1;
+    Slot* last = nullptr;    // the call completed last (tri_last_timing, tri_fetch_lnl)
 };
 
 Ctx g;
@@ -116,16 +208,27 @@ int need_ready(bool need_lc) {
 
 Col to_col(const tri_col& c) { return Col{c.ptr, c.stride}; }
 
-// copy one host column to the staging arena
-int stage(const tri_col& h, int64_t N, Col& d, cudaStream_t s) {
+// Source pointer for an H2D copy of `bytes` from the caller's `src`: the caller's buffer when it
+// is page-locked (or small, or the pinned arena is full), else a pinned copy of it.
+const void* via_pinned(Slot& S, const void* src, size_t bytes) {
+    if (bytes < kPinnedMinCopy || !S.pinned.base || is_pinned(src)) return src;
+    char* hp = S.pinned.take(bytes);
+    if (!hp) return src;
+    parallel_memcpy(hp, src, bytes);
+    return hp;
+}
+
+// copy one host column to the slot's staging arena
+int stage(Slot& S, const tri_col& h, int64_t N, Col& d, cudaStream_t s) {
     if (h.ptr == nullptr) {
         d = Col{nullptr, 0};
         return TRI_OK;
     }
     if (h.stride != 0 && h.stride != 1) return fail(TRI_EINVAL, "column stride must be 0 or 1");
     size_t n = h.stride ? (size_t)N : 1;
-    double* p = g.staging.take<double>(n);
-    CU(cudaMemcpyAsync(p, h.ptr, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    double* p = S.staging.take<double>(n);
+    CU(cudaMemcpyAsync(p, via_pinned(S, h.ptr, n * sizeof(double)), n * sizeof(double),
+                       cudaMemcpyHostToDevice, s));
     d = Col{p, h.stride};
     return TRI_OK;
 }
@@ -167,28 +270,28 @@ void finish_result(const LsePartial& r, int64_t N, tri_result* out) {
     else out->lnZ = r.m + std::log(r.s) - std::log((double)N);
 }
 
-int launch_lse(const double* lnl, Col lnprior, int64_t N, LsePartial* partials, LsePartial* out,
-               cudaStream_t s) {
+int launch_lse(Slot& S, const double* lnl, Col lnprior, int64_t N, LsePartial* partials,
+               LsePartial* out, cudaStream_t s) {
     int nb = lse_blocks(N);
     lse_partial_kernel<<<nb, kLseThreads, 0, s>>>(lnl, lnprior, N, partials);
     lse_final_kernel<<<1, 32, 0, s>>>(partials, nb, out);
-    g.launches += 2;
+    S.launches += 2;
     CU(cudaGetLastError());
     return TRI_OK;
 }
 
-int launch_lnl(LnlArgs& A, cudaStream_t s) {
+int launch_lnl(Slot& S, LnlArgs& A, cudaStream_t s) {
     size_t smem = lnl_smem_bytes();
     lnl_kernel<<<lnl_grid(), kLnlThreads, smem, s>>>(A);
-    g.launches += 1;
+    S.launches += 1;
     CU(cudaGetLastError());
     return TRI_OK;
 }
 
 // top-K of lnl on the device into (d_idx, d_val); the state record of `slot` receives n_out
-int launch_topk(const double* lnl, int64_t N, int64_t cap, int slot, int64_t* d_idx,
+int launch_topk(Slot& S, const double* lnl, int64_t N, int64_t cap, int branch, int64_t* d_idx,
                 double* d_val, cudaStream_t s) {
-    TopkState* st = g.d_topk + slot;
+    TopkState* st = S.d_topk + branch;
     int nb = (int)std::max<int64_t>(1, std::min<int64_t>((N + 4095) / 4096,
                                                          4 * (int64_t)g.sm_count));
     topk_init_kernel<<<1, 256, 0, s>>>(st, (unsigned long long)cap);
@@ -198,159 +301,136 @@ int launch_topk(const double* lnl, int64_t N, int64_t cap, int slot, int64_t* d_
     }
     topk_collect_above_kernel<<<nb, kTopkThreads, 0, s>>>(lnl, N, st, d_idx, d_val, cap);
     topk_collect_ties_kernel<<<1, 1024, 0, s>>>(lnl, N, st, d_idx, d_val, cap);
-    g.launches += 19;
+    S.launches += 19;
     CU(cudaGetLastError());
     return TRI_OK;
 }
 
-// core of tri_eval_tp*: every pointer in `a` is a device pointer
-int eval_tp_device(const tri_tp_args& a, tri_result* out, cudaStream_t s) {
+// Queue one TP-type evaluation on `s` for slot S: every pointer in `a` and in `r` (lnL_out,
+// mask_out, top_idx, top_lnL) is a device pointer.  Nothing here waits for the GPU; the small
+// result record lands in the slot's pinned buffers and is read by finish_slot.
+int enqueue_tp(Slot& S, const tri_tp_args& a, const tri_result& r, cudaStream_t s) {
     const int64_t N = a.N;
-    g.scratch.reset();
-    int rc = g.scratch.reserve(scratch_bytes(N, false));
+    S.scratch.reset();
+    int rc = S.scratch.reserve(scratch_bytes(N, false));
     if (rc) return rc;
-    Scratch S;
-    S.a = g.scratch.take<double>(N);
-    S.lnl = out->lnL_out ? out->lnL_out : g.scratch.take<double>(N);
-    S.items = g.scratch.take<int64_t>(N);
-    S.partials = g.scratch.take<LsePartial>(lse_blocks(N));
-    g.launches = 0;
-    CU(cudaMemsetAsync(g.d_counters, 0, 8 * sizeof(unsigned long long), s));
-    CU(cudaEventRecord(g.ev[0], s));
+    Scratch W;
+    W.a = S.scratch.take<double>(N);
+    W.lnl = r.lnL_out ? r.lnL_out : S.scratch.take<double>(N);
+    W.items = S.scratch.take<int64_t>(N);
+    W.partials = S.scratch.take<LsePartial>(lse_blocks(N));
+    S.launches = 0;
+    CU(cudaMemsetAsync(S.d_counters, 0, 8 * sizeof(unsigned long long), s));
+    CU(cudaEventRecord(S.ev[0], s));
     GeomTp G{};
     G.N = N;
     G.rp = to_col(a.rp); G.P = to_col(a.P_orb); G.inc = to_col(a.inc); G.ecc = to_col(a.ecc);
     G.argp = to_col(a.argp); G.mtot = to_col(a.mtot); G.rhost = to_col(a.rhost);
     G.extra_mask = a.extra_mask;
-    G.a_out = S.a; G.lnl_out = S.lnl; G.mask_out = out->mask_out;
-    G.items = S.items; G.n_items = g.d_counters + 0;
+    G.a_out = W.a; G.lnl_out = W.lnl; G.mask_out = r.mask_out;
+    G.items = W.items; G.n_items = S.d_counters + 0;
     int gb = (int)std::min<int64_t>((N + 255) / 256, (int64_t)g.sm_count * 8);
     geometry_tp_kernel<<<std::max(gb, 1), 256, 0, s>>>(G);
-    g.launches += 1;
+    S.launches += 1;
     CU(cudaGetLastError());
-    CU(cudaEventRecord(g.ev[1], s));
+    CU(cudaEventRecord(S.ev[1], s));
 
     // the work-list length stays on the device: no host round trip between the two kernels
     LnlArgs A{};
     A.lc = g.lc; A.tab = g.tab; A.eb = 0; A.companion_is_host = a.companion_is_host; A.raw = 0;
     A.twin_uniform = 0;
     A.body = to_col(a.rp); A.ebfr = Col{nullptr, 0};
-    A.P = to_col(a.P_orb); A.inc = to_col(a.inc); A.a = Col{S.a, 1}; A.rhost = to_col(a.rhost);
+    A.P = to_col(a.P_orb); A.inc = to_col(a.inc); A.a = Col{W.a, 1}; A.rhost = to_col(a.rhost);
     A.u1 = to_col(a.u1); A.u2 = to_col(a.u2); A.ecc = to_col(a.ecc); A.argp = to_col(a.argp);
     A.cfr = to_col(a.cfr);
-    A.items = S.items; A.count = 0; A.count_dev = g.d_counters + 0; A.next = g.d_counters + 2;
-    A.out = S.lnl; A.out_twin = nullptr; A.counters = g.d_counters + 4;
-    rc = launch_lnl(A, s);
+    A.items = W.items; A.count = 0; A.count_dev = S.d_counters + 0; A.next = S.d_counters + 2;
+    A.out = W.lnl; A.out_twin = nullptr; A.counters = S.d_counters + 4;
+    rc = launch_lnl(S, A, s);
     if (rc) return rc;
-    CU(cudaEventRecord(g.ev[2], s));
-    rc = launch_lse(S.lnl, to_col(a.lnprior), N, S.partials, g.d_lse_out, s);
+    CU(cudaEventRecord(S.ev[2], s));
+    rc = launch_lse(S, W.lnl, to_col(a.lnprior), N, W.partials, S.d_lse_out, s);
     if (rc) return rc;
-    const bool want_top = out->top_cap > 0 && out->top_idx && out->top_lnL;
-    if (want_top) {
-        rc = launch_topk(S.lnl, N, out->top_cap, 0, out->top_idx, out->top_lnL, s);
+    S.want_top[0] = r.top_cap > 0 && r.top_idx && r.top_lnL;
+    S.want_top[1] = false;
+    if (S.want_top[0]) {
+        rc = launch_topk(S, W.lnl, N, r.top_cap, 0, r.top_idx, r.top_lnL, s);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(g.h_topk, g.d_topk, sizeof(TopkState), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(S.h_topk, S.d_topk, sizeof(TopkState), cudaMemcpyDeviceToHost, s));
     }
-    g.last_lnl[0] = S.lnl; g.last_lnl[1] = nullptr; g.last_N = N;
-    CU(cudaEventRecord(g.ev[3], s));
-    CU(cudaMemcpyAsync(g.h_lse_out, g.d_lse_out, sizeof(LsePartial), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(g.h_counters, g.d_counters, 8 * sizeof(unsigned long long),
+    S.lnl[0] = W.lnl; S.lnl[1] = nullptr;
+    CU(cudaEventRecord(S.ev[3], s));
+    CU(cudaMemcpyAsync(S.h_lse_out, S.d_lse_out, sizeof(LsePartial), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(S.h_counters, S.d_counters, 8 * sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    g.timing_valid = true;
-    finish_result(g.h_lse_out[0], N, out);
-    out->n_pass = (int64_t)g.h_counters[0];
-    out->n_stamps = (int64_t)g.h_counters[5];
-    out->n_interior = (int64_t)g.h_counters[6];
-    out->n_limb = (int64_t)g.h_counters[7];
-    out->n_top = want_top ? (int64_t)std::min<unsigned long long>(g.h_topk[0].n_out,
-                                                                 (unsigned long long)out->top_cap)
-                          : 0;
-    out->n_evaluated = want_top ? (int64_t)g.h_topk[0].n_finite : -1;
     return TRI_OK;
 }
 
-int eval_eb_device(const tri_eb_args& a, tri_result out[2], cudaStream_t s) {
+// EB-type: the EB (period P) and EBx2P (period 2P) branches share one geometry launch and one
+// work list; r[0] / r[1] hold the device-side output pointers of the two branches.
+int enqueue_eb(Slot& S, const tri_eb_args& a, const tri_result r[2], cudaStream_t s) {
     const int64_t N = a.N;
-    g.scratch.reset();
-    int rc = g.scratch.reserve(scratch_bytes(N, true));
+    S.scratch.reset();
+    int rc = S.scratch.reserve(scratch_bytes(N, true));
     if (rc) return rc;
-    Scratch S;
-    S.a = g.scratch.take<double>(N);
-    S.p = g.scratch.take<double>(N);
-    S.lnl = out[0].lnL_out ? out[0].lnL_out : g.scratch.take<double>(N);
-    S.lnl_twin = out[1].lnL_out ? out[1].lnL_out : g.scratch.take<double>(N);
-    S.items = g.scratch.take<int64_t>(N);
-    S.n_partials = lse_blocks(N);
-    S.partials = g.scratch.take<LsePartial>(2 * S.n_partials);
-    g.launches = 0;
-    CU(cudaMemsetAsync(g.d_counters, 0, 8 * sizeof(unsigned long long), s));
-    CU(cudaEventRecord(g.ev[0], s));
+    Scratch W;
+    W.a = S.scratch.take<double>(N);
+    W.p = S.scratch.take<double>(N);
+    W.lnl = r[0].lnL_out ? r[0].lnL_out : S.scratch.take<double>(N);
+    W.lnl_twin = r[1].lnL_out ? r[1].lnL_out : S.scratch.take<double>(N);
+    W.items = S.scratch.take<int64_t>(N);
+    W.n_partials = lse_blocks(N);
+    W.partials = S.scratch.take<LsePartial>(2 * W.n_partials);
+    S.launches = 0;
+    CU(cudaMemsetAsync(S.d_counters, 0, 8 * sizeof(unsigned long long), s));
+    CU(cudaEventRecord(S.ev[0], s));
     GeomEb G{};
     G.N = N;
     G.reb = to_col(a.reb); G.q = to_col(a.q); G.P = to_col(a.P_orb); G.inc = to_col(a.inc);
     G.ecc = to_col(a.ecc); G.argp = to_col(a.argp); G.mtot = to_col(a.mtot);
     G.rhost = to_col(a.rhost);
     G.extra_mask = a.extra_mask;
-    G.a_out = S.a; G.p_out = S.p; G.lnl_out = S.lnl; G.lnl_twin_out = S.lnl_twin;
-    G.mask_out = out[0].mask_out; G.mask_twin_out = out[1].mask_out;
-    G.items = S.items; G.n_items = g.d_counters + 0;
+    G.a_out = W.a; G.p_out = W.p; G.lnl_out = W.lnl; G.lnl_twin_out = W.lnl_twin;
+    G.mask_out = r[0].mask_out; G.mask_twin_out = r[1].mask_out;
+    G.items = W.items; G.n_items = S.d_counters + 0;
     int gb = (int)std::min<int64_t>((N + 255) / 256, (int64_t)g.sm_count * 8);
     geometry_eb_kernel<<<std::max(gb, 1), 256, 0, s>>>(G);
-    g.launches += 1;
+    S.launches += 1;
     CU(cudaGetLastError());
-    CU(cudaEventRecord(g.ev[1], s));
+    CU(cudaEventRecord(S.ev[1], s));
 
     LnlArgs A{};
     A.lc = g.lc; A.tab = g.tab; A.eb = 1; A.companion_is_host = a.companion_is_host; A.raw = 0;
     A.twin_uniform = 0;
     A.body = to_col(a.reb); A.ebfr = to_col(a.ebfr);
-    A.P = Col{S.p, 1}; A.inc = to_col(a.inc); A.a = Col{S.a, 1}; A.rhost = to_col(a.rhost);
+    A.P = Col{W.p, 1}; A.inc = to_col(a.inc); A.a = Col{W.a, 1}; A.rhost = to_col(a.rhost);
     A.u1 = to_col(a.u1); A.u2 = to_col(a.u2); A.ecc = to_col(a.ecc); A.argp = to_col(a.argp);
     A.cfr = to_col(a.cfr);
-    A.items = S.items; A.count = 0; A.count_dev = g.d_counters + 0; A.next = g.d_counters + 2;
-    A.out = S.lnl; A.out_twin = S.lnl_twin; A.counters = g.d_counters + 4;
-    rc = launch_lnl(A, s);
+    A.items = W.items; A.count = 0; A.count_dev = S.d_counters + 0; A.next = S.d_counters + 2;
+    A.out = W.lnl; A.out_twin = W.lnl_twin; A.counters = S.d_counters + 4;
+    rc = launch_lnl(S, A, s);
     if (rc) return rc;
-    CU(cudaEventRecord(g.ev[2], s));
-    rc = launch_lse(S.lnl, to_col(a.lnprior), N, S.partials, g.d_lse_out, s);
+    CU(cudaEventRecord(S.ev[2], s));
+    rc = launch_lse(S, W.lnl, to_col(a.lnprior), N, W.partials, S.d_lse_out, s);
     if (rc) return rc;
-    rc = launch_lse(S.lnl_twin, to_col(a.lnprior), N, S.partials + S.n_partials,
-                    g.d_lse_out + 1, s);
+    rc = launch_lse(S, W.lnl_twin, to_col(a.lnprior), N, W.partials + W.n_partials,
+                    S.d_lse_out + 1, s);
     if (rc) return rc;
-    bool want_top[2];
     for (int b = 0; b < 2; ++b) {
-        want_top[b] = out[b].top_cap > 0 && out[b].top_idx && out[b].top_lnL;
-        if (want_top[b]) {
-            rc = launch_topk(b ? S.lnl_twin : S.lnl, N, out[b].top_cap, b, out[b].top_idx,
-                             out[b].top_lnL, s);
+        S.want_top[b] = r[b].top_cap > 0 && r[b].top_idx && r[b].top_lnL;
+        if (S.want_top[b]) {
+            rc = launch_topk(S, b ? W.lnl_twin : W.lnl, N, r[b].top_cap, b, r[b].top_idx,
+                             r[b].top_lnL, s);
             if (rc) return rc;
         }
     }
-    if (want_top[0] || want_top[1])
-        CU(cudaMemcpyAsync(g.h_topk, g.d_topk, 2 * sizeof(TopkState), cudaMemcpyDeviceToHost, s));
-    g.last_lnl[0] = S.lnl; g.last_lnl[1] = S.lnl_twin; g.last_N = N;
-    CU(cudaEventRecord(g.ev[3], s));
-    CU(cudaMemcpyAsync(g.h_lse_out, g.d_lse_out, 2 * sizeof(LsePartial), cudaMemcpyDeviceToHost,
+    if (S.want_top[0] || S.want_top[1])
+        CU(cudaMemcpyAsync(S.h_topk, S.d_topk, 2 * sizeof(TopkState), cudaMemcpyDeviceToHost, s));
+    S.lnl[0] = W.lnl; S.lnl[1] = W.lnl_twin;
+    CU(cudaEventRecord(S.ev[3], s));
+    CU(cudaMemcpyAsync(S.h_lse_out, S.d_lse_out, 2 * sizeof(LsePartial), cudaMemcpyDeviceToHost,
                        s));
-    CU(cudaMemcpyAsync(g.h_counters, g.d_counters, 8 * sizeof(unsigned long long),
+    CU(cudaMemcpyAsync(S.h_counters, S.d_counters, 8 * sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    g.timing_valid = true;
-    finish_result(g.h_lse_out[0], N, &out[0]);
-    finish_result(g.h_lse_out[1], N, &out[1]);
-    out[0].n_pass = (int64_t)g.h_counters[0] - (int64_t)g.h_counters[1];
-    out[1].n_pass = (int64_t)g.h_counters[1];
-    for (int b = 0; b < 2; ++b) {   // the two branches share one launch: totals are joint
-        out[b].n_stamps = (int64_t)g.h_counters[5];
-        out[b].n_interior = (int64_t)g.h_counters[6];
-        out[b].n_limb = (int64_t)g.h_counters[7];
-        out[b].n_top = want_top[b]
-            ? (int64_t)std::min<unsigned long long>(g.h_topk[b].n_out,
-                                                    (unsigned long long)out[b].top_cap)
-            : 0;
-        out[b].n_evaluated = want_top[b] ? (int64_t)g.h_topk[b].n_finite : -1;
-    }
     return TRI_OK;
 }
 
@@ -365,6 +445,60 @@ void sort_candidates(int64_t n, int64_t* idx, double* val) {
     for (int64_t i = 0; i < n; ++i) { val[i] = v[(size_t)i].first; idx[i] = v[(size_t)i].second; }
 }
 
+// After the slot's `done` event: turn the pinned landing zone into the caller's records.
+void finish_slot(Slot& S, tri_result* out) {
+    for (int b = 0; b < S.branches; ++b) {
+        tri_result r = S.want[b];   // keeps the caller's pointers and top_cap
+        if (S.N == 0) {
+            LsePartial z{-INFINITY, 0.0, 0, 0};
+            finish_result(z, 0, &r);
+            r.n_pass = r.n_stamps = r.n_interior = r.n_limb = r.n_top = 0;
+            r.n_evaluated = 0;
+            out[b] = r;
+            continue;
+        }
+        finish_result(S.h_lse_out[b], S.N, &r);
+        if (S.branches == 1) {
+            r.n_pass = (int64_t)S.h_counters[0];
+        } else {   // twins are counted separately by the geometry kernel
+            r.n_pass = b ? (int64_t)S.h_counters[1]
+                         : (int64_t)S.h_counters[0] - (int64_t)S.h_counters[1];
+        }
+        // the two EB branches share one launch: these totals are joint
+        r.n_stamps = (int64_t)S.h_counters[5];
+        r.n_interior = (int64_t)S.h_counters[6];
+        r.n_limb = (int64_t)S.h_counters[7];
+        r.n_top = S.want_top[b]
+            ? (int64_t)std::min<unsigned long long>(S.h_topk[b].n_out,
+                                                    (unsigned long long)r.top_cap)
+            : 0;
+        r.n_evaluated = S.want_top[b] ? (int64_t)S.h_topk[b].n_finite : -1;
+        if (S.host && S.want_top[b]) {
+            std::memcpy(r.top_idx, S.h_tidx[b], (size_t)r.n_top * 8);
+            std::memcpy(r.top_lnL, S.h_tval[b], (size_t)r.n_top * 8);
+            sort_candidates(r.n_top, r.top_idx, r.top_lnL);
+        }
+        out[b] = r;
+    }
+}
+
+Slot* free_slot() {
+    for (int i = 0; i < kSlots; ++i)
+        if (g.slots[i].ticket == 0) return &g.slots[i];
+    return nullptr;
+}
+
+Slot* find_slot(int64_t ticket) {
+    if (ticket <= 0) return nullptr;
+    for (int i = 0; i < kSlots; ++i)
+        if (g.slots[i].ticket == ticket) return &g.slots[i];
+    return nullptr;
+}
+
+int no_slot() {
+    return fail(TRI_ESTATE, "TRI_MAX_INFLIGHT evaluations are already in flight: tri_wait one");
+}
+
 int check_cols(int64_t N, std::initializer_list<const tri_col*> req) {
     if (N < 0) return fail(TRI_EINVAL, "N must be >= 0");
     for (const tri_col* c : req) {
@@ -373,6 +507,29 @@ int check_cols(int64_t N, std::initializer_list<const tri_col*> req) {
             return fail(TRI_EINVAL, "column stride must be 0 or 1");
     }
     return TRI_OK;
+}
+
+int check_tp(const tri_tp_args* a, const void* out) {
+    if (!a || !out) return fail(TRI_EINVAL, "NULL argument");
+    return check_cols(a->N, {&a->rp, &a->P_orb, &a->inc, &a->ecc, &a->argp, &a->mtot, &a->rhost,
+                             &a->u1, &a->u2, &a->cfr});
+}
+
+int check_eb(const tri_eb_args* a, const void* out) {
+    if (!a || !out) return fail(TRI_EINVAL, "NULL argument");
+    return check_cols(a->N, {&a->reb, &a->ebfr, &a->q, &a->P_orb, &a->inc, &a->ecc, &a->argp,
+                             &a->mtot, &a->rhost, &a->u1, &a->u2, &a->cfr});
+}
+
+// mark the slot in flight and hand out its ticket
+void commit(Slot& S, int branches, int64_t N, bool host, const tri_result* want,
+            int64_t* ticket) {
+    S.branches = branches;
+    S.N = N;
+    S.host = host;
+    for (int b = 0; b < branches; ++b) S.want[b] = want[b];
+    S.ticket = g.next_ticket++;
+    *ticket = S.ticket;
 }
 
 }  // namespace
@@ -397,7 +554,7 @@ int tri_init(int device) {
     g.device = device;
     g.sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    for (auto& ev : g.ev) CU(cudaEventCreate(&ev));
+    CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     // orbit table
     std::vector<double> es, ms, tae((size_t)kTableNe * kTableNm);
     linspace(0.0, kTableMaxE, kTableNe, es);
@@ -411,12 +568,17 @@ int tri_init(int device) {
     g.tab.de = es[1] - es[0];
     g.tab.dm = ms[1] - ms[0];
     g.tab.inv_dm = 1.0 / g.tab.dm;
-    CU(cudaMalloc(&g.d_counters, 8 * sizeof(unsigned long long)));
-    CU(cudaMalloc(&g.d_lse_out, 2 * sizeof(LsePartial)));
-    CU(cudaMallocHost(&g.h_lse_out, 2 * sizeof(LsePartial)));
-    CU(cudaMallocHost(&g.h_counters, 8 * sizeof(unsigned long long)));
-    CU(cudaMalloc(&g.d_topk, 2 * sizeof(TopkState)));
-    CU(cudaMallocHost(&g.h_topk, 2 * sizeof(TopkState)));
+    for (Slot& S : g.slots) {
+        CU(cudaMalloc(&S.d_counters, 8 * sizeof(unsigned long long)));
+        CU(cudaMalloc(&S.d_lse_out, 2 * sizeof(LsePartial)));
+        CU(cudaMallocHost(&S.h_lse_out, 2 * sizeof(LsePartial)));
+        CU(cudaMallocHost(&S.h_counters, 8 * sizeof(unsigned long long)));
+        CU(cudaMalloc(&S.d_topk, 2 * sizeof(TopkState)));
+        CU(cudaMallocHost(&S.h_topk, 2 * sizeof(TopkState)));
+        for (auto& ev : S.ev) CU(cudaEventCreate(&ev));
+        CU(cudaEventCreateWithFlags(&S.copied, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    }
     // occupancy of the persistent light-curve kernel
     int bps = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lnl_kernel, kLnlThreads, 0));
@@ -436,15 +598,25 @@ int tri_shutdown(void) {
     cudaFree(g.d_flux);
     cudaFree(g.d_prefix);
     cudaFree(g.d_perm);
-    cudaFree(g.d_counters);
-    cudaFree(g.d_lse_out);
-    cudaFreeHost(g.h_lse_out);
-    cudaFreeHost(g.h_counters);
-    cudaFree(g.d_topk);
-    cudaFreeHost(g.h_topk);
-    if (g.scratch.base) cudaFree(g.scratch.base);
-    if (g.staging.base) cudaFree(g.staging.base);
-    for (auto& ev : g.ev) cudaEventDestroy(ev);
+    for (Slot& S : g.slots) {
+        cudaFree(S.d_counters);
+        cudaFree(S.d_lse_out);
+        cudaFreeHost(S.h_lse_out);
+        cudaFreeHost(S.h_counters);
+        cudaFree(S.d_topk);
+        cudaFreeHost(S.h_topk);
+        if (S.scratch.base) cudaFree(S.scratch.base);
+        if (S.staging.base) cudaFree(S.staging.base);
+        if (S.pinned.base) cudaFreeHost(S.pinned.base);
+        for (int b = 0; b < 2; ++b) {
+            if (S.h_tidx[b]) cudaFreeHost(S.h_tidx[b]);
+            if (S.h_tval[b]) cudaFreeHost(S.h_tval[b]);
+        }
+        for (auto& ev : S.ev) cudaEventDestroy(ev);
+        cudaEventDestroy(S.copied);
+        cudaEventDestroy(S.done);
+    }
+    cudaStreamDestroy(g.copy_stream);
     cudaStreamDestroy(g.stream);
     g = Ctx{};
     return TRI_OK;
@@ -484,6 +656,9 @@ int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, dou
         pre[j + 1] = (double)run;
     }
     CU(cudaSetDevice(g.device));
+    // evaluations still in flight read the current light curve: let them finish first
+    for (int i = 0; i < kSlots; ++i)
+        if (g.slots[i].ticket != 0) CU(cudaEventSynchronize(g.slots[i].done));
     CU(cudaStreamSynchronize(g.stream));
     if ((size_t)npts > g.lc_cap) {
         cudaFree(g.d_time); cudaFree(g.d_flux); cudaFree(g.d_prefix); cudaFree(g.d_perm);
@@ -523,165 +698,256 @@ int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, dou
     return TRI_OK;
 }
 
-int tri_eval_tp_dev(const tri_tp_args* a, tri_result* out, void* stream) {
+// ---- submit / wait --------------------------------------------------------------------------
+int tri_submit_tp_dev(const tri_tp_args* a, const tri_result* want, void* stream,
+                      int64_t* ticket) {
     int rc = need_ready(true);
     if (rc) return rc;
-    if (!a || !out) return fail(TRI_EINVAL, "NULL argument");
-    rc = check_cols(a->N, {&a->rp, &a->P_orb, &a->inc, &a->ecc, &a->argp, &a->mtot, &a->rhost,
-                           &a->u1, &a->u2, &a->cfr});
+    if (!ticket) return fail(TRI_EINVAL, "NULL argument");
+    rc = check_tp(a, want);
     if (rc) return rc;
+    Slot* S = free_slot();
+    if (!S) return no_slot();
     CU(cudaSetDevice(g.device));
-    if (a->N == 0) {
-        LsePartial z{-INFINITY, 0.0, 0, 0};
-        finish_result(z, 0, out);
-        out->n_pass = out->n_stamps = out->n_interior = out->n_limb = out->n_top = 0;
-        return TRI_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    if (a->N > 0) {
+        rc = enqueue_tp(*S, *a, *want, s);
+        if (rc) return rc;
     }
-    return eval_tp_device(*a, out, stream ? (cudaStream_t)stream : g.stream);
+    CU(cudaEventRecord(S->done, s));
+    commit(*S, 1, a->N, false, want, ticket);
+    return TRI_OK;
+}
+
+int tri_submit_eb_dev(const tri_eb_args* a, const tri_result want[2], void* stream,
+                      int64_t* ticket) {
+    int rc = need_ready(true);
+    if (rc) return rc;
+    if (!ticket) return fail(TRI_EINVAL, "NULL argument");
+    rc = check_eb(a, want);
+    if (rc) return rc;
+    Slot* S = free_slot();
+    if (!S) return no_slot();
+    CU(cudaSetDevice(g.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    if (a->N > 0) {
+        rc = enqueue_eb(*S, *a, want, s);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(S->done, s));
+    commit(*S, 2, a->N, false, want, ticket);
+    return TRI_OK;
+}
+
+// device-side landing buffers of one branch's outputs, and the copies back to the caller's
+static int stage_outputs(Slot& S, int64_t N, const tri_result& want, tri_result& r) {
+    const bool top = want.top_cap > 0 && want.top_idx && want.top_lnL;
+    r = want;
+    r.lnL_out = want.lnL_out ? S.staging.take<double>(N) : nullptr;
+    r.mask_out = want.mask_out ? S.staging.take<uint8_t>(N) : nullptr;
+    r.top_cap = top ? want.top_cap : 0;
+    r.top_idx = top ? S.staging.take<int64_t>(want.top_cap) : nullptr;
+    r.top_lnL = top ? S.staging.take<double>(want.top_cap) : nullptr;
+    return TRI_OK;
+}
+
+// queue the read-back of branch b's candidates into the slot's pinned landing zone, and note
+// the device arrays tri_wait copies into the caller's lnL_out / mask_out
+static int queue_outputs(Slot& S, int b, const tri_result& want, const tri_result& r,
+                         cudaStream_t s) {
+    S.d_out_lnl[b] = want.lnL_out ? r.lnL_out : nullptr;
+    S.d_out_mask[b] = want.mask_out ? r.mask_out : nullptr;
+    if (r.top_cap > 0) {   // n_top is not known yet: the whole candidate buffer travels
+        CU(cudaMemcpyAsync(S.h_tidx[b], r.top_idx, (size_t)r.top_cap * 8,
+                           cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(S.h_tval[b], r.top_lnL, (size_t)r.top_cap * 8,
+                           cudaMemcpyDeviceToHost, s));
+    }
+    return TRI_OK;
+}
+
+// pinned landing zone for `cap` candidates per branch (grow-only)
+static int reserve_top(Slot& S, int64_t cap) {
+    if (cap <= S.h_top_cap) return TRI_OK;
+    for (int b = 0; b < 2; ++b) {
+        if (S.h_tidx[b]) cudaFreeHost(S.h_tidx[b]);
+        if (S.h_tval[b]) cudaFreeHost(S.h_tval[b]);
+        S.h_tidx[b] = nullptr;
+        S.h_tval[b] = nullptr;
+    }
+    S.h_top_cap = 0;
+    for (int b = 0; b < 2; ++b) {
+        CU(cudaMallocHost(&S.h_tidx[b], (size_t)cap * 8));
+        CU(cudaMallocHost(&S.h_tval[b], (size_t)cap * 8));
+    }
+    S.h_top_cap = cap;
+    return TRI_OK;
+}
+
+int tri_submit_tp(const tri_tp_args* a, const tri_result* want, int64_t* ticket) {
+    int rc = need_ready(true);
+    if (rc) return rc;
+    if (!ticket) return fail(TRI_EINVAL, "NULL argument");
+    rc = check_tp(a, want);
+    if (rc) return rc;
+    Slot* S = free_slot();
+    if (!S) return no_slot();
+    CU(cudaSetDevice(g.device));
+    const int64_t N = a->N;
+    if (N > 0) {
+        cudaStream_t cs = g.copy_stream;
+        S->staging.reset();
+        rc = S->staging.reserve((size_t)N * 8 * 13 + (size_t)N * 2 + 8192
+                                + (size_t)std::max<int64_t>(want->top_cap, 0) * 16);
+        if (rc) return rc;
+        S->pinned.reset();
+        if (!is_pinned(a->inc.ptr)) {   // pageable caller columns go through the pinned arena
+            rc = S->pinned.reserve(std::min(kPinnedLimit, (size_t)N * 8 * 12 + (size_t)N + 8192));
+            if (rc) return rc;
+        }
+        tri_tp_args d = *a;
+        Col c;
+#define STAGE(field)                                   \
+    rc = stage(*S, a->field, N, c, cs);                \
+    if (rc) return rc;                                 \
+    d.field = tri_col{c.p, c.stride};
+        STAGE(rp) STAGE(P_orb) STAGE(inc) STAGE(ecc) STAGE(argp) STAGE(mtot) STAGE(rhost)
+        STAGE(u1) STAGE(u2) STAGE(cfr) STAGE(lnprior)
+        if (a->extra_mask) {
+            uint8_t* m = S->staging.take<uint8_t>(N);
+            CU(cudaMemcpyAsync(m, via_pinned(*S, a->extra_mask, (size_t)N), (size_t)N,
+                               cudaMemcpyHostToDevice, cs));
+            d.extra_mask = m;
+        }
+        rc = reserve_top(*S, want->top_cap);
+        if (rc) return rc;
+        tri_result r;
+        stage_outputs(*S, N, *want, r);
+        if (r.top_cap > 0) {
+            CU(cudaMemsetAsync(r.top_idx, 0, (size_t)r.top_cap * 8, cs));
+            CU(cudaMemsetAsync(r.top_lnL, 0, (size_t)r.top_cap * 8, cs));
+        }
+        // the kernels start when the columns have landed; the next call's copies overlap them
+        CU(cudaEventRecord(S->copied, cs));
+        CU(cudaStreamWaitEvent(g.stream, S->copied, 0));
+        rc = enqueue_tp(*S, d, r, g.stream);
+        if (rc) return rc;
+        rc = queue_outputs(*S, 0, *want, r, g.stream);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(S->done, g.stream));
+    commit(*S, 1, N, true, want, ticket);
+    return TRI_OK;
+}
+
+int tri_submit_eb(const tri_eb_args* a, const tri_result want[2], int64_t* ticket) {
+    int rc = need_ready(true);
+    if (rc) return rc;
+    if (!ticket) return fail(TRI_EINVAL, "NULL argument");
+    rc = check_eb(a, want);
+    if (rc) return rc;
+    Slot* S = free_slot();
+    if (!S) return no_slot();
+    CU(cudaSetDevice(g.device));
+    const int64_t N = a->N;
+    if (N > 0) {
+        cudaStream_t cs = g.copy_stream;
+        S->staging.reset();
+        rc = S->staging.reserve((size_t)N * 8 * 16 + (size_t)N * 3 + 8192
+                                + (size_t)std::max<int64_t>(want[0].top_cap, 0) * 16
+                                + (size_t)std::max<int64_t>(want[1].top_cap, 0) * 16);
+        if (rc) return rc;
+        S->pinned.reset();
+        if (!is_pinned(a->inc.ptr)) {
+            rc = S->pinned.reserve(std::min(kPinnedLimit, (size_t)N * 8 * 14 + (size_t)N + 8192));
+            if (rc) return rc;
+        }
+        tri_eb_args d = *a;
+        Col c;
+        STAGE(reb) STAGE(ebfr) STAGE(q) STAGE(P_orb) STAGE(inc) STAGE(ecc) STAGE(argp)
+        STAGE(mtot) STAGE(rhost) STAGE(u1) STAGE(u2) STAGE(cfr) STAGE(lnprior)
+#undef STAGE
+        if (a->extra_mask) {
+            uint8_t* m = S->staging.take<uint8_t>(N);
+            CU(cudaMemcpyAsync(m, via_pinned(*S, a->extra_mask, (size_t)N), (size_t)N,
+                               cudaMemcpyHostToDevice, cs));
+            d.extra_mask = m;
+        }
+        rc = reserve_top(*S, std::max(want[0].top_cap, want[1].top_cap));
+        if (rc) return rc;
+        tri_result r[2];
+        for (int b = 0; b < 2; ++b) {
+            stage_outputs(*S, N, want[b], r[b]);
+            if (r[b].top_cap > 0) {
+                CU(cudaMemsetAsync(r[b].top_idx, 0, (size_t)r[b].top_cap * 8, cs));
+                CU(cudaMemsetAsync(r[b].top_lnL, 0, (size_t)r[b].top_cap * 8, cs));
+            }
+        }
+        CU(cudaEventRecord(S->copied, cs));
+        CU(cudaStreamWaitEvent(g.stream, S->copied, 0));
+        rc = enqueue_eb(*S, d, r, g.stream);
+        if (rc) return rc;
+        for (int b = 0; b < 2; ++b) {
+            rc = queue_outputs(*S, b, want[b], r[b], g.stream);
+            if (rc) return rc;
+        }
+    }
+    CU(cudaEventRecord(S->done, g.stream));
+    commit(*S, 2, N, true, want, ticket);
+    return TRI_OK;
+}
+
+int tri_wait(int64_t ticket, tri_result* out) {
+    int rc = need_ready(false);
+    if (rc) return rc;
+    if (!out) return fail(TRI_EINVAL, "NULL argument");
+    Slot* S = find_slot(ticket);
+    if (!S) return fail(TRI_EINVAL, "unknown ticket (already waited for?)");
+    CU(cudaSetDevice(g.device));
+    cudaError_t e = cudaEventSynchronize(S->done);
+    if (e != cudaSuccess) {
+        S->ticket = 0;
+        return fail(TRI_ECUDA, std::string("cudaEventSynchronize: ") + cudaGetErrorString(e));
+    }
+    finish_slot(*S, out);
+    S->ticket = 0;
+    g.last = S;
+    if (S->host && S->N > 0) {   // per-draw outputs (parity runs): copied now, synchronously
+        for (int b = 0; b < S->branches; ++b) {
+            if (S->d_out_lnl[b])
+                CU(cudaMemcpy(S->want[b].lnL_out, S->d_out_lnl[b], (size_t)S->N * 8,
+                              cudaMemcpyDeviceToHost));
+            if (S->d_out_mask[b])
+                CU(cudaMemcpy(S->want[b].mask_out, S->d_out_mask[b], (size_t)S->N,
+                              cudaMemcpyDeviceToHost));
+        }
+    }
+    return TRI_OK;
+}
+
+// ---- the synchronous forms: submit, then wait ------------------------------------------------
+int tri_eval_tp_dev(const tri_tp_args* a, tri_result* out, void* stream) {
+    int64_t t = 0;
+    int rc = tri_submit_tp_dev(a, out, stream, &t);
+    return rc ? rc : tri_wait(t, out);
 }
 
 int tri_eval_eb_dev(const tri_eb_args* a, tri_result out[2], void* stream) {
-    int rc = need_ready(true);
-    if (rc) return rc;
-    if (!a || !out) return fail(TRI_EINVAL, "NULL argument");
-    rc = check_cols(a->N, {&a->reb, &a->ebfr, &a->q, &a->P_orb, &a->inc, &a->ecc, &a->argp,
-                           &a->mtot, &a->rhost, &a->u1, &a->u2, &a->cfr});
-    if (rc) return rc;
-    CU(cudaSetDevice(g.device));
-    if (a->N == 0) {
-        LsePartial z{-INFINITY, 0.0, 0, 0};
-        for (int b = 0; b < 2; ++b) {
-            finish_result(z, 0, &out[b]);
-            out[b].n_pass = out[b].n_stamps = out[b].n_interior = out[b].n_limb = out[b].n_top = 0;
-        }
-        return TRI_OK;
-    }
-    return eval_eb_device(*a, out, stream ? (cudaStream_t)stream : g.stream);
+    int64_t t = 0;
+    int rc = tri_submit_eb_dev(a, out, stream, &t);
+    return rc ? rc : tri_wait(t, out);
 }
 
 int tri_eval_tp(const tri_tp_args* a, tri_result* out) {
-    int rc = need_ready(true);
-    if (rc) return rc;
-    if (!a || !out) return fail(TRI_EINVAL, "NULL argument");
-    rc = check_cols(a->N, {&a->rp, &a->P_orb, &a->inc, &a->ecc, &a->argp, &a->mtot, &a->rhost,
-                           &a->u1, &a->u2, &a->cfr});
-    if (rc) return rc;
-    if (a->N == 0) return tri_eval_tp_dev(a, out, nullptr);
-    CU(cudaSetDevice(g.device));
-    const int64_t N = a->N;
-    cudaStream_t s = g.stream;
-    g.staging.reset();
-    rc = g.staging.reserve((size_t)N * 8 * 13 + (size_t)N * 2 + 8192
-                           + (size_t)std::max<int64_t>(out->top_cap, 0) * 16);
-    if (rc) return rc;
-    tri_tp_args d = *a;
-    Col c;
-#define STAGE(field)                                   \
-    rc = stage(a->field, N, c, s);                     \
-    if (rc) return rc;                                 \
-    d.field = tri_col{c.p, c.stride};
-    STAGE(rp) STAGE(P_orb) STAGE(inc) STAGE(ecc) STAGE(argp) STAGE(mtot) STAGE(rhost)
-    STAGE(u1) STAGE(u2) STAGE(cfr) STAGE(lnprior)
-    if (a->extra_mask) {
-        uint8_t* m = g.staging.take<uint8_t>(N);
-        CU(cudaMemcpyAsync(m, a->extra_mask, (size_t)N, cudaMemcpyHostToDevice, s));
-        d.extra_mask = m;
-    }
-    tri_result r = *out;
-    double* h_lnl = out->lnL_out;
-    uint8_t* h_mask = out->mask_out;
-    int64_t* h_tidx = out->top_idx;
-    double* h_tval = out->top_lnL;
-    const bool top = out->top_cap > 0 && h_tidx && h_tval;
-    r.lnL_out = h_lnl ? g.staging.take<double>(N) : nullptr;
-    r.mask_out = h_mask ? g.staging.take<uint8_t>(N) : nullptr;
-    r.top_cap = top ? out->top_cap : 0;
-    r.top_idx = top ? g.staging.take<int64_t>(out->top_cap) : nullptr;
-    r.top_lnL = top ? g.staging.take<double>(out->top_cap) : nullptr;
-    rc = eval_tp_device(d, &r, s);
-    if (rc) return rc;
-    if (h_lnl) CU(cudaMemcpyAsync(h_lnl, r.lnL_out, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
-    if (h_mask) CU(cudaMemcpyAsync(h_mask, r.mask_out, (size_t)N, cudaMemcpyDeviceToHost, s));
-    if (top && r.n_top > 0) {
-        CU(cudaMemcpyAsync(h_tidx, r.top_idx, (size_t)r.n_top * 8, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(h_tval, r.top_lnL, (size_t)r.n_top * 8, cudaMemcpyDeviceToHost, s));
-    }
-    CU(cudaStreamSynchronize(s));
-    if (top) sort_candidates(r.n_top, h_tidx, h_tval);
-    r.lnL_out = h_lnl;
-    r.mask_out = h_mask;
-    r.top_cap = out->top_cap;
-    r.top_idx = h_tidx;
-    r.top_lnL = h_tval;
-    *out = r;
-    return TRI_OK;
+    int64_t t = 0;
+    int rc = tri_submit_tp(a, out, &t);
+    return rc ? rc : tri_wait(t, out);
 }
 
 int tri_eval_eb(const tri_eb_args* a, tri_result out[2]) {
-    int rc = need_ready(true);
-    if (rc) return rc;
-    if (!a || !out) return fail(TRI_EINVAL, "NULL argument");
-    rc = check_cols(a->N, {&a->reb, &a->ebfr, &a->q, &a->P_orb, &a->inc, &a->ecc, &a->argp,
-                           &a->mtot, &a->rhost, &a->u1, &a->u2, &a->cfr});
-    if (rc) return rc;
-    if (a->N == 0) return tri_eval_eb_dev(a, out, nullptr);
-    CU(cudaSetDevice(g.device));
-    const int64_t N = a->N;
-    cudaStream_t s = g.stream;
-    g.staging.reset();
-    rc = g.staging.reserve((size_t)N * 8 * 16 + (size_t)N * 3 + 8192
-                           + (size_t)std::max<int64_t>(out[0].top_cap, 0) * 16
-                           + (size_t)std::max<int64_t>(out[1].top_cap, 0) * 16);
-    if (rc) return rc;
-    tri_eb_args d = *a;
-    Col c;
-    STAGE(reb) STAGE(ebfr) STAGE(q) STAGE(P_orb) STAGE(inc) STAGE(ecc) STAGE(argp) STAGE(mtot)
-    STAGE(rhost) STAGE(u1) STAGE(u2) STAGE(cfr) STAGE(lnprior)
-#undef STAGE
-    if (a->extra_mask) {
-        uint8_t* m = g.staging.take<uint8_t>(N);
-        CU(cudaMemcpyAsync(m, a->extra_mask, (size_t)N, cudaMemcpyHostToDevice, s));
-        d.extra_mask = m;
-    }
-    tri_result r[2] = {out[0], out[1]};
-    double* h_lnl[2] = {out[0].lnL_out, out[1].lnL_out};
-    uint8_t* h_mask[2] = {out[0].mask_out, out[1].mask_out};
-    int64_t* h_tidx[2] = {out[0].top_idx, out[1].top_idx};
-    double* h_tval[2] = {out[0].top_lnL, out[1].top_lnL};
-    bool top[2];
-    for (int b = 0; b < 2; ++b) {
-        top[b] = out[b].top_cap > 0 && h_tidx[b] && h_tval[b];
-        r[b].lnL_out = h_lnl[b] ? g.staging.take<double>(N) : nullptr;
-        r[b].mask_out = h_mask[b] ? g.staging.take<uint8_t>(N) : nullptr;
-        r[b].top_cap = top[b] ? out[b].top_cap : 0;
-        r[b].top_idx = top[b] ? g.staging.take<int64_t>(out[b].top_cap) : nullptr;
-        r[b].top_lnL = top[b] ? g.staging.take<double>(out[b].top_cap) : nullptr;
-    }
-    rc = eval_eb_device(d, r, s);
-    if (rc) return rc;
-    for (int b = 0; b < 2; ++b) {
-        if (h_lnl[b])
-            CU(cudaMemcpyAsync(h_lnl[b], r[b].lnL_out, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
-        if (h_mask[b])
-            CU(cudaMemcpyAsync(h_mask[b], r[b].mask_out, (size_t)N, cudaMemcpyDeviceToHost, s));
-        if (top[b] && r[b].n_top > 0) {
-            CU(cudaMemcpyAsync(h_tidx[b], r[b].top_idx, (size_t)r[b].n_top * 8,
-                               cudaMemcpyDeviceToHost, s));
-            CU(cudaMemcpyAsync(h_tval[b], r[b].top_lnL, (size_t)r[b].n_top * 8,
-                               cudaMemcpyDeviceToHost, s));
-        }
-    }
-    CU(cudaStreamSynchronize(s));
-    for (int b = 0; b < 2; ++b) {
-        if (top[b]) sort_candidates(r[b].n_top, h_tidx[b], h_tval[b]);
-        r[b].lnL_out = h_lnl[b];
-        r[b].mask_out = h_mask[b];
-        r[b].top_cap = out[b].top_cap;
-        r[b].top_idx = h_tidx[b];
-        r[b].top_lnL = h_tval[b];
-        out[b] = r[b];
-    }
-    return TRI_OK;
+    int64_t t = 0;
+    int rc = tri_submit_eb(a, out, &t);
+    return rc ? rc : tri_wait(t, out);
 }
 
 static int lnl_seam(int eb, int64_t n, const double* body, const double* ebfr, const double* P,
@@ -701,15 +967,16 @@ static int lnl_seam(int eb, int64_t n, const double* body, const double* ebfr, c
         return fail(TRI_EINVAL, "model matrix too large (n * npts > 2^28): simulate fewer draws");
     CU(cudaSetDevice(g.device));
     cudaStream_t s = g.stream;
-    g.staging.reset();
-    rc = g.staging.reserve((size_t)n * 8 * 14 + 8192 + (model_out ? (size_t)n * npts * 8 : 0));
+    Slot& S = g.slots[kSlots];
+    S.staging.reset();
+    rc = S.staging.reserve((size_t)n * 8 * 14 + 8192 + (model_out ? (size_t)n * npts * 8 : 0));
     if (rc) return rc;
     LnlArgs A{};
     A.lc = g.lc; A.tab = g.tab; A.eb = eb; A.companion_is_host = is_host; A.raw = 1;
     A.twin_uniform = twin ? 1 : 0;
     Col c;
 #define UP(dst, src)                                           \
-    rc = stage(tri_col{src, 1}, n, c, s);                      \
+    rc = stage(S, tri_col{src, 1}, n, c, s);                   \
     if (rc) return rc;                                         \
     A.dst = c;
     UP(body, body)
@@ -717,28 +984,30 @@ static int lnl_seam(int eb, int64_t n, const double* body, const double* ebfr, c
     UP(P, P) UP(inc, inc) UP(a, a) UP(rhost, R_s) UP(u1, u1) UP(u2, u2) UP(ecc, ecc)
     UP(argp, argp) UP(cfr, cfr)
 #undef UP
-    double* d_out = g.staging.take<double>(n);
-    double* d_model = model_out ? g.staging.take<double>((size_t)n * npts) : nullptr;
-    double* d_sec = secdepth_out ? g.staging.take<double>(n) : nullptr;
-    g.launches = 0;
-    CU(cudaMemsetAsync(g.d_counters, 0, 8 * sizeof(unsigned long long), s));
-    A.items = nullptr; A.count = n; A.count_dev = nullptr; A.next = g.d_counters + 2;
-    A.out = d_out; A.out_twin = nullptr; A.counters = g.d_counters + 4;
+    double* d_out = S.staging.take<double>(n);
+    double* d_model = model_out ? S.staging.take<double>((size_t)n * npts) : nullptr;
+    double* d_sec = secdepth_out ? S.staging.take<double>(n) : nullptr;
+    S.launches = 0;
+    CU(cudaMemsetAsync(S.d_counters, 0, 8 * sizeof(unsigned long long), s));
+    A.items = nullptr; A.count = n; A.count_dev = nullptr; A.next = S.d_counters + 2;
+    A.out = d_out; A.out_twin = nullptr; A.counters = S.d_counters + 4;
     A.model_out = d_model; A.secdepth_out = d_sec; A.perm = g.d_perm;
     A.scalar_rule = scalar_rule;
-    CU(cudaEventRecord(g.ev[0], s));
-    CU(cudaEventRecord(g.ev[1], s));
-    rc = launch_lnl(A, s);
+    CU(cudaEventRecord(S.ev[0], s));
+    CU(cudaEventRecord(S.ev[1], s));
+    rc = launch_lnl(S, A, s);
     if (rc) return rc;
-    CU(cudaEventRecord(g.ev[2], s));
-    CU(cudaEventRecord(g.ev[3], s));
+    CU(cudaEventRecord(S.ev[2], s));
+    CU(cudaEventRecord(S.ev[3], s));
     if (out) CU(cudaMemcpyAsync(out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
     if (model_out)
         CU(cudaMemcpyAsync(model_out, d_model, (size_t)n * npts * 8, cudaMemcpyDeviceToHost, s));
     if (secdepth_out)
         CU(cudaMemcpyAsync(secdepth_out, d_sec, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    g.timing_valid = true;
+    S.lnl[0] = S.lnl[1] = nullptr;
+    S.N = n;
+    g.last = &S;
     return TRI_OK;
 }
 
@@ -782,10 +1051,10 @@ int tri_fetch_lnl(int32_t branch, double* out, int64_t N) {
     int rc = need_ready(false);
     if (rc) return rc;
     if (branch < 0 || branch > 1 || !out) return fail(TRI_EINVAL, "bad argument");
-    if (!g.last_lnl[branch] || N != g.last_N)
-        return fail(TRI_ESTATE, "no lnL array of that size from the last tri_eval_* call");
+    if (!g.last || !g.last->lnl[branch] || N != g.last->N)
+        return fail(TRI_ESTATE, "no lnL array of that size from the last completed evaluation");
     CU(cudaSetDevice(g.device));
-    CU(cudaMemcpy(out, g.last_lnl[branch], (size_t)N * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, g.last->lnl[branch], (size_t)N * 8, cudaMemcpyDeviceToHost));
     return TRI_OK;
 }
 
@@ -800,33 +1069,35 @@ int tri_log_mean_exp(const double* logw, int64_t n, tri_result* out) {
     }
     CU(cudaSetDevice(g.device));
     cudaStream_t s = g.stream;
-    g.staging.reset();
-    rc = g.staging.reserve((size_t)n * 8 + (size_t)lse_blocks(n) * sizeof(LsePartial) + 8192);
+    Slot& S = g.slots[kSlots];
+    S.staging.reset();
+    rc = S.staging.reserve((size_t)n * 8 + (size_t)lse_blocks(n) * sizeof(LsePartial) + 8192);
     if (rc) return rc;
-    double* d = g.staging.take<double>(n);
-    LsePartial* parts = g.staging.take<LsePartial>(lse_blocks(n));
+    double* d = S.staging.take<double>(n);
+    LsePartial* parts = S.staging.take<LsePartial>(lse_blocks(n));
     CU(cudaMemcpyAsync(d, logw, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-    g.launches = 0;
-    rc = launch_lse(d, Col{nullptr, 0}, n, parts, g.d_lse_out, s);
+    int launches_before = S.launches;
+    rc = launch_lse(S, d, Col{nullptr, 0}, n, parts, S.d_lse_out, s);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(g.h_lse_out, g.d_lse_out, sizeof(LsePartial), cudaMemcpyDeviceToHost, s));
+    S.launches = launches_before;
+    CU(cudaMemcpyAsync(S.h_lse_out, S.d_lse_out, sizeof(LsePartial), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    finish_result(g.h_lse_out[0], n, out);
+    finish_result(S.h_lse_out[0], n, out);
     return TRI_OK;
 }
 
 int tri_last_timing(double* geometry_ms, double* lnl_ms, double* lse_ms, int32_t* launches) {
     int rc = need_ready(false);
     if (rc) return rc;
-    if (!g.timing_valid) return fail(TRI_ESTATE, "no timed call yet");
+    if (!g.last || g.last->N == 0) return fail(TRI_ESTATE, "no timed call yet");
     float a = 0, b = 0, c = 0;
-    CU(cudaEventElapsedTime(&a, g.ev[0], g.ev[1]));
-    CU(cudaEventElapsedTime(&b, g.ev[1], g.ev[2]));
-    CU(cudaEventElapsedTime(&c, g.ev[2], g.ev[3]));
+    CU(cudaEventElapsedTime(&a, g.last->ev[0], g.last->ev[1]));
+    CU(cudaEventElapsedTime(&b, g.last->ev[1], g.last->ev[2]));
+    CU(cudaEventElapsedTime(&c, g.last->ev[2], g.last->ev[3]));
     if (geometry_ms) *geometry_ms = a;
     if (lnl_ms) *lnl_ms = b;
     if (lse_ms) *lse_ms = c;
-    if (launches) *launches = g.launches;
+    if (launches) *launches = g.last->launches;
     return TRI_OK;
 }
 

@@ -167,8 +167,9 @@ struct LnlArgs {
     unsigned long long* next;  // work-queue cursor
     double* out;             // lnL of the (EB) branch, indexed by sample
     double* out_twin;        // lnL of the twin branch (fused EB only)
-    unsigned long long* counters;  // optional [4]: model points evaluated, time stamps in
-                                   // windows, interior-case points, limb/edge-case points
+    unsigned long long* counters;  // optional [4]: stamps inside transit windows, stamps whose
+                                   // sub-exposures were evaluated (window minus centre-probe
+                                   // skips), interior-case points, limb/edge-case points
     // simulate mode (simulate_TP_transit_p / simulate_EB_transit_p, likelihoods.py:302-439):
     double* model_out;       // optional [count][npts] diluted model flux, caller's stamp order
     double* secdepth_out;    // optional [count] secondary-eclipse depth (EB-type)
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
     const double sigma = lc.sigma;
     unsigned long long n_stamps = 0;
     unsigned n_interior = 0, n_limb = 0;   // per lane; flushed per draw
+    unsigned n_skip = 0;                    // per lane: window stamps the centre probe dismissed
     unsigned long long n_int_tot = 0, n_limb_tot = 0;
     const int64_t count = A.count_dev ? (int64_t)(*A.count_dev) : A.count;
 
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                         const double toff = is ? exptime * ((is - 0.5) * inv_ns - 0.5) : 0.0;
                         const double z = z_at(o, A.tab, t + toff);
                         if (is == 0) {   // stamp centre: is the whole exposure out of transit?
-                            if (fabs(z) > skip_beyond) { acc = (double)ns; break; }
+                            if (fabs(z) > skip_beyond) { acc = (double)ns; ++n_skip; break; }
                             continue;
                         }
                         acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
@@ -382,13 +384,15 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
         n_interior = n_limb = 0;
     }
     if (A.counters) {
+        unsigned long long n_skip_tot = n_skip;
         for (int o = 16; o > 0; o >>= 1) {
+            n_skip_tot += __shfl_xor_sync(0xffffffffu, n_skip_tot, o);
             n_int_tot += __shfl_xor_sync(0xffffffffu, n_int_tot, o);
             n_limb_tot += __shfl_xor_sync(0xffffffffu, n_limb_tot, o);
         }
         if (lane == 0) {
-            atomicAdd(A.counters + 0, n_stamps * (unsigned long long)lc.nsamples);
-            atomicAdd(A.counters + 1, n_stamps);
+            atomicAdd(A.counters + 0, n_stamps);   // stamps inside the transit windows
+            atomicAdd(A.counters + 1, n_stamps - n_skip_tot);
             atomicAdd(A.counters + 2, n_int_tot);
             atomicAdd(A.counters + 3, n_limb_tot);
         }

@@ -201,23 +201,36 @@ def _table(lb, dev, twin, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cf
 
 def _run_tp(eng, dev, n, N, M_host, R_host, u1, u2, P, mtot, rps, incs, eccs, argps, cfr, lnprior,
             extra_mask, is_host):
-    res = eng.eval_tp_tensors(n, dict(rp=rps, P_orb=P, inc=incs, ecc=eccs, argp=argps, mtot=mtot,
-                                      rhost=R_host, u1=u1, u2=u2, cfr=cfr, lnprior=lnprior),
-                              extra_mask, is_host, N_SAMPLES)
-    lb = _dispatch.gather_local(res, N, eng)
-    return _table(lb, dev, False, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cfr, rps=rps)
+    p = _dispatch._submit(eng, "tp_tensors", n,
+                          dict(rp=rps, P_orb=P, inc=incs, ecc=eccs, argp=argps, mtot=mtot,
+                               rhost=R_host, u1=u1, u2=u2, cfr=cfr, lnprior=lnprior),
+                          extra_mask, is_host, N_SAMPLES)
+
+    def table():
+        lb = _dispatch.gather_local(p.result(), N, eng)
+        return _table(lb, dev, False, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cfr,
+                      rps=rps)
+    return _dispatch.deliver(table)
 
 
 def _run_eb(eng, dev, n, N, M_host, R_host, u1, u2, P, mtot, incs, qs, eccs, argps, masses, radii,
             fluxratios, cfr, lnprior, extra_mask, is_host):
-    r0, r1 = eng.eval_eb_tensors(n, dict(reb=radii, ebfr=fluxratios, q=qs, P_orb=P, inc=incs,
-                                         ecc=eccs, argp=argps, mtot=mtot, rhost=R_host, u1=u1,
-                                         u2=u2, cfr=cfr, lnprior=lnprior),
-                                 extra_mask, is_host, N_SAMPLES)
+    p = _dispatch._submit(eng, "eb_tensors", n,
+                          dict(reb=radii, ebfr=fluxratios, q=qs, P_orb=P, inc=incs, ecc=eccs,
+                               argp=argps, mtot=mtot, rhost=R_host, u1=u1, u2=u2, cfr=cfr,
+                               lnprior=lnprior),
+                          extra_mask, is_host, N_SAMPLES)
     common = (M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cfr)
     kw = dict(masses=masses, radii=radii, fluxratios=fluxratios)
-    return (_table(_dispatch.gather_local(r0, N, eng), dev, False, *common, **kw),
-            _table(_dispatch.gather_local(r1, N, eng), dev, True, *common, **kw))
+    both = []
+
+    def tables():   # both branches at the first request, in a fixed order (collectives inside)
+        if not both:
+            r0, r1 = p.result()
+            both.append(_table(_dispatch.gather_local(r0, N, eng), dev, False, *common, **kw))
+            both.append(_table(_dispatch.gather_local(r1, N, eng), dev, True, *common, **kw))
+        return both
+    return _dispatch.deliver(lambda: tables()[0]), _dispatch.deliver(lambda: tables()[1])
 
 
 # ------------------------------------------------------------------------------- scenarios

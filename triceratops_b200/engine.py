@@ -46,6 +46,35 @@ class BranchResult:
             self.n_evaluated = None
 
 
+class Pending:
+    """An evaluation queued with tri_submit_* and not necessarily finished.  `result()` waits
+    for it (once) and returns what the synchronous call returns."""
+
+    def __init__(self, engine, ticket, rr, n_branches, keep, build, n_best):
+        self._engine, self._ticket, self._rr, self._nb = engine, ticket, rr, n_branches
+        self._keep, self._build, self._n_best = keep, build, n_best
+        self._out = None
+
+    def done(self):
+        return self._out is not None
+
+    def result(self):
+        if self._out is None:
+            eng = self._engine
+            _cabi.check(eng.lib.tri_wait(ctypes.c_int64(self._ticket), self._rr))
+            eng._inflight.remove(self)
+            out = self._build(self._rr)
+            # fewer finite draws than the table has rows: the caller pads the table from the
+            # full lnL array, which is only reachable until the next evaluation completes
+            for b, br in enumerate(out):
+                if (self._n_best > 0 and br.lnL is None and br.N > 0
+                        and br.n_evaluated is not None and br.n_evaluated < self._n_best):
+                    br.lnL = eng.fetch_lnl(b, br.N)
+            self._keep = None
+            self._out = out[0] if self._nb == 1 else tuple(out)
+        return self._out
+
+
 def combine_lse(parts, N_total):
     """lnZ from per-rank (m, s, n_finite, n_posinf) records over disjoint slices of N_total draws.
 
@@ -71,6 +100,17 @@ class Engine:
         _cabi.check(self.lib.tri_init(self.device))
         self._lc_key = None
         self._keep = []
+        self._inflight = []      # Pendings not waited for yet, oldest first
+
+    def _make_room(self):
+        """The library holds TRI_MAX_INFLIGHT evaluations: wait for the oldest when full."""
+        while len(self._inflight) >= _cabi.TRI_MAX_INFLIGHT:
+            self._inflight[0].result()
+
+    def drain(self):
+        """Wait for everything in flight (results stay available from their Pendings)."""
+        while self._inflight:
+            self._inflight[0].result()
 
     # ------------------------------------------------------------------ light curve
     def set_lightcurve(self, time, flux, sigma, exptime, nsamples):
@@ -131,10 +171,19 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ L2 seam
-    def eval_tp(self, N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
-                extra_mask=None, companion_is_host=False, want_lnL=True, want_mask=False,
-                n_best=0):
+    def eval_tp(self, *args, **kw):
+        return self.submit_tp(*args, **kw).result()
+
+    def eval_eb(self, *args, **kw):
+        return self.submit_eb(*args, **kw).result()
+
+    def submit_tp(self, N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
+                  extra_mask=None, companion_is_host=False, want_lnL=True, want_mask=False,
+                  n_best=0):
+        """Queue a TP-type evaluation (tri_submit_tp) and return its Pending: the column copies
+        overlap the kernels of the call submitted before.  `eval_tp` is submit + result()."""
         N = int(N)
+        self._make_room()
         self._keep = []
         a = tri_tp_args()
         a.N = N
@@ -145,14 +194,23 @@ class Engine:
         a.extra_mask = self._mask(extra_mask, N)
         a.companion_is_host = int(bool(companion_is_host))
         r, lnL, mask, top = self._result(N, want_lnL, want_mask, n_best)
-        _cabi.check(self.lib.tri_eval_tp(ctypes.byref(a), ctypes.byref(r)))
-        self._keep = []
-        return BranchResult(r, N, lnL, mask.astype(bool) if mask is not None else None, top, 0)
+        rr = (tri_result * 1)(r)
+        ticket = ctypes.c_int64()
+        _cabi.check(self.lib.tri_submit_tp(ctypes.byref(a), rr, ctypes.byref(ticket)))
+        keep, self._keep = self._keep + [a, lnL, mask, top], []
 
-    def eval_eb(self, N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr,
-                lnprior=None, extra_mask=None, companion_is_host=False, want_lnL=True,
-                want_mask=False, n_best=0):
+        def build(rr):
+            return [BranchResult(rr[0], N, lnL, mask.astype(bool) if mask is not None else None,
+                                 top, 0)]
+        p = Pending(self, ticket.value, rr, 1, keep, build, n_best)
+        self._inflight.append(p)
+        return p
+
+    def submit_eb(self, N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr,
+                  lnprior=None, extra_mask=None, companion_is_host=False, want_lnL=True,
+                  want_mask=False, n_best=0):
         N = int(N)
+        self._make_room()
         self._keep = []
         a = tri_eb_args()
         a.N = N
@@ -168,12 +226,18 @@ class Engine:
             r, lnL, mask, top = self._result(N, want_lnL, want_mask, n_best)
             rr[b] = r
             outs.append((lnL, mask, top))
-        _cabi.check(self.lib.tri_eval_eb(ctypes.byref(a), rr))
-        self._keep = []
-        return tuple(BranchResult(rr[b], N, outs[b][0],
-                                  outs[b][1].astype(bool) if outs[b][1] is not None else None,
-                                  outs[b][2], b)
-                     for b in range(2))
+        ticket = ctypes.c_int64()
+        _cabi.check(self.lib.tri_submit_eb(ctypes.byref(a), rr, ctypes.byref(ticket)))
+        keep, self._keep = self._keep + [a, outs], []
+
+        def build(rr):
+            return [BranchResult(rr[b], N, outs[b][0],
+                                 outs[b][1].astype(bool) if outs[b][1] is not None else None,
+                                 outs[b][2], b)
+                    for b in range(2)]
+        p = Pending(self, ticket.value, rr, 2, keep, build, n_best)
+        self._inflight.append(p)
+        return p
 
     # ------------------------------------------------------------------ L2 seam, device columns
     def _tensor_col(self, x, N, keep):
@@ -219,9 +283,10 @@ class Engine:
         order = np.lexsort((idx, -val))
         return idx[order], val[order]
 
-    def _eval_tensors(self, kind, N, cols, extra_mask, companion_is_host, n_best):
+    def _submit_tensors(self, kind, N, cols, extra_mask, companion_is_host, n_best):
         import torch
         N = int(N)
+        self._make_room()
         keep = []
         a = tri_tp_args() if kind == "tp" else tri_eb_args()
         a.N = N
@@ -242,20 +307,32 @@ class Engine:
             rr[b], ti, tv = self._tensor_result(N, n_best, keep)
             tops.append((ti, tv))
         stream = torch.cuda.current_stream(self._torch_device()).cuda_stream
-        fn = self.lib.tri_eval_tp_dev if kind == "tp" else self.lib.tri_eval_eb_dev
-        _cabi.check(fn(ctypes.byref(a), rr, ctypes.c_void_p(stream)))
-        out = []
-        for b in range(nb):
-            out.append(BranchResult(rr[b], N, None, None, self._sorted_top(rr[b], *tops[b]), b))
-        return out
+        fn = self.lib.tri_submit_tp_dev if kind == "tp" else self.lib.tri_submit_eb_dev
+        ticket = ctypes.c_int64()
+        _cabi.check(fn(ctypes.byref(a), rr, ctypes.c_void_p(stream), ctypes.byref(ticket)))
+        keep.append(a)
 
-    def eval_tp_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
-        """tri_eval_tp_dev on torch CUDA tensors (columns: rp, P_orb, inc, ecc, argp, mtot, rhost,
-        u1, u2, cfr, lnprior; tensors of N values or scalars)."""
-        return self._eval_tensors("tp", N, cols, extra_mask, companion_is_host, n_best)[0]
+        def build(rr):
+            return [BranchResult(rr[b], N, None, None, self._sorted_top(rr[b], *tops[b]), b)
+                    for b in range(nb)]
+        p = Pending(self, ticket.value, rr, nb, keep, build, 0)
+        self._inflight.append(p)
+        return p
 
-    def eval_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
-        return tuple(self._eval_tensors("eb", N, cols, extra_mask, companion_is_host, n_best))
+    def submit_tp_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
+        """tri_submit_tp_dev on torch CUDA tensors (columns: rp, P_orb, inc, ecc, argp, mtot,
+        rhost, u1, u2, cfr, lnprior; tensors of N values or scalars), queued on torch's current
+        stream behind the kernels that produce them.  Returns a Pending."""
+        return self._submit_tensors("tp", N, cols, extra_mask, companion_is_host, n_best)
+
+    def submit_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
+        return self._submit_tensors("eb", N, cols, extra_mask, companion_is_host, n_best)
+
+    def eval_tp_tensors(self, *args, **kw):
+        return self.submit_tp_tensors(*args, **kw).result()
+
+    def eval_eb_tensors(self, *args, **kw):
+        return self.submit_eb_tensors(*args, **kw).result()
 
     # ------------------------------------------------------------------ L1 seam
     def lnl_tp(self, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr, companion_is_host):

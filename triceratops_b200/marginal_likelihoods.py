@@ -207,19 +207,21 @@ def _eb_result(br, twin, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, mas
 
 def _run_tp(N, M_host, R_host, u1, u2, P, mtot, rps, incs, eccs, argps, cfr, lnprior,
             extra_mask, companion_is_host):
-    br = _dispatch.run_tp(N, rps, P, incs, eccs, argps, mtot, R_host, u1, u2, cfr,
-                          lnprior=lnprior, extra_mask=extra_mask,
-                          companion_is_host=companion_is_host)
-    return _tp_result(br, M_host, R_host, u1, u2, P, mtot, incs, rps, eccs, argps, cfr)
+    pb = _dispatch.submit_tp(N, rps, P, incs, eccs, argps, mtot, R_host, u1, u2, cfr,
+                             lnprior=lnprior, extra_mask=extra_mask,
+                             companion_is_host=companion_is_host)
+    return _dispatch.deliver(lambda: _tp_result(pb.finish(), M_host, R_host, u1, u2, P, mtot,
+                                                incs, rps, eccs, argps, cfr))
 
 
 def _run_eb(N, M_host, R_host, u1, u2, P, mtot, incs, qs, eccs, argps, masses, radii,
             fluxratios, cfr, lnprior, extra_mask, companion_is_host):
-    br, br_twin = _dispatch.run_eb(N, radii, fluxratios, qs, P, incs, eccs, argps, mtot, R_host,
-                                   u1, u2, cfr, lnprior=lnprior, extra_mask=extra_mask,
-                                   companion_is_host=companion_is_host)
+    pb = _dispatch.submit_eb(N, radii, fluxratios, qs, P, incs, eccs, argps, mtot, R_host,
+                             u1, u2, cfr, lnprior=lnprior, extra_mask=extra_mask,
+                             companion_is_host=companion_is_host)
     common = (M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, masses, radii, fluxratios, cfr)
-    return _eb_result(br, False, *common), _eb_result(br_twin, True, *common)
+    return (_dispatch.deliver(lambda: _eb_result(pb.finish()[0], False, *common)),
+            _dispatch.deliver(lambda: _eb_result(pb.finish()[1], True, *common)))
 
 
 # ------------------------------------------------------------------- target-star scenarios

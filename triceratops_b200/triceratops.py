@@ -12,12 +12,14 @@ package's scope: there is no network here, so a 
 from a stars table the caller already has (the reference's `target.stars` DataFrame, e.g. saved
 from an online session), optionally its `pix_coords`, and a saved TRILEGAL file.
 """
+import collections
 import warnings
 
 import numpy as np
 from pandas import DataFrame
 from scipy.special import ndtr
 
+from . import _dispatch
 from ._numerics import _normalize_probabilities
 from .funcs import renorm_flux
 from .marginal_likelihoods import (lnZ_BEB, lnZ_BTP, lnZ_DEB, lnZ_DTP, lnZ_PEB, lnZ_PTP, lnZ_SEB,
@@ -25,6 +27,9 @@ from .marginal_likelihoods import (lnZ_BEB, lnZ_BTP, lnZ_DEB, lnZ_DTP, lnZ_PEB, 
 
 _STAR_COLUMNS = ("ID", "Tmag", "Jmag", "Hmag", "Kmag", "ra", "dec", "mass", "rad", "Teff", "plx",
                  "fluxratio", "tdepth")
+
+# scenario rows whose results may still be in flight while the next scenario is being drawn
+_PIPELINE_DEPTH = 3
 
 _RESULT_KEYS = ("M_s", "R_s", "u1", "u2", "P_orb", "inc", "b", "R_p", "ecc", "argp", "M_EB",
                 "R_EB", "fluxratio_EB", "fluxratio_comp")
@@ -145,14 +150,25 @@ class target:
         best = {k: np.zeros(n_rows) for k in _RESULT_KEYS}
         lnZ = np.zeros(n_rows)
 
+        # Results are read a few scenarios after they were requested: the GPU works on one
+        # scenario while the host draws the priors of the next (_dispatch.deferring).
+        waiting = collections.deque()
+
+        def settle(keep):
+            while len(waiting) > keep:
+                j, res = waiting.popleft()
+                res = _dispatch.resolve(res)
+                for k in _RESULT_KEYS:
+                    best[k][j] = res[k][0]
+                lnZ[j] = res["lnZ"]
+
         def store(j, ID, num, name, res):
             targets[j], star_num[j], scenarios[j] = ID, num, name
             if res is None:
                 lnZ[j] = -np.inf
                 return
-            for k in _RESULT_KEYS:
-                best[k][j] = res[k][0]
-            lnZ[j] = res["lnZ"]
+            waiting.append((j, res))
+            settle(_PIPELINE_DEPTH)
 
         def say(msg):
             if verbose == 1:
@@ -163,71 +179,73 @@ class target:
                                "the online query of the reference is out of scope")
         trilegal_fname = self.trilegal_fname
 
-        for i, ID in enumerate(filtered["ID"].values):
-            star = {c: filtered[c].values[i] for c in _STAR_COLUMNS}
-            flux, flux_err = renorm_flux(flux_0, flux_err_0, star["fluxratio"])
-            M_s, R_s, Teff, plx = star["mass"], star["rad"], star["Teff"], star["plx"]
-            mags = (star["Tmag"], star["Jmag"], star["Hmag"], star["Kmag"])
-            Z = 0.0
-            lc = (time, flux, flux_err, P_orb)
-            tail = (N, parallel, self.mission, flatpriors, exptime, nsamples)
+        with _dispatch.deferring():
+            for i, ID in enumerate(filtered["ID"].values):
+                star = {c: filtered[c].values[i] for c in _STAR_COLUMNS}
+                flux, flux_err = renorm_flux(flux_0, flux_err_0, star["fluxratio"])
+                M_s, R_s, Teff, plx = star["mass"], star["rad"], star["Teff"], star["plx"]
+                mags = (star["Tmag"], star["Jmag"], star["Hmag"], star["Kmag"])
+                Z = 0.0
+                lc = (time, flux, flux_err, P_orb)
+                tail = (N, parallel, self.mission, flatpriors, exptime, nsamples)
 
-            if i == 0:
-                if np.isnan(M_s) or np.isnan(R_s) or np.isnan(Teff) or np.isnan(plx):
-                    print("Insufficient information to validate " + str(ID)
-                          + ". Please ensure a stellar mass (in M_Sun), radius (in R_Sun), "
-                          + "Teff (in K), and plx (in mas) are provided in the .stars dataframe.")
-                    break
-                runners = {
-                    "TP": lambda: lnZ_TTP(*lc, M_s, R_s, Teff, Z, *tail),
-                    "EB": lambda: lnZ_TEB(*lc, M_s, R_s, Teff, Z, *tail),
-                    "PTP": lambda: lnZ_PTP(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
-                                           filt, *tail, molusc_file),
-                    "PEB": lambda: lnZ_PEB(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
-                                           filt, *tail, molusc_file),
-                    "STP": lambda: lnZ_STP(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
-                                           filt, *tail, molusc_file),
-                    "SEB": lambda: lnZ_SEB(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
-                                           filt, *tail, molusc_file),
-                    "DTP": lambda: lnZ_DTP(*lc, M_s, R_s, Teff, Z, *mags, trilegal_fname,
-                                           contrast_curve_file, filt, *tail),
-                    "DEB": lambda: lnZ_DEB(*lc, M_s, R_s, Teff, Z, *mags, trilegal_fname,
-                                           contrast_curve_file, filt, *tail),
-                    "BTP": lambda: lnZ_BTP(*lc, M_s, R_s, Teff, *mags, trilegal_fname,
-                                           contrast_curve_file, filt, *tail),
-                    "BEB": lambda: lnZ_BEB(*lc, M_s, R_s, Teff, *mags, trilegal_fname,
-                                           contrast_curve_file, filt, *tail),
-                }
-                for key, row, num, names in _TARGET_SCENARIOS:
-                    if key in drop_scenario:
-                        for k, name in enumerate(names):
-                            store(row + k, ID, num, name, None)
-                        continue
-                    if len(names) == 1:
-                        say("Calculating " + names[0] + " scenario probability for "
-                            + str(ID) + ".")
-                        store(row, ID, num, names[0], runners[key]())
-                    else:
-                        say("Calculating " + names[0] + " and " + names[1]
-                            + " scenario probabilities for " + str(ID) + ".")
-                        res, res_twin = runners[key]()
-                        store(row, ID, num, names[0], res)
-                        store(row + 1, ID, num, names[1], res_twin)
-            else:
-                # nearby star: unknown properties default to solar (triceratops.py:1345-1350)
-                if np.isnan(Teff):
-                    Teff = 5777
-                if np.isnan(M_s):
-                    M_s = 1.0
-                if np.isnan(R_s):
-                    R_s = 1.0
-                say("Calculating NTP, NEB, and NEB2xP scenario probabilities for "
-                    + str(ID) + ".")
-                row = 15 + 3 * (i - 1)
-                store(row, ID, 1, "NTP", lnZ_TTP(*lc, M_s, R_s, Teff, Z, *tail))
-                res, res_twin = lnZ_TEB(*lc, M_s, R_s, Teff, Z, *tail)
-                store(row + 1, ID, 1, "NEB", res)
-                store(row + 2, ID, 1, "NEBx2P", res_twin)
+                if i == 0:
+                    if np.isnan(M_s) or np.isnan(R_s) or np.isnan(Teff) or np.isnan(plx):
+                        print("Insufficient information to validate " + str(ID)
+                              + ". Please ensure a stellar mass (in M_Sun), radius (in R_Sun), "
+                              + "Teff (in K), and plx (in mas) are provided in the .stars dataframe.")
+                        break
+                    runners = {
+                        "TP": lambda: lnZ_TTP(*lc, M_s, R_s, Teff, Z, *tail),
+                        "EB": lambda: lnZ_TEB(*lc, M_s, R_s, Teff, Z, *tail),
+                        "PTP": lambda: lnZ_PTP(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                               filt, *tail, molusc_file),
+                        "PEB": lambda: lnZ_PEB(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                               filt, *tail, molusc_file),
+                        "STP": lambda: lnZ_STP(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                               filt, *tail, molusc_file),
+                        "SEB": lambda: lnZ_SEB(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                               filt, *tail, molusc_file),
+                        "DTP": lambda: lnZ_DTP(*lc, M_s, R_s, Teff, Z, *mags, trilegal_fname,
+                                               contrast_curve_file, filt, *tail),
+                        "DEB": lambda: lnZ_DEB(*lc, M_s, R_s, Teff, Z, *mags, trilegal_fname,
+                                               contrast_curve_file, filt, *tail),
+                        "BTP": lambda: lnZ_BTP(*lc, M_s, R_s, Teff, *mags, trilegal_fname,
+                                               contrast_curve_file, filt, *tail),
+                        "BEB": lambda: lnZ_BEB(*lc, M_s, R_s, Teff, *mags, trilegal_fname,
+                                               contrast_curve_file, filt, *tail),
+                    }
+                    for key, row, num, names in _TARGET_SCENARIOS:
+                        if key in drop_scenario:
+                            for k, name in enumerate(names):
+                                store(row + k, ID, num, name, None)
+                            continue
+                        if len(names) == 1:
+                            say("Calculating " + names[0] + " scenario probability for "
+                                + str(ID) + ".")
+                            store(row, ID, num, names[0], runners[key]())
+                        else:
+                            say("Calculating " + names[0] + " and " + names[1]
+                                + " scenario probabilities for " + str(ID) + ".")
+                            res, res_twin = runners[key]()
+                            store(row, ID, num, names[0], res)
+                            store(row + 1, ID, num, names[1], res_twin)
+                else:
+                    # nearby star: unknown properties default to solar (triceratops.py:1345-1350)
+                    if np.isnan(Teff):
+                        Teff = 5777
+                    if np.isnan(M_s):
+                        M_s = 1.0
+                    if np.isnan(R_s):
+                        R_s = 1.0
+                    say("Calculating NTP, NEB, and NEB2xP scenario probabilities for "
+                        + str(ID) + ".")
+                    row = 15 + 3 * (i - 1)
+                    store(row, ID, 1, "NTP", lnZ_TTP(*lc, M_s, R_s, Teff, Z, *tail))
+                    res, res_twin = lnZ_TEB(*lc, M_s, R_s, Teff, Z, *tail)
+                    store(row + 1, ID, 1, "NEB", res)
+                    store(row + 2, ID, 1, "NEBx2P", res_twin)
+            settle(0)
 
         relative_probs, status = _normalize_probabilities(lnZ)
         if status == 'anomaly':
