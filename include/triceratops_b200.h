@@ -109,7 +109,8 @@ int tri_eval_tp(const tri_tp_args* args, tri_result* out);
 int tri_eval_eb(const tri_eb_args* args, tri_result out[2]); /* [0]=EB, [1]=EBx2P */
 
 /* Same with every pointer (columns, extra_mask, lnL_out, mask_out) in DEVICE memory; work is
- * queued on `stream` (a cudaStream_t, NULL = the library's stream) and the call returns after
+ * queued on `stream` (a cudaStream_t; NULL = the CUDA default stream, so that the work is ordered
+ * after the kernels that produced the columns there) and the call returns after
  * the small result record has been read back. */
 int tri_eval_tp_dev(const tri_tp_args* args, tri_result* out, void* stream);
 int tri_eval_eb_dev(const tri_eb_args* args, tri_result out[2], void* stream);
@@ -173,6 +174,14 @@ int tri_log_mean_exp(const double* logw, int64_t n, tri_result* out);
 /* Device time [ms] of the kernels of the most recent eval/lnl call, from CUDA events on the
  * stream they ran on: geometry, light-curve/chi^2, log-mean-exp, and their launch count. */
 int tri_last_timing(double* geometry_ms, double* lnl_ms, double* lse_ms, int32_t* launches);
+
+/* Device-side prior sampler support (opt-in mode, triceratops_b200.set_sampler("device")):
+ * FITPACK B-spline evaluation y[i] = s(x[i]) for the stellar relations of funcs.py:54-140
+ * (scipy splev, ext=0: the end intervals extrapolate).  t[n] knots and c[n] coefficients of a
+ * degree-k spline (1 <= k <= 5, n <= 512); every pointer is a DEVICE pointer; x and y may alias.
+ * Queued on `stream` (NULL = the CUDA default stream); does not wait for the GPU. */
+int tri_dev_splev(const double* t, const double* c, int32_t n, int32_t k, const double* x,
+                  double* y, int64_t N, void* stream);
 
 /* Measured FP64 FMA issue rate of this GPU [DFMA/s] (roofline denominator). */
 int tri_fp64_peak(double* dfma_per_s);

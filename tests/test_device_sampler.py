@@ -235,3 +235,24 @@ def test_device_mode_calc_probs_runs_and_is_reproducible(gpu_engine, toi465_lc, 
     finally:
         triceratops_b200.set_sampler("host")
     assert np.array_equal(out[0], out[1])      # same seed, same streams, same answer
+
+
+@pytest.mark.gpu
+def test_splev_kernel_matches_scipy(gpu_engine):
+    """tri_dev_splev (one launch per spline evaluation in device mode) against scipy's FITPACK,
+    inside the knot range and extrapolating beyond both ends."""
+    import torch
+    from scipy.interpolate import InterpolatedUnivariateSpline, splev as sp_splev
+    from triceratops_b200 import device_priors as dp, funcs
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(0.05, 2.6, 200_000), [0.0, 0.1, 0.63, 2.0, 3.5, -1.0]])
+    xd = torch.as_tensor(x, device="cuda")
+    splines = [funcs._hot_R, funcs._cool_R, funcs._hot_T, funcs._cool_T]
+    splines += list(funcs._FLUX_SPLINES.values())
+    for k in (1, 2, 4, 5):     # the stellar relations are cubic; cover the other degrees too
+        xs = np.linspace(0, 3, 15)
+        splines.append(InterpolatedUnivariateSpline(xs, np.sin(xs) + xs ** 2, k=k))
+    for spl in splines:
+        want = sp_splev(x, spl._eval_args, ext=0)
+        got = dp.splev(spl, xd).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-13 * np.abs(want).max())

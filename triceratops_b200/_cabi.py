@@ -57,7 +57,8 @@ EXPORTS = ("tri_init", "tri_shutdown", "tri_last_error", "tri_set_lightcurve", "
            "tri_eval_eb", "tri_eval_tp_dev", "tri_eval_eb_dev", "tri_lnl_tp", "tri_lnl_eb",
            "tri_simulate_tp", "tri_simulate_eb",
            "tri_fetch_lnl", "tri_log_mean_exp", "tri_last_timing", "tri_fp64_peak", "tri_sm_count",
-           "tri_submit_tp", "tri_submit_eb", "tri_submit_tp_dev", "tri_submit_eb_dev", "tri_wait")
+           "tri_submit_tp", "tri_submit_eb", "tri_submit_tp_dev", "tri_submit_eb_dev", "tri_wait",
+           "tri_dev_splev")
 
 _lib = None
 
@@ -98,6 +99,8 @@ def load():
     L.tri_submit_eb_dev.argtypes = [ctypes.POINTER(tri_eb_args), ctypes.POINTER(tri_result),
                                     ctypes.c_void_p, c_i64_p]
     L.tri_wait.argtypes = [ctypes.c_int64, ctypes.POINTER(tri_result)]
+    L.tri_dev_splev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     L.tri_lnl_tp.argtypes = [ctypes.c_int64] + [c_double_p] * 10 + [ctypes.c_int32, c_double_p]
     L.tri_lnl_eb.argtypes = ([ctypes.c_int64] + [c_double_p] * 11
                              + [ctypes.c_int32, ctypes.c_int32, c_double_p])

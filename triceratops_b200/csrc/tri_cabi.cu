@@ -709,7 +709,7 @@ int tri_submit_tp_dev(const tri_tp_args* a, const tri_result* want, void* stream
     Slot* S = free_slot();
     if (!S) return no_slot();
     CU(cudaSetDevice(g.device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    cudaStream_t s = (cudaStream_t)stream;   // NULL is the CUDA default stream, as everywhere
     if (a->N > 0) {
         rc = enqueue_tp(*S, *a, *want, s);
         if (rc) return rc;
@@ -729,7 +729,7 @@ int tri_submit_eb_dev(const tri_eb_args* a, const tri_result want[2], void* stre
     Slot* S = free_slot();
     if (!S) return no_slot();
     CU(cudaSetDevice(g.device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    cudaStream_t s = (cudaStream_t)stream;   // NULL is the CUDA default stream, as everywhere
     if (a->N > 0) {
         rc = enqueue_eb(*S, *a, want, s);
         if (rc) return rc;
@@ -1098,6 +1098,28 @@ int tri_last_timing(double* geometry_ms, double* lnl_ms, double* lse_ms, int32_t
     if (lnl_ms) *lnl_ms = b;
     if (lse_ms) *lse_ms = c;
     if (launches) *launches = g.last->launches;
+    return TRI_OK;
+}
+
+int tri_dev_splev(const double* t, const double* c, int32_t n, int32_t k, const double* x,
+                  double* y, int64_t N, void* stream) {
+    int rc = need_ready(false);
+    if (rc) return rc;
+    if (!t || !c || N < 0 || (N > 0 && (!x || !y))) return fail(TRI_EINVAL, "NULL argument");
+    if (k < 1 || k > 5 || n < 2 * (k + 1) || n > kSplevMaxKnots)
+        return fail(TRI_EINVAL, "spline degree must be 1..5 and 2(k+1) <= knots <= 512");
+    if (N == 0) return TRI_OK;
+    CU(cudaSetDevice(g.device));
+    cudaStream_t s = (cudaStream_t)stream;   // NULL is the CUDA default stream, as everywhere
+    int blocks = (int)std::min<int64_t>((N + 255) / 256, (int64_t)g.sm_count * 8);
+    switch (k) {
+        case 1: splev_kernel<1><<<blocks, 256, 0, s>>>(t, c, n, x, y, N); break;
+        case 2: splev_kernel<2><<<blocks, 256, 0, s>>>(t, c, n, x, y, N); break;
+        case 3: splev_kernel<3><<<blocks, 256, 0, s>>>(t, c, n, x, y, N); break;
+        case 4: splev_kernel<4><<<blocks, 256, 0, s>>>(t, c, n, x, y, N); break;
+        default: splev_kernel<5><<<blocks, 256, 0, s>>>(t, c, n, x, y, N); break;
+    }
+    CU(cudaGetLastError());
     return TRI_OK;
 }
 

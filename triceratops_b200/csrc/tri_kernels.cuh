@@ -602,6 +602,55 @@ topk_collect_ties_kernel(const double* lnl, int64_t N, TopkState* st, int64_t* o
     if (threadIdx.x == 0) st->n_out = base_sh;
 }
 
+// ---- FITPACK B-spline evaluation (device sampler: stellar relations, funcs.py:54-140) ----------
+// y[i] = s(x[i]) for the spline (t[n], c[n], degree k <= 5) with extrapolation from the end
+// intervals (splev ext=0): interval search + de Boor's recurrence (fpbspl), one thread per value.
+constexpr int kSplevMaxKnots = 512;
+
+template <int K>
+__global__ void __launch_bounds__(256) splev_kernel(const double* __restrict__ t,
+                                                     const double* __restrict__ c, int n,
+                                                     const double* x, double* y, int64_t N) {
+    constexpr int k = K;
+    __shared__ double st[kSplevMaxKnots], sc[kSplevMaxKnots];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        st[j] = t[j];
+        sc[j] = c[j];
+    }
+    __syncthreads();
+    const int lmin = k, lmax = n - k - 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double xv = x[i];
+        // l = (number of knots <= x) - 1, clamped to the interior intervals
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (st[mid] <= xv) lo = mid + 1; else hi = mid;
+        }
+        int l = min(max(lo - 1, lmin), lmax);
+        double h[K + 1], hh[K > 0 ? K : 1];
+        h[0] = 1.0;
+#pragma unroll
+        for (int j = 1; j <= k; ++j) {
+#pragma unroll
+            for (int q = 0; q < j; ++q) hh[q] = h[q];
+            h[0] = 0.0;
+#pragma unroll
+            for (int q = 0; q < j; ++q) {
+                const double ti = st[l + q + 1], tj = st[l + q + 1 - j];
+                const double f = hh[q] / (ti - tj);
+                h[q] = h[q] + f * (ti - xv);
+                h[q + 1] = f * (xv - tj);
+            }
+        }
+        double sp = 0.0;
+#pragma unroll
+        for (int j = 0; j <= k; ++j) sp += sc[l - k + j] * h[j];
+        y[i] = sp;
+    }
+}
+
 // ---- FP64 issue-rate probe (roofline denominator measured on the box) -----------------------
 __global__ void dfma_peak_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;

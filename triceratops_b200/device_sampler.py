@@ -156,10 +156,19 @@ def _background_prior(bg, n, dev, contrast_curve_file, dmag_tess, dmag_cc):
 
 
 # ------------------------------------------------------------------------------- result tables
-def _take(x, idx, dev):
-    if torch.is_tensor(x):
-        return x[idx].cpu().numpy()
-    return np.full(len(idx), x)
+def _take_rows(columns, idx, dev):
+    """Rows `idx` of every column (device tensors or scalars) as numpy arrays, with a single
+    device-to-host copy for all tensor columns."""
+    n = len(idx)
+    tens = [k for k, v in columns.items() if torch.is_tensor(v)]
+    out = {}
+    if tens and n:
+        block = torch.stack([columns[k][idx].to(dp.F64) for k in tens]).cpu().numpy()
+        out = {k: block[i] for i, k in enumerate(tens)}
+    for k, v in columns.items():
+        if k not in out and v is not None:
+            out[k] = np.zeros(n) if torch.is_tensor(v) else np.full(n, float(v))
+    return out
 
 
 def _semi_major_axis(mtot, P):
@@ -176,21 +185,22 @@ def _table(lb, dev, twin, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cf
     draws, merged across ranks."""
     from .marginal_likelihoods import ScenarioResult
     idx = torch.as_tensor(np.asarray(lb.idx, dtype=np.int64), device=dev)
-    g = lambda x: _take(x, idx, dev)  # noqa: E731
     n = len(lb.idx)
-    P_i = g(P) * (2 if twin else 1)
-    a_i = _semi_major_axis(g(mtot), P_i)
-    ecc, argp, inc, Rh = g(eccs), g(argps), g(incs), g(R_host)
+    got = _take_rows(dict(M_host=M_host, R_host=R_host, u1=u1, u2=u2, P=P, mtot=mtot, inc=incs,
+                          ecc=eccs, argp=argps, cfr=cfr, rps=rps, masses=masses, radii=radii,
+                          fluxratios=fluxratios), idx, dev)
+    P_i = got["P"] * (2 if twin else 1)
+    a_i = _semi_major_axis(got["mtot"], P_i)
+    ecc, argp, inc, Rh = got["ecc"], got["argp"], got["inc"], got["R_host"]
     r = a_i * (1 - ecc ** 2) / (1 + ecc * np.sin(argp * np.pi / 180))
     zeros = np.zeros(n)
     local = {
-        'M_s': g(M_host), 'R_s': Rh, 'u1': g(u1), 'u2': g(u2), 'P_orb': P_i, 'inc': inc,
-        'b': r * np.cos(inc * pi / 180) / (Rh * Rsun),
-        'R_p': g(rps) if rps is not None else zeros, 'ecc': ecc, 'argp': argp,
-        'M_EB': g(masses) if masses is not None else zeros,
-        'R_EB': g(radii) if radii is not None else zeros,
-        'fluxratio_EB': g(fluxratios) if fluxratios is not None else zeros,
-        'fluxratio_comp': g(cfr) if torch.is_tensor(cfr) else zeros,
+        'M_s': got["M_host"], 'R_s': Rh, 'u1': got["u1"], 'u2': got["u2"], 'P_orb': P_i,
+        'inc': inc, 'b': r * np.cos(inc * pi / 180) / (Rh * Rsun),
+        'R_p': got.get("rps", zeros), 'ecc': ecc, 'argp': argp,
+        'M_EB': got.get("masses", zeros), 'R_EB': got.get("radii", zeros),
+        'fluxratio_EB': got.get("fluxratios", zeros),
+        'fluxratio_comp': got["cfr"] if torch.is_tensor(cfr) else zeros,
     }
     lnZ, n_pass, n_eval, merged = _dispatch.merge_tables(lb, local, _KEYS)
     merged['lnZ'] = lnZ

@@ -294,11 +294,8 @@ class Engine:
             setattr(a, name, self._tensor_col(val, N, keep))
         if extra_mask is not None:
             m = extra_mask.to(torch.uint8).contiguous()
-            if bool(m.all()):
-                m = None
-            else:
-                keep.append(m)
-                a.extra_mask = m.data_ptr()
+            keep.append(m)
+            a.extra_mask = m.data_ptr()
         a.companion_is_host = int(bool(companion_is_host))
         nb = 1 if kind == "tp" else 2
         rr = (tri_result * nb)()

@@ -5,6 +5,8 @@ scope).  Every function returns bit-identical arra
 reference counterpart for the same inputs: same spline nodes, same scipy objects, same
 operation order.
 """
+import os
+
 import numpy as np
 from pandas import read_csv
 from scipy.interpolate import InterpolatedUnivariateSpline as _Spline
@@ -85,10 +87,25 @@ def separation_at_contrast(delta_mags, separations, contrasts):
     return np.interp(delta_mags, contrasts, separations)
 
 
+_trilegal_cache = {}
+
+
+def _read_trilegal(fname):
+    """The saved table minus its two trailer rows (funcs.py:353); parsed once per file version
+    (a calc_probs reads it four times, a sweep once per target)."""
+    st = os.stat(fname)
+    key = (os.path.abspath(fname), st.st_mtime_ns, st.st_size)
+    if key not in _trilegal_cache:
+        if len(_trilegal_cache) > 8:
+            _trilegal_cache.clear()
+        _trilegal_cache[key] = read_csv(fname)[:-2]
+    return _trilegal_cache[key]
+
+
 def trilegal_results(trilegal_fname: str, Tmag: float):
     """Background-star population fainter than the target from a saved TRILEGAL table
     (funcs.py:335-403): (Tmags, Masses, loggs, Teffs, Zs, Jmags, Hmags, Kmags)."""
-    df = read_csv(trilegal_fname)[:-2]
+    df = _read_trilegal(trilegal_fname)
     Masses = df["Mact"].values
     loggs = df["logg"].values
     Teffs = 10 ** df["logTe"].values
