@@ -26,9 +26,12 @@ def _n_threads():
     if v:
         return max(1, int(v))
     try:
-        return max(1, min(len(os.sched_getaffinity(0)), 32))
+        cores = len(os.sched_getaffinity(0))
     except AttributeError:  # pragma: no cover
-        return max(1, min(os.cpu_count() or 1, 32))
+        cores = os.cpu_count() or 1
+    # one process per GPU: the ranks of a node share its cores
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, min(cores // ranks, 32))
 
 
 N_THREADS = _n_threads()
@@ -46,6 +49,8 @@ def _host_lib():
         if os.path.exists(_build.HOST_SO_PATH):
             L = ctypes.CDLL(_build.HOST_SO_PATH)
             L.trih_splev.argtypes = [_D, ctypes.c_int, _D, ctypes.c_int, _D, _D, ctypes.c_int64]
+            if hasattr(L, "trih_set_threads"):
+                L.trih_set_threads(ctypes.c_int(N_THREADS))
             _lib = L
     return _lib
 

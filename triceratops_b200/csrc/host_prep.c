@@ -67,3 +67,14 @@ int trih_num_threads(void) {
     return 1;
 #endif
 }
+
+/* Launchers such as torchrun export OMP_NUM_THREADS=1 for every rank; the Python side decides
+ * how many host threads a rank may use (cores / ranks on the node) and says so here. */
+void trih_set_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

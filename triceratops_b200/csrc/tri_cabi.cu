@@ -89,7 +89,11 @@ int host_threads() {
     static int n = [] {
         const char* e = std::getenv("TRI_B200_HOST_THREADS");
         int v = e ? std::atoi(e) : 0;
-        if (v <= 0) v = (int)std::thread::hardware_concurrency() / 2;
+        if (v <= 0) {   // half the cores, shared between the ranks of the node
+            const char* w = std::getenv("LOCAL_WORLD_SIZE");
+            int ranks = std::max(1, w ? std::atoi(w) : 1);
+            v = (int)std::thread::hardware_concurrency() / (2 * ranks);
+        }
         return std::max(1, std::min(v, 8));
     }();
     return n;
@@ -797,12 +801,13 @@ int tri_submit_tp(const tri_tp_args* a, const tri_result* want, int64_t* ticket)
     if (N > 0) {
         cudaStream_t cs = g.copy_stream;
         S->staging.reset();
-        rc = S->staging.reserve((size_t)N * 8 * 13 + (size_t)N * 2 + 8192
-                                + (size_t)std::max<int64_t>(want->top_cap, 0) * 16);
+        rc = S->staging.reserve((size_t)N * 8 * 16 + (size_t)N * 3 + 8192
+                                + (size_t)std::max<int64_t>(want->top_cap, 0) * 32);
         if (rc) return rc;
         S->pinned.reset();
         if (!is_pinned(a->inc.ptr)) {   // pageable caller columns go through the pinned arena
-            rc = S->pinned.reserve(std::min(kPinnedLimit, (size_t)N * 8 * 12 + (size_t)N + 8192));
+            // (sized for the EB-type column set too: a slot serves both kinds in turn)
+            rc = S->pinned.reserve(std::min(kPinnedLimit, (size_t)N * 8 * 14 + (size_t)N + 8192));
             if (rc) return rc;
         }
         tri_tp_args d = *a;
