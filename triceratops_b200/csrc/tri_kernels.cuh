@@ -323,20 +323,33 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
             const double skip_beyond =
                 1.0 + k + max_projected_speed(o, a_rs) * (0.5 * exptime) + 1e-9;
             double red = primary ? 0.0 : INFINITY;
-            // lane <-> time stamp, serial over sub-exposures
+            // lane <-> time stamp, serial over sub-exposures.  In the last, partly filled round
+            // 2 (<= 16 stamps left) or 4 (<= 8) lanes share one stamp's sub-exposures, so the
+            // round costs a half or a quarter of a full one.
 #pragma unroll 1
             for (int base = jlo; base < jhi; base += 32) {
-                const int j = base + lane;
-                if (j < jhi) {
+                const int rem = jhi - base;
+                const int gsh = (primary && ns >= 4) ? (rem <= 8 ? 2 : (rem <= 16 ? 1 : 0)) : 0;
+                const int j = base + (lane >> gsh);
+                const int sub = lane & ((1 << gsh) - 1);
+                const bool have = j < jhi;
+                double acc = 0.0;
+                if (have) {
                     const double t = primary ? lc.time[j]
                                              : ((j == 24) ? 0.05 : -0.05 + j * ((0.05 - -0.05) / 24.0));
-                    double acc = 0.0;
+                    // this lane's sub-exposures: is_lo .. is_hi of 1 .. ns
+                    const int is_lo = 1 + ((sub * ns) >> gsh), is_hi = ((sub + 1) * ns) >> gsh;
 #pragma unroll 1
-                    for (int is = probe ? 0 : 1; is <= ns; ++is) {
+                    for (int is = probe ? 0 : is_lo; is <= is_hi; ++is) {
                         const double toff = is ? exptime * ((is - 0.5) * inv_ns - 0.5) : 0.0;
                         const double z = z_at(o, A.tab, t + toff);
                         if (is == 0) {   // stamp centre: is the whole exposure out of transit?
-                            if (fabs(z) > skip_beyond) { acc = (double)ns; ++n_skip; break; }
+                            if (fabs(z) > skip_beyond) {
+                                acc = (double)(is_hi - is_lo + 1);
+                                n_skip += (sub == 0);
+                                break;
+                            }
+                            is = is_lo - 1;
                             continue;
                         }
                         acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
@@ -345,6 +358,12 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                             if (z < 1.0 - k) ++n_interior; else ++n_limb;
                         }
                     }
+                }
+                if (gsh) {   // (warp-uniform) the lanes of a stamp pool their sub-exposure sums
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    if (gsh == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                }
+                if (have && sub == 0) {
                     const double m = acc / ns;
                     if (primary) {
                         const double md = dilute(D, m);

@@ -503,23 +503,57 @@ TRI_HD bool in_arc(const Orbit& o, double ta, double cmax) {
 TRI_HD bool transit_window(const Orbit& o, const OrbitTable& T, double a_rs, double p,
                            const LightCurve& lc, Window& win) {
     if (o.table_clamped) return false;
+    // z^2 = r^2 (1 - sin^2(w+f) sin^2 i) <= (1+k)^2 with r >= a(1-e) bounds the in-transit arc:
+    // cos^2(w+f) <= (c0^2 - cos^2 i) / sin^2 i, c0 = (1+k)/r_min.  (Grazing and high-impact
+    // draws get the short window their chord deserves; 1e-12 covers the cancellation.)
     double rmin = a_rs * (1.0 - o.e);
-    double cmax = (1.0 + o.k) / rmin * (1.0 + 1e-9) + 1e-12;
+    double c0 = (1.0 + o.k) / rmin;
+    double num = c0 * c0 - (1.0 - o.sini2);
+    double cmax = sqrt(fmax(num, 0.0) / o.sini2 + 1e-12) * (1.0 + 1e-9);
     if (!(cmax < 0.95)) return false;  // wide arcs: not worth it / not safe
     // f(M) is monotone (bilinear blend of monotone rows); M is taken relative to mid-transit.
-    // Per side: probe the centre (must be inside), the opposite point (must be outside), then
-    // bisect; one probe site keeps the code small.
+    // The centre must be inside the arc and the opposite point outside; each edge is then the
+    // first offset known to be outside.
     double ma0 = o.ma_tr - kTwoPi * floor(o.ma_tr * kInvTwoPi);
     double edge[2];
 #if defined(__CUDA_ARCH__)
+    // The whole warp works on one draw: a 17-ary search, 16 lanes per side, replaces 2 x 28
+    // serial bisection steps by 7 evaluations (resolution pi / 17^6 = 1.3e-7 rad).
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        const int side = (int)(lane >> 4);
+        const int q = (int)(lane & 15u);
+        const double sgn = side ? 1.0 : -1.0;
+        double lo = 0.0, hi = kPi;  // offset from mid-transit; lo inside the arc, hi outside
 #pragma unroll 1
-#endif
+        for (int it = -1; it < 6; ++it) {
+            double mid = (it < 0) ? (lane == 0 ? 0.0 : kPi)
+                                  : lo + (hi - lo) * ((double)(q + 1) * (1.0 / 17.0));
+            double m = ma0 + sgn * mid;
+            m -= kTwoPi * floor(m * kInvTwoPi);
+            if (m >= kTwoPi) m -= kTwoPi;
+            if (m < 0.0) m += kTwoPi;
+            const bool inside = in_arc(o, ta_from_ma(o, T, m), cmax);
+            const unsigned b = __ballot_sync(0xffffffffu, inside);
+            if (it < 0) {   // lane 0 probed the centre, lane 1 the opposite point
+                if ((b & 3u) != 1u) return false;
+                continue;
+            }
+            // first lane of this side that is outside (16: none)
+            const unsigned out = ~(b >> (side * 16)) & 0xffffu;
+            const int c = out ? (__ffs(out) - 1) : 16;
+            const double up = __shfl_sync(0xffffffffu, mid, side * 16 + min(c, 15));
+            const double dn = __shfl_sync(0xffffffffu, mid, side * 16 + max(c - 1, 0));
+            if (c < 16) hi = up;
+            if (c > 0) lo = dn;
+        }
+        edge[0] = __shfl_sync(0xffffffffu, hi, 0);
+        edge[1] = __shfl_sync(0xffffffffu, hi, 16);
+    }
+#else
     for (int side = 0; side < 2; ++side) {
         double sgn = side ? 1.0 : -1.0;
         double lo = 0.0, hi = kPi;  // offset from mid-transit; lo inside the arc, hi outside
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
         for (int it = -2; it < 26; ++it) {
             double mid = (it == -2) ? 0.0 : (it == -1) ? kPi : 0.5 * (lo + hi);
             double m = ma0 + sgn * mid;
@@ -534,6 +568,7 @@ TRI_HD bool transit_window(const Orbit& o, const OrbitTable& T, double a_rs, dou
         }
         edge[side] = hi;  // first offset known to be outside
     }
+#endif
     // offsets in mean anomaly -> time (mid-transit is t = 0); pad for rounding
     double pad = 1e-9 * p + 1e-12;
     win.t_lo = -edge[0] / o.n_rate - pad;

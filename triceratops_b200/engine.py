@@ -101,6 +101,8 @@ class Engine:
         self._lc_key = None
         self._keep = []
         self._inflight = []      # Pendings not waited for yet, oldest first
+        self._side_streams = None
+        self._side_turn = 0
 
     def _make_room(self):
         """The library holds TRI_MAX_INFLIGHT evaluations: wait for the oldest when full."""
@@ -303,7 +305,17 @@ class Engine:
         for b in range(nb):
             rr[b], ti, tv = self._tensor_result(N, n_best, keep)
             tops.append((ti, tv))
-        stream = torch.cuda.current_stream(self._torch_device()).cuda_stream
+        # The evaluation runs on one of two side streams, ordered after what torch's current
+        # stream has queued so far (the kernels that produced the columns): the sampler kernels
+        # of the next scenario then overlap this evaluation's tail instead of queueing behind it.
+        # The columns stay referenced by the Pending until the evaluation has completed.
+        cur = torch.cuda.current_stream(self._torch_device())
+        if self._side_streams is None:
+            self._side_streams = [torch.cuda.Stream(self._torch_device()) for _ in range(2)]
+        side = self._side_streams[self._side_turn]
+        self._side_turn ^= 1
+        side.wait_stream(cur)
+        stream = side.cuda_stream
         fn = self.lib.tri_submit_tp_dev if kind == "tp" else self.lib.tri_submit_eb_dev
         ticket = ctypes.c_int64()
         _cabi.check(fn(ctypes.byref(a), rr, ctypes.c_void_p(stream), ctypes.byref(ticket)))
