@@ -136,3 +136,49 @@ def test_calc_probs_drops_nan_stamps_like_the_reference(oracle_engine, toi465_lc
         tgt.calc_probs(tt, ff, s, 3.836169, N=500, parallel=True, drop_scenario=drop, verbose=0)
         out.append(tgt.lnZ[0])
     assert np.isfinite(out[0]) and out[0] == out[1]
+
+
+def test_deferred_results_equal_immediate_ones(oracle_engine, toi465_lc, trilegal_file,
+                                               contrast_file, monkeypatch):
+    """calc_probs reads each scenario's result a few scenarios late (the GPU works while the
+    host draws the next priors); the answer must not depend on how late."""
+    from triceratops_b200 import synthetic as synth
+    from triceratops_b200 import triceratops as T
+    t, f, s = toi465_lc
+    stars = synth.stars_table(270380593, TOI465["T"], TOI465["J"], TOI465["H"], TOI465["K"],
+                              TOI465["M"], TOI465["R"], TOI465["Teff"], TOI465["plx"])
+    out = []
+    for depth in (0, 3, 50):
+        monkeypatch.setattr(T, "_PIPELINE_DEPTH", depth)
+        tgt = T.target(270380593, stars=stars, trilegal_fname=trilegal_file)
+        np.random.seed(4)
+        tgt.calc_probs(t, f, s, TOI465["P"], contrast_curve_file=contrast_file, filt="K", N=300,
+                       parallel=True, verbose=0)
+        out.append((tgt.lnZ.copy(), tgt.probs.copy(), tgt.FPP))
+    for lnZ, probs, fpp in out[1:]:
+        assert np.array_equal(lnZ, out[0][0]) and fpp == out[0][2]
+        assert probs.equals(out[0][1])
+
+
+def test_lnz_functions_return_finished_dictionaries_outside_calc_probs(oracle_engine, toi465_lc):
+    """Deferred results exist only inside calc_probs: a direct call behaves like the
+    reference's and returns the dictionary."""
+    from triceratops_b200 import _dispatch
+    from triceratops_b200 import marginal_likelihoods as ml
+    t, f, s = toi465_lc
+    np.random.seed(2)
+    res = ml.lnZ_TTP(t, f, s, TOI465["P"], TOI465["M"], TOI465["R"], TOI465["Teff"], 0.0, 200, True)
+    assert isinstance(res, dict) and "lnZ" in res
+    with _dispatch.deferring():
+        np.random.seed(2)
+        late = ml.lnZ_TTP(t, f, s, TOI465["P"], TOI465["M"], TOI465["R"], TOI465["Teff"], 0.0, 200,
+                          True)
+        assert isinstance(late, _dispatch.Deferred)
+        pair = ml.lnZ_TEB(t, f, s, TOI465["P"], TOI465["M"], TOI465["R"], TOI465["Teff"], 0.0, 200,
+                          True)
+        assert all(isinstance(p, _dispatch.Deferred) for p in pair)
+    got = late.resolve()
+    assert got is late.resolve() and got["lnZ"] == res["lnZ"]
+    assert np.array_equal(got["R_p"], res["R_p"])
+    eb, twin = (p.resolve() for p in pair)
+    assert set(eb) == set(res) and set(twin) == set(res)

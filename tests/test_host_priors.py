@@ -73,3 +73,25 @@ def test_renorm_flux():
     f, e = funcs.renorm_flux(np.array([1.0, 0.99]), 0.001, 0.5)
     np.testing.assert_allclose(f, [1.0, 0.98])
     assert e == 0.002
+
+
+def test_trilegal_table_is_cached_per_file_version(tmp_path, trilegal_file):
+    """The saved TRILEGAL table is parsed once per (path, mtime, size); a rewritten file is read
+    again."""
+    import os
+    import shutil
+    from triceratops_b200 import funcs
+    path = str(tmp_path / "tri.csv")
+    shutil.copy(trilegal_file, path)
+    a = funcs.trilegal_results(path, 10.0)
+    assert funcs._read_trilegal(path) is funcs._read_trilegal(path)
+    b = funcs.trilegal_results(path, 10.0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    lines = open(path).read().splitlines()
+    with open(path, "w") as fh:                 # drop ten stars, keep header and trailer rows
+        fh.write("\n".join(lines[:1] + lines[11:]) + "\n")
+    st = os.stat(path)
+    os.utime(path, ns=(st.st_atime_ns, st.st_mtime_ns + 1_000_000))
+    c = funcs.trilegal_results(path, -99.0)
+    full = funcs.trilegal_results(trilegal_file, -99.0)
+    assert c[0].size == full[0].size - 10
