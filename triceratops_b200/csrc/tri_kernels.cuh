@@ -196,6 +196,8 @@ constexpr int kLnlThreads = 128;
 #endif
 constexpr int kLnlMinBlocks = TRI_LNL_MIN_BLOCKS;
 
+constexpr int kToffTable = 64;
+
 __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs A) {
     extern __shared__ double smem[];
     // Stage the folded light curve once per block when it fits (else read through L1/L2).
@@ -219,6 +221,15 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
             lc.flux = sf;
             lc.prefix = sp;
         }
+    }
+    // sub-exposure offsets of the observed light curve (the same for every draw)
+    __shared__ double s_toff[kToffTable];
+    const bool toff_tab = lc.nsamples < kToffTable;
+    if (toff_tab) {
+        const double inv = 1.0 / lc.nsamples;
+        for (int is = threadIdx.x; is <= lc.nsamples; is += blockDim.x)
+            s_toff[is] = is ? lc.exptime * ((is - 0.5) * inv - 0.5) : 0.0;
+        __syncthreads();
     }
     const int lane = threadIdx.x & 31;
     const double sigma = lc.sigma;
@@ -341,7 +352,9 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                     const int is_lo = 1 + ((sub * ns) >> gsh), is_hi = ((sub + 1) * ns) >> gsh;
 #pragma unroll 1
                     for (int is = probe ? 0 : is_lo; is <= is_hi; ++is) {
-                        const double toff = is ? exptime * ((is - 0.5) * inv_ns - 0.5) : 0.0;
+                        // sub-exposure offset exptime ((is - 1/2)/ns - 1/2), tabulated per block
+                        const double toff = toff_tab ? (primary ? s_toff[is] : 0.0)
+                                                     : (is ? exptime * ((is - 0.5) * inv_ns - 0.5) : 0.0);
                         const double z = z_at(o, A.tab, t + toff);
                         if (is == 0) {   // stamp centre: is the whole exposure out of transit?
                             if (fabs(z) > skip_beyond) {
@@ -352,11 +365,10 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                             is = is_lo - 1;
                             continue;
                         }
-                        acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
-                        // work classes of SURVEY.md 8(d): interior (z <= 1-k) / limb-crossing
-                        if (primary && z >= 0.0 && z <= 1.0 + k && !(k >= 1.0 && z <= k - 1.0)) {
-                            if (z < 1.0 - k) ++n_interior; else ++n_limb;
-                        }
+                        int cls = 0;   // work class of SURVEY.md 8(d): 1 interior, 2 limb-crossing
+                        acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L, cls);
+                        n_interior += (unsigned)(primary && cls == 1);
+                        n_limb += (unsigned)(primary && cls == 2);
                     }
                 }
                 if (gsh) {   // (warp-uniform) the lanes of a stamp pool their sub-exposure sums

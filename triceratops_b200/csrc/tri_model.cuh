@@ -378,7 +378,10 @@ TRI_HD void limb_setup(Limb& L, double u1, double u2, double k) {
 //   * the third-kind parameter n only enters through p = sqrt(n + 1), which is
 //     (k+z)/|k-z| in case IV and 1/|k-z| in case III, and 1/x1 follows from the same
 //     reciprocal: no square root or extra division is needed for them.
-TRI_HD double occult_quad(double z, double k, const Limb& L) {
+// `cls` receives the work class of SURVEY.md 8(d): 0 = trivial (out of transit, behind the
+// star, total eclipse), 1 = interior (z <= 1 - k), 2 = limb-crossing.
+TRI_HD double occult_quad(double z, double k, const Limb& L, int& cls) {
+    cls = 0;
     if (fabs(z - k) < 1e-6) z += 1e-6;
     if (z > 1.0 + k || z < 0.0) return 1.0;
     if (k >= 1.0 && z <= k - 1.0) return 0.0;
@@ -389,6 +392,7 @@ TRI_HD double occult_quad(double z, double k, const Limb& L) {
     double le = 0.0, ld = 0.0, ed = 0.0, kap0 = 0.0, kap1 = 0.0;
 
     const bool partial = (z >= fabs(1.0 - k) && z <= 1.0 + k);
+    cls = partial ? 2 : 1;
     if (partial) {
         double iz = fast_rcp(z);
         kap1 = acos(fmin((1.0 - k2 + z2) * 0.5 * iz, 1.0));
@@ -466,6 +470,11 @@ TRI_HD double occult_quad(double z, double k, const Limb& L) {
         ed = 3.0 / 32.0;
     }
     return 1.0 - (L.c_le * le + L.c_ld * ld + L.u2 * ed) * L.inv_omega;
+}
+
+TRI_HD double occult_quad(double z, double k, const Limb& L) {
+    int cls;
+    return occult_quad(z, k, L, cls);
 }
 
 // Supersampled flux at one time stamp (mean over sub-exposures).
