@@ -1,3 +1,5 @@
+"""Host time spent inside tri_submit_tp for pageable and for page-locked caller columns (the
+call must not wait for the GPU): python scripts/submit_cost.py (needs a GPU)."""
 import sys, os, time, ctypes, numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -1,6 +1,9 @@
+"""Wall time of one config-5 sweep job (device sampler) in a warm process, with a cProfile of
+three jobs: python scripts/sweep_job_profile.py (needs a GPU)."""
 import sys, os, time, cProfile, pstats, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import torch
 from sweep_config5 import make_jobs
 from triceratops_b200.batch import run_job

@@ -596,7 +596,7 @@ int tri_init(int device) {
 int tri_shutdown(void) {
     if (!g.ready) return TRI_OK;
     cudaSetDevice(g.device);
-    cudaStreamSynchronize(g.stream);
+    cudaDeviceSynchronize();   // evaluations may still be running on caller streams
     cudaFree(g.d_tae);
     cudaFree(g.d_time);
     cudaFree(g.d_flux);
