@@ -148,8 +148,11 @@ def test_deferred_results_equal_immediate_ones(oracle_engine, toi465_lc, trilega
     stars = synth.stars_table(270380593, TOI465["T"], TOI465["J"], TOI465["H"], TOI465["K"],
                               TOI465["M"], TOI465["R"], TOI465["Teff"], TOI465["plx"])
     out = []
-    for depth in (0, 3, 50):
+    # ... nor on how many threads prepare consecutive scenarios (numpy's generator is handed
+    # from one scenario to the next in the reference's order)
+    for depth, threads in ((0, 1), (3, 3), (50, 2), (1, 4)):
         monkeypatch.setattr(T, "_PIPELINE_DEPTH", depth)
+        monkeypatch.setenv("TRI_B200_SCENARIO_THREADS", str(threads))
         tgt = T.target(270380593, stars=stars, trilegal_fname=trilegal_file)
         np.random.seed(4)
         tgt.calc_probs(t, f, s, TOI465["P"], contrast_curve_file=contrast_file, filt="K", N=300,

@@ -8,6 +8,7 @@ evaluates the contiguous slice [r*N/G, (r+1)*N/G), and one all-gather of a 206-d
 scenario branch replaces any exchange of per-draw data.
 """
 import contextlib
+import threading
 
 import numpy as np
 
@@ -160,6 +161,30 @@ def _gather_branch(res, lo, hi, N, eng=None):
     return br
 
 
+# ---- the light curve of the scenario being prepared (per thread) --------------------------------
+_tls = threading.local()
+_fallback_lock = threading.Lock()
+
+
+def use_lightcurve(time, flux, sigma, exptime, nsamples):
+    """What every lnZ_* does first: name the light curve its draws will be evaluated against.
+    It becomes the engine's current light curve together with the submission (scenario functions
+    may run in different threads; the engine has one current light curve)."""
+    _tls.lightcurve = (time, flux, sigma, exptime, nsamples)
+
+
+def current_lightcurve():
+    return getattr(_tls, "lightcurve", None)
+
+
+def rng_done():
+    """Called by an lnZ_* function after its last draw from numpy's global generator: the next
+    scenario may start drawing while this one finishes its deterministic work."""
+    ev = getattr(_tls, "rng_event", None)
+    if ev is not None:
+        ev.set()
+
+
 # ---- submit / finish ----------------------------------------------------------------------------
 class _Done:
     """Pending-like wrapper of an already computed result (engines without a submit API)."""
@@ -172,10 +197,14 @@ class _Done:
 
 
 def _submit(eng, name, *args, **kw):
+    lc = current_lightcurve()
     fn = getattr(eng, "submit_" + name, None)
     if fn is not None:
-        return fn(*args, **kw)
-    return _Done(getattr(eng, "eval_" + name)(*args, **kw))
+        return fn(*args, lightcurve=lc, **kw)
+    with _fallback_lock:     # engines without a submit API (test stand-ins): one call at a time
+        if lc is not None:
+            eng.set_lightcurve(*lc)
+        return _Done(getattr(eng, "eval_" + name)(*args, **kw))
 
 
 class PendingBranches:
@@ -260,12 +289,58 @@ def deferring():
         _deferring = saved
 
 
+class ScenarioChain:
+    """Runs scenario functions in a few threads while keeping numpy's global generator strictly
+    sequential: scenario k+1 starts when scenario k has made its last draw (`rng_done()`, or its
+    return), so its draws follow in the reference's order while k's deterministic preparation
+    (stellar relations, priors, flux ratios, submission) still runs."""
+
+    def __init__(self, n_threads):
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(n_threads) if n_threads > 1 else None
+        self._last = None
+
+    def run(self, fn):
+        """Start fn() after the previous scenario's draws; returns an object with .result()."""
+        if self._pool is None:
+            return _Done(fn())
+        prev, mine = self._last, threading.Event()
+        self._last = mine
+        deferring_now = _deferring
+
+        def task():
+            if prev is not None:
+                prev.wait()
+            _tls.rng_event = mine
+            try:
+                return fn()
+            finally:
+                _tls.rng_event = None
+                mine.set()
+        assert deferring_now, "scenario threads are used inside deferring() only"
+        return self._pool.submit(task)
+
+    def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+
+
 def deliver(make):
     return Deferred(make) if _deferring else make()
 
 
 def resolve(res):
     return res.resolve() if isinstance(res, Deferred) else res
+
+
+def scenario_threads():
+    """Threads calc_probs uses for the host-side preparation of consecutive scenarios
+    (TRI_B200_SCENARIO_THREADS, default 3; 1 = everything in the calling thread)."""
+    import os
+    try:
+        return max(1, int(os.environ.get("TRI_B200_SCENARIO_THREADS", "3")))
+    except ValueError:
+        return 3
 
 
 # ---- device-sampler mode: every rank owns its own draws --------------------------------------

@@ -52,6 +52,7 @@ def _worker(worker_id, n_gpus, jobs, out_q):
     # leave the cores to the other workers: one numpy/OpenMP thread each
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("TRI_B200_HOST_THREADS", "1")
+    os.environ.setdefault("TRI_B200_SCENARIO_THREADS", "1")
     try:
         for idx, job in jobs:
             out_q.put((idx, run_job(job), None))

@@ -42,7 +42,7 @@ def _device():
 def _begin(time, flux, sigma, exptime, nsamples, N):
     """Upload the light curve, seed this call's stream, return (device, local draw count)."""
     eng = _dispatch.get_engine()
-    eng.set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)   # applied with the submission
     dev = _device()
     lo, hi = _dispatch.shard_bounds(N)
     if _state["seed"] is not None:

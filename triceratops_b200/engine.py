@@ -5,8 +5,10 @@ one-process-per-GPU launch convention (LOCAL_RANK), and results of ranks that ho
 slices of the prior draws are merged with `combine_lse`.
 """
 import ctypes
+import functools
 import math
 import os
+import threading
 
 import numpy as np
 
@@ -46,6 +48,16 @@ class BranchResult:
             self.n_evaluated = None
 
 
+def _locked(method):
+    """The library is not re-entrant: every call into it (and the engine's own bookkeeping) is
+    serialised, so that scenario functions running in different threads can share the engine."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kw):
+        with self._lock:
+            return method(self, *args, **kw)
+    return wrapper
+
+
 class Pending:
     """An evaluation queued with tri_submit_* and not necessarily finished.  `result()` waits
     for it (once) and returns what the synchronous call returns."""
@@ -59,6 +71,10 @@ class Pending:
         return self._out is not None
 
     def result(self):
+        with self._engine._lock:
+            return self._result()
+
+    def _result(self):
         if self._out is None:
             eng = self._engine
             _cabi.check(eng.lib.tri_wait(ctypes.c_int64(self._ticket), self._rr))
@@ -94,6 +110,7 @@ def combine_lse(parts, N_total):
 class Engine:
     def __init__(self, device=None):
         self.lib = _cabi.load()
+        self._lock = threading.RLock()
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.device = int(device)
@@ -104,17 +121,20 @@ class Engine:
         self._side_streams = None
         self._side_turn = 0
 
+    @_locked
     def _make_room(self):
         """The library holds TRI_MAX_INFLIGHT evaluations: wait for the oldest when full."""
         while len(self._inflight) >= _cabi.TRI_MAX_INFLIGHT:
-            self._inflight[0].result()
+            self._inflight[0]._result()
 
+    @_locked
     def drain(self):
         """Wait for everything in flight (results stay available from their Pendings)."""
         while self._inflight:
-            self._inflight[0].result()
+            self._inflight[0]._result()
 
     # ------------------------------------------------------------------ light curve
+    @_locked
     def set_lightcurve(self, time, flux, sigma, exptime, nsamples):
         time = _cabi.f64(time)
         flux = _cabi.f64(flux)
@@ -166,6 +186,7 @@ class Engine:
             r.top_idx, r.top_lnL = top[0].ctypes.data, top[1].ctypes.data
         return r, lnL, mask, top
 
+    @_locked
     def fetch_lnl(self, branch, N):
         """Per-draw lnL of the most recent eval_tp / eval_eb call (kept on the device)."""
         out = np.empty(int(N))
@@ -179,12 +200,17 @@ class Engine:
     def eval_eb(self, *args, **kw):
         return self.submit_eb(*args, **kw).result()
 
+    @_locked
     def submit_tp(self, N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
                   extra_mask=None, companion_is_host=False, want_lnL=True, want_mask=False,
-                  n_best=0):
+                  n_best=0, lightcurve=None):
         """Queue a TP-type evaluation (tri_submit_tp) and return its Pending: the column copies
-        overlap the kernels of the call submitted before.  `eval_tp` is submit + result()."""
+        overlap the kernels of the call submitted before.  `eval_tp` is submit + result().
+        `lightcurve` = (time, flux, sigma, exptime, nsamples) makes that the current light
+        curve in the same critical section (callers in several threads)."""
         N = int(N)
+        if lightcurve is not None:
+            self.set_lightcurve(*lightcurve)
         self._make_room()
         self._keep = []
         a = tri_tp_args()
@@ -208,10 +234,13 @@ class Engine:
         self._inflight.append(p)
         return p
 
+    @_locked
     def submit_eb(self, N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr,
                   lnprior=None, extra_mask=None, companion_is_host=False, want_lnL=True,
-                  want_mask=False, n_best=0):
+                  want_mask=False, n_best=0, lightcurve=None):
         N = int(N)
+        if lightcurve is not None:
+            self.set_lightcurve(*lightcurve)
         self._make_room()
         self._keep = []
         a = tri_eb_args()
@@ -285,9 +314,13 @@ class Engine:
         order = np.lexsort((idx, -val))
         return idx[order], val[order]
 
-    def _submit_tensors(self, kind, N, cols, extra_mask, companion_is_host, n_best):
+    @_locked
+    def _submit_tensors(self, kind, N, cols, extra_mask, companion_is_host, n_best,
+                        lightcurve=None):
         import torch
         N = int(N)
+        if lightcurve is not None:
+            self.set_lightcurve(*lightcurve)
         self._make_room()
         keep = []
         a = tri_tp_args() if kind == "tp" else tri_eb_args()
@@ -328,14 +361,18 @@ class Engine:
         self._inflight.append(p)
         return p
 
-    def submit_tp_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
+    def submit_tp_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100,
+                          lightcurve=None):
         """tri_submit_tp_dev on torch CUDA tensors (columns: rp, P_orb, inc, ecc, argp, mtot,
         rhost, u1, u2, cfr, lnprior; tensors of N values or scalars), queued on torch's current
         stream behind the kernels that produce them.  Returns a Pending."""
-        return self._submit_tensors("tp", N, cols, extra_mask, companion_is_host, n_best)
+        return self._submit_tensors("tp", N, cols, extra_mask, companion_is_host, n_best,
+                                    lightcurve)
 
-    def submit_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
-        return self._submit_tensors("eb", N, cols, extra_mask, companion_is_host, n_best)
+    def submit_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100,
+                          lightcurve=None):
+        return self._submit_tensors("eb", N, cols, extra_mask, companion_is_host, n_best,
+                                    lightcurve)
 
     def eval_tp_tensors(self, *args, **kw):
         return self.submit_tp_tensors(*args, **kw).result()
@@ -344,6 +381,7 @@ class Engine:
         return self.submit_eb_tensors(*args, **kw).result()
 
     # ------------------------------------------------------------------ L1 seam
+    @_locked
     def lnl_tp(self, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr, companion_is_host):
         n = int(np.size(R_p))
         cols = [self._full(x, n) for x in (R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr)]
@@ -352,6 +390,7 @@ class Engine:
                                         int(bool(companion_is_host)), _cabi.dptr(out)))
         return out
 
+    @_locked
     def lnl_eb(self, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
                companion_is_host, twin):
         n = int(np.size(R_EB))
@@ -364,6 +403,7 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ simulate seam
+    @_locked
     def simulate_tp(self, npts, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
                     companion_is_host):
         n = int(np.size(R_p))
@@ -374,6 +414,7 @@ class Engine:
                                                  int(bool(companion_is_host)), _cabi.dptr(out)))
         return out
 
+    @_locked
     def simulate_eb(self, npts, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp, cfr,
                     companion_is_host, scalar_rule=False):
         n = int(np.size(R_EB))
@@ -399,12 +440,14 @@ class Engine:
         return a
 
     # ------------------------------------------------------------------ misc
+    @_locked
     def log_mean_exp(self, logw):
         logw = _cabi.f64(logw)
         r = tri_result()
         _cabi.check(self.lib.tri_log_mean_exp(_cabi.dptr(logw), logw.size, ctypes.byref(r)))
         return r.lnZ, (r.m, r.s, r.n_finite, r.n_posinf)
 
+    @_locked
     def last_timing(self):
         g, l, s = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         n = ctypes.c_int32()
@@ -413,11 +456,13 @@ class Engine:
         return {"geometry_ms": g.value, "lnl_ms": l.value, "lse_ms": s.value,
                 "launches": n.value}
 
+    @_locked
     def fp64_peak(self):
         v = ctypes.c_double()
         _cabi.check(self.lib.tri_fp64_peak(ctypes.byref(v)))
         return v.value
 
+    @_locked
     def sm_count(self):
         n = ctypes.c_int32()
         _cabi.check(self.lib.tri_sm_count(ctypes.byref(n)))

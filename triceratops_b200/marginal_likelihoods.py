@@ -236,10 +236,11 @@ def lnZ_TTP(time: np.ndarray, flux: np.ndarray, sigma: float,
         from . import device_sampler
         return device_sampler.lnZ_TTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
+    _dispatch.rng_done()
     return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, 0.0, None, None, False)
 
 
@@ -262,10 +263,11 @@ def lnZ_TEB(time: np.ndarray, flux: np.ndarray, sigma: float,
         from . import device_sampler
         return device_sampler.lnZ_TEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
+    _dispatch.rng_done()
     masses = qs * M_s
     radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
     fluxratios = _fluxratio(masses, M_s)
@@ -287,10 +289,14 @@ def lnZ_PTP(time: np.ndarray, flux: np.ndarray, sigma: float,
         from . import device_sampler
         return device_sampler.lnZ_PTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples, molusc_file)
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
+    # all draws first, in the reference's order (q_comp, rp, inc, ecc, argp); what follows is
+    # deterministic and may overlap the next scenario's draws
     qs_comp = _companion_q(N, M_s, molusc_file)
+    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
+    _dispatch.rng_done()
     masses_comp = qs_comp * M_s
     fluxratios_comp = _fluxratio(masses_comp, M_s)
 
@@ -300,7 +306,6 @@ def lnZ_PTP(time: np.ndarray, flux: np.ndarray, sigma: float,
 
     lnprior = _bound_prior(lnprior_bound_TP, M_s, plx, N, molusc_file, contrast_curve_file,
                            fluxratios_comp / (1 - fluxratios_comp), cc_term)
-    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
     return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, fluxratios_comp,
                    lnprior, qs_comp != 0.0, False)
 
@@ -318,11 +323,12 @@ def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
         from . import device_sampler
         return device_sampler.lnZ_PEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples, molusc_file)
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
     qs_comp = _companion_q(N, M_s, molusc_file)
+    _dispatch.rng_done()
     masses = qs * M_s
     radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
     fluxratios = _fluxratio(masses, M_s)
@@ -362,9 +368,12 @@ def lnZ_STP(time: np.ndarray, flux: np.ndarray, sigma: float,
         from . import device_sampler
         return device_sampler.lnZ_STP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples, molusc_file)
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
+    # draws first (q_comp, then the planet around a host of mass q_comp M_s), see lnZ_PTP
     qs_comp = _companion_q(N, M_s, molusc_file)
+    rps, incs, eccs, argps = _draw_planet(N, qs_comp * M_s, flatpriors, P_mean)
+    _dispatch.rng_done()
     (masses_comp, radii_comp, _, fluxratios_comp, u1s, u2s) = _companion_stars(
         N, M_s, R_s, Teff, Z, mission, qs_comp, 10000)
 
@@ -374,7 +383,6 @@ def lnZ_STP(time: np.ndarray, flux: np.ndarray, sigma: float,
 
     lnprior = _bound_prior(lnprior_bound_TP, M_s, plx, N, molusc_file, contrast_curve_file,
                            fluxratios_comp / (1 - fluxratios_comp), cc_term)
-    rps, incs, eccs, argps = _draw_planet(N, masses_comp, flatpriors, P_mean)
     return _run_tp(N, masses_comp, radii_comp, u1s, u2s, P, masses_comp, rps, incs, eccs, argps,
                    fluxratios_comp, lnprior, qs_comp != 0.0, True)
 
@@ -392,10 +400,11 @@ def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
         from . import device_sampler
         return device_sampler.lnZ_SEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples, molusc_file)
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
     qs_comp = _companion_q(N, M_s, molusc_file)
+    _dispatch.rng_done()
     # Teff clamp of 13000 K (grid stops at 10000 K) as in the reference, :1181
     (masses_comp, radii_comp, Teffs_comp, fluxratios_comp, u1s, u2s) = _companion_stars(
         N, M_s, R_s, Teff, Z, mission, qs_comp, 13000)
@@ -430,15 +439,16 @@ def lnZ_DTP(time: np.ndarray, flux: np.ndarray, sigma: float,
         from . import device_sampler
         return device_sampler.lnZ_DTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, Tmag, Jmag, Hmag, Kmag, trilegal_fname, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
     idxs = np.random.randint(0, bg.N_comp - 1, N)     # upper bound N_comp-1, as :1463
+    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
+    _dispatch.rng_done()
     cfr = bg.fluxratios[idxs]
     lnprior = _background_prior(bg, N, contrast_curve_file,
                                 2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
-    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
     return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, cfr, lnprior, None,
                    False)
 
@@ -456,15 +466,16 @@ def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
         from . import device_sampler
         return device_sampler.lnZ_DEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, Tmag, Jmag, Hmag, Kmag, trilegal_fname, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
+    bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
+    idxs = np.random.randint(0, bg.N_comp - 1, N)     # :1672
+    _dispatch.rng_done()
     masses = qs * M_s
     radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
     fluxratios = _fluxratio(masses, M_s)
-    bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
-    idxs = np.random.randint(0, bg.N_comp - 1, N)     # :1672
     cfr = bg.fluxratios[idxs]
     lnprior = _background_prior(bg, N, contrast_curve_file,
                                 2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
@@ -485,17 +496,18 @@ def lnZ_BTP(time: np.ndarray, flux: np.ndarray, sigma: float,
         from . import device_sampler
         return device_sampler.lnZ_BTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Tmag, Jmag, Hmag, Kmag, trilegal_fname, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
+    idxs = np.random.randint(0, bg.N_comp, N)         # :1926
+    host_masses = bg.masses[idxs]
+    rps, incs, eccs, argps = _draw_planet(N, host_masses, flatpriors, P_mean)
+    _dispatch.rng_done()
     radii_comp = bg.radii()
     u1s_comp, u2s_comp = grid_for(mission).nearest_each(bg.Teffs, bg.loggs, bg.Zs)
-    idxs = np.random.randint(0, bg.N_comp, N)         # :1926
     cfr = bg.fluxratios[idxs]
     lnprior = _background_prior(bg, N, contrast_curve_file,
                                 2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
-    host_masses = bg.masses[idxs]
-    rps, incs, eccs, argps = _draw_planet(N, host_masses, flatpriors, P_mean)
     extra = (bg.loggs[idxs] >= 3.5) & (bg.Teffs[idxs] <= 10000)
     return _run_tp(N, host_masses, radii_comp[idxs], u1s_comp[idxs], u2s_comp[idxs], P,
                    host_masses, rps, incs, eccs, argps, cfr, lnprior, extra, True)
@@ -514,7 +526,7 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
         from . import device_sampler
         return device_sampler.lnZ_BEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Tmag, Jmag, Hmag, Kmag, trilegal_fname, contrast_curve_file, filt, N, parallel, mission, flatpriors, exptime, nsamples)
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     incs = sample_inc(np.random.rand(N))
     qs = sample_q(np.random.rand(N), M_s)
@@ -522,9 +534,10 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     eccs = sample_ecc(np.random.rand(N), planet=False, P_orb=P_mean)
     argps = sample_w(np.random.rand(N))
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
+    idxs = np.random.randint(0, bg.N_comp, N)         # :2139
+    _dispatch.rng_done()
     radii_comp = bg.radii()
     u1s_comp, u2s_comp = grid_for(mission).nearest_each(bg.Teffs, bg.loggs, bg.Zs)
-    idxs = np.random.randint(0, bg.N_comp, N)         # :2139
     host_masses = bg.masses[idxs]
     host_radii = radii_comp[idxs]
     cfr = bg.fluxratios[idxs]
@@ -590,7 +603,7 @@ def lnZ_NTP_unknown(time: np.ndarray, flux: np.ndarray, sigma: float,
     """Planet on a nearby star of unknown properties, host drawn from the TRILEGAL stars of
     similar brightness (marginal_likelihoods.py:2365-2551)."""
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     hosts = _PossibleHosts(trilegal_fname, Tmag, mission)
     if hosts.n == 0:
@@ -610,7 +623,7 @@ def lnZ_NEB_unknown(time: np.ndarray, flux: np.ndarray, sigma: float,
                     exptime: float = 0.00139, nsamples: int = 20):
     """EB on a nearby star of unknown properties (marginal_likelihoods.py:2554-2829)."""
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     incs, qs, eccs, argps = _draw_binary(N, 1.0, P_mean)       # sample_q with M_s = 1.0, :2593
     hosts = _PossibleHosts(trilegal_fname, Tmag, mission)
@@ -641,7 +654,7 @@ def lnZ_NTP_evolved(time: np.ndarray, flux: np.ndarray, sigma: float,
                     exptime: float = 0.00139, nsamples: int = 20):
     """Planet on a nearby subgiant (logg = 3) of radius R_s (marginal_likelihoods.py:2832-2966)."""
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     logg, M_s = _subgiant_mass(R_s)
     u1, u2 = grid_for(mission).nearest(Z, Teff, logg)
@@ -661,7 +674,7 @@ def lnZ_NEB_evolved(time: np.ndarray, flux: np.ndarray, sigma: float,
     branches therefore see different companion radii and are evaluated in two engine calls.
     """
     N = int(N)
-    _dispatch.get_engine().set_lightcurve(time, flux, sigma, exptime, nsamples)
+    _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     logg, M_s = _subgiant_mass(R_s)
     u1, u2 = grid_for(mission).nearest(Z, Teff, logg)

@@ -13,6 +13,7 @@ from a stars table the caller already has (the reference's `target.stars` DataFr
 from an online session), optionally its `pix_coords`, and a saved TRILEGAL file.
 """
 import collections
+import functools
 import warnings
 
 import numpy as np
@@ -151,23 +152,35 @@ class target:
         lnZ = np.zeros(n_rows)
 
         # Results are read a few scenarios after they were requested: the GPU works on one
-        # scenario while the host draws the priors of the next (_dispatch.deferring).
-        waiting = collections.deque()
+        # scenario while the host draws the priors of the next (_dispatch.deferring), and with
+        # numpy's draws (host sampler) the scenario functions run in a few threads chained so
+        # that the global generator is still consumed in the reference's order
+        # (_dispatch.ScenarioChain).
+        waiting = collections.deque()      # (rows, pending scenario call)
+        from . import marginal_likelihoods as _ml
+        threads = _dispatch.scenario_threads() if _ml._sampler_mode() == "host" else 1
+        chain = _dispatch.ScenarioChain(threads)
 
         def settle(keep):
             while len(waiting) > keep:
-                j, res = waiting.popleft()
-                res = _dispatch.resolve(res)
-                for k in _RESULT_KEYS:
-                    best[k][j] = res[k][0]
-                lnZ[j] = res["lnZ"]
+                rows, call = waiting.popleft()
+                out = call.result()
+                for j, res in zip(rows, out if isinstance(out, tuple) else (out,)):
+                    res = _dispatch.resolve(res)
+                    for k in _RESULT_KEYS:
+                        best[k][j] = res[k][0]
+                    lnZ[j] = res["lnZ"]
 
-        def store(j, ID, num, name, res):
-            targets[j], star_num[j], scenarios[j] = ID, num, name
-            if res is None:
-                lnZ[j] = -np.inf
+        def launch(row, ID, num, names, fn):
+            """Start one lnZ_* call (one or two table rows) and read older results."""
+            rows = [row + k for k in range(len(names))]
+            for j, name in zip(rows, names):
+                targets[j], star_num[j], scenarios[j] = ID, num, name
+            if fn is None:
+                for j in rows:
+                    lnZ[j] = -np.inf
                 return
-            waiting.append((j, res))
+            waiting.append((rows, chain.run(fn)))
             settle(_PIPELINE_DEPTH)
 
         def say(msg):
@@ -179,73 +192,71 @@ class target:
                                "the online query of the reference is out of scope")
         trilegal_fname = self.trilegal_fname
 
-        with _dispatch.deferring():
-            for i, ID in enumerate(filtered["ID"].values):
-                star = {c: filtered[c].values[i] for c in _STAR_COLUMNS}
-                flux, flux_err = renorm_flux(flux_0, flux_err_0, star["fluxratio"])
-                M_s, R_s, Teff, plx = star["mass"], star["rad"], star["Teff"], star["plx"]
-                mags = (star["Tmag"], star["Jmag"], star["Hmag"], star["Kmag"])
-                Z = 0.0
-                lc = (time, flux, flux_err, P_orb)
-                tail = (N, parallel, self.mission, flatpriors, exptime, nsamples)
+        try:
+            with _dispatch.deferring():
+                for i, ID in enumerate(filtered["ID"].values):
+                    star = {c: filtered[c].values[i] for c in _STAR_COLUMNS}
+                    flux, flux_err = renorm_flux(flux_0, flux_err_0, star["fluxratio"])
+                    M_s, R_s, Teff, plx = star["mass"], star["rad"], star["Teff"], star["plx"]
+                    mags = (star["Tmag"], star["Jmag"], star["Hmag"], star["Kmag"])
+                    Z = 0.0
+                    lc = (time, flux, flux_err, P_orb)
+                    tail = (N, parallel, self.mission, flatpriors, exptime, nsamples)
 
-                if i == 0:
-                    if np.isnan(M_s) or np.isnan(R_s) or np.isnan(Teff) or np.isnan(plx):
-                        print("Insufficient information to validate " + str(ID)
-                              + ". Please ensure a stellar mass (in M_Sun), radius (in R_Sun), "
-                              + "Teff (in K), and plx (in mas) are provided in the .stars dataframe.")
-                        break
-                    runners = {
-                        "TP": lambda: lnZ_TTP(*lc, M_s, R_s, Teff, Z, *tail),
-                        "EB": lambda: lnZ_TEB(*lc, M_s, R_s, Teff, Z, *tail),
-                        "PTP": lambda: lnZ_PTP(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
-                                               filt, *tail, molusc_file),
-                        "PEB": lambda: lnZ_PEB(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
-                                               filt, *tail, molusc_file),
-                        "STP": lambda: lnZ_STP(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
-                                               filt, *tail, molusc_file),
-                        "SEB": lambda: lnZ_SEB(*lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
-                                               filt, *tail, molusc_file),
-                        "DTP": lambda: lnZ_DTP(*lc, M_s, R_s, Teff, Z, *mags, trilegal_fname,
-                                               contrast_curve_file, filt, *tail),
-                        "DEB": lambda: lnZ_DEB(*lc, M_s, R_s, Teff, Z, *mags, trilegal_fname,
-                                               contrast_curve_file, filt, *tail),
-                        "BTP": lambda: lnZ_BTP(*lc, M_s, R_s, Teff, *mags, trilegal_fname,
-                                               contrast_curve_file, filt, *tail),
-                        "BEB": lambda: lnZ_BEB(*lc, M_s, R_s, Teff, *mags, trilegal_fname,
-                                               contrast_curve_file, filt, *tail),
-                    }
-                    for key, row, num, names in _TARGET_SCENARIOS:
-                        if key in drop_scenario:
-                            for k, name in enumerate(names):
-                                store(row + k, ID, num, name, None)
-                            continue
-                        if len(names) == 1:
-                            say("Calculating " + names[0] + " scenario probability for "
-                                + str(ID) + ".")
-                            store(row, ID, num, names[0], runners[key]())
-                        else:
-                            say("Calculating " + names[0] + " and " + names[1]
-                                + " scenario probabilities for " + str(ID) + ".")
-                            res, res_twin = runners[key]()
-                            store(row, ID, num, names[0], res)
-                            store(row + 1, ID, num, names[1], res_twin)
-                else:
-                    # nearby star: unknown properties default to solar (triceratops.py:1345-1350)
-                    if np.isnan(Teff):
-                        Teff = 5777
-                    if np.isnan(M_s):
-                        M_s = 1.0
-                    if np.isnan(R_s):
-                        R_s = 1.0
-                    say("Calculating NTP, NEB, and NEB2xP scenario probabilities for "
-                        + str(ID) + ".")
-                    row = 15 + 3 * (i - 1)
-                    store(row, ID, 1, "NTP", lnZ_TTP(*lc, M_s, R_s, Teff, Z, *tail))
-                    res, res_twin = lnZ_TEB(*lc, M_s, R_s, Teff, Z, *tail)
-                    store(row + 1, ID, 1, "NEB", res)
-                    store(row + 2, ID, 1, "NEBx2P", res_twin)
-            settle(0)
+                    if i == 0:
+                        if np.isnan(M_s) or np.isnan(R_s) or np.isnan(Teff) or np.isnan(plx):
+                            print("Insufficient information to validate " + str(ID)
+                                  + ". Please ensure a stellar mass (in M_Sun), radius (in R_Sun), "
+                                  + "Teff (in K), and plx (in mas) are provided in the .stars dataframe.")
+                            break
+                        bind = functools.partial      # (the loop variables change under the threads)
+                        runners = {
+                            "TP": bind(lnZ_TTP, *lc, M_s, R_s, Teff, Z, *tail),
+                            "EB": bind(lnZ_TEB, *lc, M_s, R_s, Teff, Z, *tail),
+                            "PTP": bind(lnZ_PTP, *lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                        filt, *tail, molusc_file),
+                            "PEB": bind(lnZ_PEB, *lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                        filt, *tail, molusc_file),
+                            "STP": bind(lnZ_STP, *lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                        filt, *tail, molusc_file),
+                            "SEB": bind(lnZ_SEB, *lc, M_s, R_s, Teff, Z, plx, contrast_curve_file,
+                                        filt, *tail, molusc_file),
+                            "DTP": bind(lnZ_DTP, *lc, M_s, R_s, Teff, Z, *mags, trilegal_fname,
+                                        contrast_curve_file, filt, *tail),
+                            "DEB": bind(lnZ_DEB, *lc, M_s, R_s, Teff, Z, *mags, trilegal_fname,
+                                        contrast_curve_file, filt, *tail),
+                            "BTP": bind(lnZ_BTP, *lc, M_s, R_s, Teff, *mags, trilegal_fname,
+                                        contrast_curve_file, filt, *tail),
+                            "BEB": bind(lnZ_BEB, *lc, M_s, R_s, Teff, *mags, trilegal_fname,
+                                        contrast_curve_file, filt, *tail),
+                        }
+                        for key, row, num, names in _TARGET_SCENARIOS:
+                            if len(names) == 1:
+                                say("Calculating " + names[0] + " scenario probability for "
+                                    + str(ID) + ".")
+                            else:
+                                say("Calculating " + names[0] + " and " + names[1]
+                                    + " scenario probabilities for " + str(ID) + ".")
+                            launch(row, ID, num, names,
+                                   None if key in drop_scenario else runners[key])
+                    else:
+                        # nearby star: unknown properties default to solar (triceratops.py:1345-1350)
+                        if np.isnan(Teff):
+                            Teff = 5777
+                        if np.isnan(M_s):
+                            M_s = 1.0
+                        if np.isnan(R_s):
+                            R_s = 1.0
+                        say("Calculating NTP, NEB, and NEB2xP scenario probabilities for "
+                            + str(ID) + ".")
+                        row = 15 + 3 * (i - 1)
+                        launch(row, ID, 1, ("NTP",),
+                               functools.partial(lnZ_TTP, *lc, M_s, R_s, Teff, Z, *tail))
+                        launch(row + 1, ID, 1, ("NEB", "NEBx2P"),
+                               functools.partial(lnZ_TEB, *lc, M_s, R_s, Teff, Z, *tail))
+                settle(0)
+        finally:
+            chain.close()
 
         relative_probs, status = _normalize_probabilities(lnZ)
         if status == 'anomaly':
