@@ -335,12 +335,12 @@ def resolve(res):
 
 def scenario_threads():
     """Threads calc_probs uses for the host-side preparation of consecutive scenarios
-    (TRI_B200_SCENARIO_THREADS, default 3; 1 = everything in the calling thread)."""
+    (TRI_B200_SCENARIO_THREADS, default 4; 1 = everything in the calling thread)."""
     import os
     try:
-        return max(1, int(os.environ.get("TRI_B200_SCENARIO_THREADS", "3")))
+        return max(1, int(os.environ.get("TRI_B200_SCENARIO_THREADS", "4")))
     except ValueError:
-        return 3
+        return 4
 
 
 # ---- device-sampler mode: every rank owns its own draws --------------------------------------

@@ -76,12 +76,52 @@ def _impact(a, ecc, argp, inc, R_host):
     return r * np.cos(inc * pi / 180) / (R_host * Rsun)
 
 
+class _PlanetDraws:
+    """The deviates of a planet draw, taken from numpy's generator in the reference's order
+    (rp, inc, ecc, argp; the eccentricity sampler draws from the generator itself).  The
+    inverse-CDF transforms are applied by finish(), which a scenario calls after it has handed
+    the generator on (_dispatch.rng_done): they are deterministic."""
+
+    def __init__(self, N, P_mean):
+        self.x_rp = np.random.rand(N)
+        self.x_inc = np.random.rand(N)
+        self.eccs = sample_ecc(np.random.rand(N), planet=True, P_orb=P_mean)
+        self.x_w = np.random.rand(N)
+
+    def finish(self, host_masses, flatpriors):
+        return (sample_rp(self.x_rp, host_masses, flatpriors), sample_inc(self.x_inc), self.eccs,
+                sample_w(self.x_w))
+
+
 def _draw_planet(N, host_masses, flatpriors, P_mean):
-    rps = sample_rp(np.random.rand(N), host_masses, flatpriors)
-    incs = sample_inc(np.random.rand(N))
-    eccs = sample_ecc(np.random.rand(N), planet=True, P_orb=P_mean)
-    argps = sample_w(np.random.rand(N))
-    return rps, incs, eccs, argps
+    return _PlanetDraws(N, P_mean).finish(host_masses, flatpriors)
+
+
+class _BinaryDraws:
+    """Same for a stellar companion: inc, q, ecc, argp."""
+
+    def __init__(self, N, P_mean):
+        self.x_inc = np.random.rand(N)
+        self.x_q = np.random.rand(N)
+        self.eccs = sample_ecc(np.random.rand(N), planet=False, P_orb=P_mean)
+        self.x_w = np.random.rand(N)
+
+    def finish(self, M_s):
+        return sample_inc(self.x_inc), sample_q(self.x_q, M_s), self.eccs, sample_w(self.x_w)
+
+
+class _CompanionDraw:
+    """Mass ratios of bound companions: one uniform draw (transformed later) or, with a MOLUSC
+    table, no draw at all (e.g. :455-464)."""
+
+    def __init__(self, N, molusc_file):
+        self.N, self.molusc_file = N, molusc_file
+        self.x = np.random.rand(N) if molusc_file is None else None
+
+    def finish(self, M_s):
+        if self.molusc_file is None:
+            return sample_q_companion(self.x, M_s)
+        return _companion_q(self.N, M_s, self.molusc_file)
 
 
 def _companion_q(N, M_s, molusc_file):
@@ -239,17 +279,14 @@ def lnZ_TTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
-    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
+    draws = _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
+    rps, incs, eccs, argps = draws.finish(np.full(N, M_s), flatpriors)
     return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, 0.0, None, None, False)
 
 
 def _draw_binary(N, M_s, P_mean):
-    incs = sample_inc(np.random.rand(N))
-    qs = sample_q(np.random.rand(N), M_s)
-    eccs = sample_ecc(np.random.rand(N), planet=False, P_orb=P_mean)
-    argps = sample_w(np.random.rand(N))
-    return incs, qs, eccs, argps
+    return _BinaryDraws(N, P_mean).finish(M_s)
 
 
 def lnZ_TEB(time: np.ndarray, flux: np.ndarray, sigma: float,
@@ -266,8 +303,9 @@ def lnZ_TEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
-    incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
+    draws = _BinaryDraws(N, P_mean)
     _dispatch.rng_done()
+    incs, qs, eccs, argps = draws.finish(M_s)
     masses = qs * M_s
     radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
     fluxratios = _fluxratio(masses, M_s)
@@ -294,9 +332,10 @@ def lnZ_PTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     # all draws first, in the reference's order (q_comp, rp, inc, ecc, argp); what follows is
     # deterministic and may overlap the next scenario's draws
-    qs_comp = _companion_q(N, M_s, molusc_file)
-    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
+    comp, draws = _CompanionDraw(N, molusc_file), _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
+    qs_comp = comp.finish(M_s)
+    rps, incs, eccs, argps = draws.finish(np.full(N, M_s), flatpriors)
     masses_comp = qs_comp * M_s
     fluxratios_comp = _fluxratio(masses_comp, M_s)
 
@@ -326,9 +365,10 @@ def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
-    incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
-    qs_comp = _companion_q(N, M_s, molusc_file)
+    draws, comp = _BinaryDraws(N, P_mean), _CompanionDraw(N, molusc_file)
     _dispatch.rng_done()
+    incs, qs, eccs, argps = draws.finish(M_s)
+    qs_comp = comp.finish(M_s)
     masses = qs * M_s
     radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
     fluxratios = _fluxratio(masses, M_s)
@@ -371,9 +411,10 @@ def lnZ_STP(time: np.ndarray, flux: np.ndarray, sigma: float,
     _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     # draws first (q_comp, then the planet around a host of mass q_comp M_s), see lnZ_PTP
-    qs_comp = _companion_q(N, M_s, molusc_file)
-    rps, incs, eccs, argps = _draw_planet(N, qs_comp * M_s, flatpriors, P_mean)
+    comp, draws = _CompanionDraw(N, molusc_file), _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
+    qs_comp = comp.finish(M_s)
+    rps, incs, eccs, argps = draws.finish(qs_comp * M_s, flatpriors)
     (masses_comp, radii_comp, _, fluxratios_comp, u1s, u2s) = _companion_stars(
         N, M_s, R_s, Teff, Z, mission, qs_comp, 10000)
 
@@ -402,9 +443,10 @@ def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     N = int(N)
     _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
-    incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
-    qs_comp = _companion_q(N, M_s, molusc_file)
+    draws, comp = _BinaryDraws(N, P_mean), _CompanionDraw(N, molusc_file)
     _dispatch.rng_done()
+    incs, qs, eccs, argps = draws.finish(M_s)
+    qs_comp = comp.finish(M_s)
     # Teff clamp of 13000 K (grid stops at 10000 K) as in the reference, :1181
     (masses_comp, radii_comp, Teffs_comp, fluxratios_comp, u1s, u2s) = _companion_stars(
         N, M_s, R_s, Teff, Z, mission, qs_comp, 13000)
@@ -444,8 +486,9 @@ def lnZ_DTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
     idxs = np.random.randint(0, bg.N_comp - 1, N)     # upper bound N_comp-1, as :1463
-    rps, incs, eccs, argps = _draw_planet(N, np.full(N, M_s), flatpriors, P_mean)
+    draws = _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
+    rps, incs, eccs, argps = draws.finish(np.full(N, M_s), flatpriors)
     cfr = bg.fluxratios[idxs]
     lnprior = _background_prior(bg, N, contrast_curve_file,
                                 2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
@@ -469,10 +512,11 @@ def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
-    incs, qs, eccs, argps = _draw_binary(N, M_s, P_mean)
+    draws = _BinaryDraws(N, P_mean)
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
     idxs = np.random.randint(0, bg.N_comp - 1, N)     # :1672
     _dispatch.rng_done()
+    incs, qs, eccs, argps = draws.finish(M_s)
     masses = qs * M_s
     radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
     fluxratios = _fluxratio(masses, M_s)
@@ -500,9 +544,10 @@ def lnZ_BTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     P, P_mean = _periods(P_orb, N)
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
     idxs = np.random.randint(0, bg.N_comp, N)         # :1926
-    host_masses = bg.masses[idxs]
-    rps, incs, eccs, argps = _draw_planet(N, host_masses, flatpriors, P_mean)
+    draws = _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
+    host_masses = bg.masses[idxs]
+    rps, incs, eccs, argps = draws.finish(host_masses, flatpriors)
     radii_comp = bg.radii()
     u1s_comp, u2s_comp = grid_for(mission).nearest_each(bg.Teffs, bg.loggs, bg.Zs)
     cfr = bg.fluxratios[idxs]
@@ -528,14 +573,14 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     N = int(N)
     _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
-    incs = sample_inc(np.random.rand(N))
-    qs = sample_q(np.random.rand(N), M_s)
-    sample_q_companion(np.random.rand(N), M_s)        # drawn and never used, as :2089
+    x_inc, x_q = np.random.rand(N), np.random.rand(N)
+    np.random.rand(N)                                 # q_comp: drawn and never used, as :2089
     eccs = sample_ecc(np.random.rand(N), planet=False, P_orb=P_mean)
-    argps = sample_w(np.random.rand(N))
+    x_w = np.random.rand(N)
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
     idxs = np.random.randint(0, bg.N_comp, N)         # :2139
     _dispatch.rng_done()
+    incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
     radii_comp = bg.radii()
     u1s_comp, u2s_comp = grid_for(mission).nearest_each(bg.Teffs, bg.loggs, bg.Zs)
     host_masses = bg.masses[idxs]
