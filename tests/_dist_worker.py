@@ -30,8 +30,12 @@ def main(out_path):
     np.random.seed(125)
     ptp = ml.lnZ_PTP(t, f, s, TOI465["P"], TOI465["M"], TOI465["R"], TOI465["Teff"], 0.0,
                      TOI465["plx"], None, "TESS", N, True)
+    # the full call: scenario threads + deferred results, collectives at resolve time
+    from conftest import calc_probs_small
+    lnZ_cp = calc_probs_small(t, f, s)
     with open(out_path + ".%d" % rank, "wb") as fh:
-        pickle.dump(dict(rank=rank, world=world, shard=(lo, hi), tp=tp, eb=eb, ptp=ptp), fh)
+        pickle.dump(dict(rank=rank, world=world, shard=(lo, hi), tp=tp, eb=eb, ptp=ptp,
+                         lnZ_cp=lnZ_cp), fh)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -185,3 +185,16 @@ def draw_eb_columns(N, seed, star=None):
                                         + funcs.flux_relation(np.array([star["M"]])))
     return dict(reb=radii, ebfr=fr, q=q, P_orb=star["P"], inc=inc, ecc=ecc, argp=argp,
                 mtot=star["M"] + masses, rhost=star["R"], u1=0.4338, u2=0.2008, cfr=0.0)
+
+
+def calc_probs_small(t, f, s, N=301, seed=77):
+    """A short calc_probs (three target-star scenario calls) used by the multi-rank test."""
+    from triceratops_b200 import synthetic as synth
+    from triceratops_b200.triceratops import target
+    stars = synth.stars_table(9, TOI465["T"], TOI465["J"], TOI465["H"], TOI465["K"], TOI465["M"],
+                              TOI465["R"], TOI465["Teff"], TOI465["plx"], n_neighbours=0)
+    tgt = target(9, stars=stars, trilegal_fname=os.path.join(GOLD, "trilegal_synth.csv"))
+    np.random.seed(seed)
+    tgt.calc_probs(t, f, s, TOI465["P"], N=N, parallel=True, verbose=0,
+                   drop_scenario=["PTP", "PEB", "STP", "SEB", "DEB", "BTP", "BEB"])
+    return tgt.lnZ.copy()

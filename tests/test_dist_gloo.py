@@ -54,6 +54,12 @@ def test_two_ranks_equal_one(tmp_path, oracle_engine, toi465_lc):
         for k in RESULT_KEYS:
             np.testing.assert_allclose(a[k][:k_rows], b[k][:k_rows], rtol=1e-12, err_msg=k)
 
+    from conftest import calc_probs_small
+    lnZ_cp = calc_probs_small(t, f, s)
+    assert np.isfinite(lnZ_cp).sum() >= 3
+    for r in res:
+        np.testing.assert_allclose(r["lnZ_cp"], lnZ_cp, rtol=0, atol=1e-9)
+
     for r in res:                       # both ranks hold the combined answer
         same(r["tp"], tp)
         same(r["ptp"], ptp)

@@ -157,7 +157,16 @@ def _gather_branch(res, lo, hi, N, eng=None):
     ok = ~np.isnan(gidx)
     vals, gidx = vals[ok], gidx[ok].astype(np.int64)
     order = np.lexsort((gidx, -vals))
-    br.idx = gidx[order][:N_BEST]
+    idx = gidx[order][:N_BEST]
+    want = min(N_BEST, N)
+    if idx.size < want:
+        # fewer finite draws than table rows: the reference fills the table with zero-weight
+        # draws in whatever order its argsort leaves them; here every rank appends the lowest
+        # draw indices not yet listed, so that all ranks build the same table
+        taken = set(idx.tolist())
+        extra = [i for i in range(min(N, want + idx.size)) if i not in taken][:want - idx.size]
+        idx = np.concatenate([idx, np.asarray(extra, dtype=np.int64)])
+    br.idx = idx
     return br
 
 
