@@ -1,6 +1,6 @@
 """Wall time of one config-5 sweep job (device sampler) in a warm process, with a cProfile of
 three jobs: python scripts/sweep_job_profile.py (needs a GPU)."""
-import sys, os, time, cProfile, pstats, numpy as np
+import sys, os, time, cProfile, pstats
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
