@@ -347,7 +347,8 @@ int enqueue_tp(Slot& S, const tri_tp_args& a, const tri_result& r, cudaStream_t 
     A.P = to_col(a.P_orb); A.inc = to_col(a.inc); A.a = Col{W.a, 1}; A.rhost = to_col(a.rhost);
     A.u1 = to_col(a.u1); A.u2 = to_col(a.u2); A.ecc = to_col(a.ecc); A.argp = to_col(a.argp);
     A.cfr = to_col(a.cfr);
-    A.items = W.items; A.count = 0; A.count_dev = S.d_counters + 0; A.next = S.d_counters + 2;
+    A.items = W.items; A.items_cap = N; A.count = 0; A.count_dev = S.d_counters + 0;
+    A.next = S.d_counters + 2;
     A.out = W.lnl; A.out_twin = nullptr; A.counters = S.d_counters + 4;
     rc = launch_lnl(S, A, s);
     if (rc) return rc;
@@ -409,7 +410,8 @@ int enqueue_eb(Slot& S, const tri_eb_args& a, const tri_result r[2], cudaStream_
     A.P = Col{W.p, 1}; A.inc = to_col(a.inc); A.a = Col{W.a, 1}; A.rhost = to_col(a.rhost);
     A.u1 = to_col(a.u1); A.u2 = to_col(a.u2); A.ecc = to_col(a.ecc); A.argp = to_col(a.argp);
     A.cfr = to_col(a.cfr);
-    A.items = W.items; A.count = 0; A.count_dev = S.d_counters + 0; A.next = S.d_counters + 2;
+    A.items = W.items; A.items_cap = N; A.count = 0; A.count_dev = S.d_counters + 0;
+    A.next = S.d_counters + 2;
     A.out = W.lnl; A.out_twin = W.lnl_twin; A.counters = S.d_counters + 4;
     rc = launch_lnl(S, A, s);
     if (rc) return rc;
@@ -462,11 +464,12 @@ void finish_slot(Slot& S, tri_result* out) {
             continue;
         }
         finish_result(S.h_lse_out[b], S.N, &r);
+        // work items: [0] at the front of the list, [3] at the back (short chords)
+        const int64_t n_items = (int64_t)S.h_counters[0] + (int64_t)S.h_counters[3];
         if (S.branches == 1) {
-            r.n_pass = (int64_t)S.h_counters[0];
+            r.n_pass = n_items;
         } else {   // twins are counted separately by the geometry kernel
-            r.n_pass = b ? (int64_t)S.h_counters[1]
-                         : (int64_t)S.h_counters[0] - (int64_t)S.h_counters[1];
+            r.n_pass = b ? (int64_t)S.h_counters[1] : n_items - (int64_t)S.h_counters[1];
         }
         // the two EB branches share one launch: these totals are joint
         r.n_stamps = (int64_t)S.h_counters[5];

@@ -38,8 +38,9 @@ struct GeomTp {
     double* a_out;              // [N] semi-major axis [cm] of surviving draws
     double* lnl_out;            // [N] pre-filled with -inf for the rejected draws
     uint8_t* mask_out;          // optional [N]
-    int64_t* items;             // work list (sample index << 1)
-    unsigned long long* n_items;
+    int64_t* items;             // work list (sample index << 1), capacity N: long items are
+                                // appended from the front, short ones from the back
+    unsigned long long* n_items;  // [0] items at the front, [3] items at the back
 };
 
 struct GeomEb {
@@ -52,8 +53,8 @@ struct GeomEb {
     double* lnl_twin_out;  // [N] twin branch, -inf default
     uint8_t* mask_out;       // optional [N]: mask of the EB branch
     uint8_t* mask_twin_out;  // optional [N]: mask of the twin branch
-    int64_t* items;     // (sample index << 1) | twin
-    unsigned long long* n_items;  // [0] all surviving draws, [1] of which twin
+    int64_t* items;     // (sample index << 1) | twin; front / back as in GeomTp
+    unsigned long long* n_items;  // [0] items at the front, [1] twins, [3] items at the back
 };
 
 __device__ __forceinline__ double neg_inf() { return -INFINITY; }
@@ -71,23 +72,42 @@ __device__ __forceinline__ bool transits(double inc_deg, double Ptra) {
     return inc_deg >= inc_min;
 }
 
-__device__ __forceinline__ void push_item(bool take, int64_t item, int64_t* items,
-                                          unsigned long long* n_items) {
-    unsigned ballot = __ballot_sync(0xffffffffu, take);
+// A draw whose chord is short (cos i > 0.92 Ptra, i.e. impact parameter above 0.92 (1 + k):
+// at most 40 % of the central transit duration) is cheap to evaluate.  Such draws go to the back
+// of the work list and are handed out last, so that the warps that finish the launch are busy
+// with short items and the tail of the persistent kernel is short (longest-first scheduling
+// with two classes; the result does not depend on the order).
+__device__ __forceinline__ bool short_chord(double inc_deg, double Ptra) {
+    return Ptra <= 1.0 && cos(inc_deg * (kPi / 180.0)) > 0.92 * Ptra;
+}
+
+__device__ __forceinline__ void push_one(unsigned ballot, bool mine, int64_t item, int64_t* slot0,
+                                         int dir, unsigned long long* counter) {
     if (ballot == 0) return;
     int lane = threadIdx.x & 31;
     int leader = __ffs(ballot) - 1;
     unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(n_items, (unsigned long long)__popc(ballot));
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(ballot));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (take) items[base + __popc(ballot & ((1u << lane) - 1u))] = item;
+    if (mine) {
+        long long off = (long long)(base + __popc(ballot & ((1u << lane) - 1u)));
+        slot0[dir * off] = item;
+    }
+}
+
+__device__ __forceinline__ void push_item(bool take, bool is_short, int64_t item, int64_t* items,
+                                          int64_t cap, unsigned long long* n_items) {
+    const unsigned front = __ballot_sync(0xffffffffu, take && !is_short);
+    const unsigned back = __ballot_sync(0xffffffffu, take && is_short);
+    push_one(front, take && !is_short, item, items, +1, n_items + 0);
+    push_one(back, take && is_short, item, items + (cap - 1), -1, n_items + 3);
 }
 
 __global__ void geometry_tp_kernel(GeomTp g) {
     int64_t n_round = (g.N + 31) / 32 * 32;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_round;
          i += (int64_t)gridDim.x * blockDim.x) {
-        bool take = false;
+        bool take = false, brief = false;
         if (i < g.N) {
             double rp = g.rp.at(i), P = g.P.at(i), inc = g.inc.at(i), ecc = g.ecc.at(i);
             double argp = g.argp.at(i), rhost = g.rhost.at(i);
@@ -100,10 +120,13 @@ __global__ void geometry_tp_kernel(GeomTp g) {
             take = transits(inc, Ptra) && !coll;
             if (g.extra_mask) take = take && (g.extra_mask[i] != 0);
             g.lnl_out[i] = neg_inf();
-            if (take) g.a_out[i] = a;
+            if (take) {
+                g.a_out[i] = a;
+                brief = short_chord(inc, Ptra);
+            }
             if (g.mask_out) g.mask_out[i] = take ? 1 : 0;
         }
-        push_item(take, i << 1, g.items, g.n_items);
+        push_item(take, brief, i << 1, g.items, g.N, g.n_items);
     }
 }
 
@@ -111,7 +134,7 @@ __global__ void geometry_eb_kernel(GeomEb g) {
     int64_t n_round = (g.N + 31) / 32 * 32;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_round;
          i += (int64_t)gridDim.x * blockDim.x) {
-        bool take = false;
+        bool take = false, brief = false;
         int twin = 0;
         if (i < g.N) {
             double reb = g.reb.at(i), q = g.q.at(i), P = g.P.at(i), inc = g.inc.at(i);
@@ -139,11 +162,12 @@ __global__ void geometry_eb_kernel(GeomEb g) {
             if (take) {
                 g.a_out[i] = a;
                 g.p_out[i] = twin ? 2.0 * P : P;
+                brief = short_chord(inc, Ptra);
             }
             if (g.mask_out) g.mask_out[i] = (take && !twin) ? 1 : 0;
             if (g.mask_twin_out) g.mask_twin_out[i] = (take && twin) ? 1 : 0;
         }
-        push_item(take, (i << 1) | twin, g.items, g.n_items);
+        push_item(take, brief, (i << 1) | twin, g.items, g.N, g.n_items);
         unsigned bt = __ballot_sync(0xffffffffu, take && twin);
         if ((threadIdx.x & 31) == 0 && bt) atomicAdd(g.n_items + 1, (unsigned long long)__popc(bt));
     }
@@ -163,7 +187,10 @@ struct LnlArgs {
     Col P, inc, a, rhost, u1, u2, ecc, argp, cfr;
     const int64_t* items;    // nullptr: identity list 0..count-1
     int64_t count;             // number of work items when count_dev == nullptr
-    const unsigned long long* count_dev;  // else read from device memory (written by geometry)
+    const unsigned long long* count_dev;  // else read from device memory (written by geometry):
+                                          // count_dev[0] items at the front of `items`,
+                                          // count_dev[3] at the back (handed out last)
+    int64_t items_cap;         // capacity of `items` (the back grows down from items_cap - 1)
     unsigned long long* next;  // work-queue cursor
     double* out;             // lnL of the (EB) branch, indexed by sample
     double* out_twin;        // lnL of the twin branch (fused EB only)
@@ -237,7 +264,8 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
     unsigned n_interior = 0, n_limb = 0;   // per lane; flushed per draw
     unsigned n_skip = 0;                    // per lane: window stamps the centre probe dismissed
     unsigned long long n_int_tot = 0, n_limb_tot = 0;
-    const int64_t count = A.count_dev ? (int64_t)(*A.count_dev) : A.count;
+    const int64_t n_front = A.count_dev ? (int64_t)A.count_dev[0] : A.count;
+    const int64_t count = n_front + (A.count_dev ? (int64_t)A.count_dev[3] : 0);
 
 #pragma unroll 1
     for (;;) {
@@ -245,7 +273,9 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
         if (lane == 0) w = atomicAdd(A.next, 1ull);
         w = __shfl_sync(0xffffffffu, w, 0);
         if ((int64_t)w >= count) break;
-        int64_t item = A.items ? A.items[w] : (((int64_t)w << 1) | A.twin_uniform);
+        int64_t item = !A.items ? (((int64_t)w << 1) | A.twin_uniform)
+                     : ((int64_t)w < n_front ? A.items[w]
+                                             : A.items[A.items_cap - 1 - ((int64_t)w - n_front)]);
         const int64_t i = item >> 1;
         const int twin = (int)(item & 1);
 
