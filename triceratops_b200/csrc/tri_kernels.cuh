@@ -260,6 +260,8 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
     }
     const int lane = threadIdx.x & 31;
     const double sigma = lc.sigma;
+    // the Gaussian constant, once per light curve (marginal_likelihoods.py:130)
+    const double lnorm = -0.5 * log(2.0 * kPi) - log(sigma);
     unsigned long long n_stamps = 0;
     unsigned n_interior = 0, n_limb = 0;   // per lane; flushed per draw
     unsigned n_skip = 0;                    // per lane: window stamps the centre probe dismissed
@@ -436,8 +438,7 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
         chi += (lc.prefix[jlo] - lc.prefix[0]) + (lc.prefix[lc.npts] - lc.prefix[jhi]);
         if (lane == 0) {
             double half_chi2 = 0.5 * (chi / (sigma * sigma));       // likelihoods.py:486
-            outp[i] = A.raw ? half_chi2
-                            : (-0.5 * log(2.0 * kPi) - log(sigma)) - half_chi2;
+            outp[i] = A.raw ? half_chi2 : lnorm - half_chi2;
             n_stamps += (unsigned long long)(jhi - jlo);
         }
         n_int_tot += n_interior;
