@@ -366,16 +366,26 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
             const double skip_beyond =
                 1.0 + k + max_projected_speed(o, a_rs) * (0.5 * exptime) + 1e-9;
             double red = primary ? 0.0 : INFINITY;
-            // lane <-> time stamp, serial over sub-exposures.  In the last, partly filled round
-            // 2 (<= 16 stamps left) or 4 (<= 8) lanes share one stamp's sub-exposures, so the
-            // round costs a half or a quarter of a full one.
+            // lane <-> time stamp, serial over sub-exposures.  Full rounds take 16 stamps from
+            // the front of the window and 16 from its back: ingress and egress mirror each
+            // other, so the two halves of the warp are in the same occultation case (limb or
+            // interior) at the same time instead of one half waiting for the other.  The
+            // remainder (< 32 stamps, in the middle) forms the last round, where 2 (<= 16 stamps)
+            // or 4 (<= 8) lanes share one stamp's sub-exposures.
+            const int n_full = (jhi - jlo) >> 5;
+            const int mid_lo = jlo + 16 * n_full, rem = (jhi - jlo) - 32 * n_full;
 #pragma unroll 1
-            for (int base = jlo; base < jhi; base += 32) {
-                const int rem = jhi - base;
-                const int gsh = (primary && ns >= 4) ? (rem <= 8 ? 2 : (rem <= 16 ? 1 : 0)) : 0;
-                const int j = base + (lane >> gsh);
-                const int sub = lane & ((1 << gsh) - 1);
-                const bool have = j < jhi;
+            for (int r = 0; r < n_full + (rem > 0 ? 1 : 0); ++r) {
+                int gsh = 0, j, sub = 0;
+                bool have = true;
+                if (r < n_full) {
+                    j = (lane < 16) ? jlo + 16 * r + lane : jhi - 16 * (r + 1) + (lane - 16);
+                } else {
+                    gsh = (primary && ns >= 4) ? (rem <= 8 ? 2 : (rem <= 16 ? 1 : 0)) : 0;
+                    j = mid_lo + (lane >> gsh);
+                    sub = lane & ((1 << gsh) - 1);
+                    have = (lane >> gsh) < rem;
+                }
                 double acc = 0.0;
                 if (have) {
                     const double t = primary ? lc.time[j]
