@@ -378,8 +378,10 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
             for (int r = 0; r < n_full + (rem > 0 ? 1 : 0); ++r) {
                 int gsh = 0, j, sub = 0;
                 bool have = true;
+                bool mirror = false;
                 if (r < n_full) {
-                    j = (lane < 16) ? jlo + 16 * r + lane : jhi - 16 * (r + 1) + (lane - 16);
+                    mirror = lane >= 16;
+                    j = mirror ? jhi - 16 * r - 1 - (lane - 16) : jlo + 16 * r + lane;
                 } else {
                     gsh = (primary && ns >= 4) ? (rem <= 8 ? 2 : (rem <= 16 ? 1 : 0)) : 0;
                     j = mid_lo + (lane >> gsh);
@@ -395,8 +397,11 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
 #pragma unroll 1
                     for (int is = probe ? 0 : is_lo; is <= is_hi; ++is) {
                         // sub-exposure offset exptime ((is - 1/2)/ns - 1/2), tabulated per block
-                        const double toff = toff_tab ? (primary ? s_toff[is] : 0.0)
-                                                     : (is ? exptime * ((is - 0.5) * inv_ns - 0.5) : 0.0);
+                        // (the back half of a paired round runs its sub-exposures backwards in
+                        // time, the mirror image of the front half)
+                        const int iso = (mirror && is) ? ns + 1 - is : is;
+                        const double toff = toff_tab ? (primary ? s_toff[iso] : 0.0)
+                                                     : (iso ? exptime * ((iso - 0.5) * inv_ns - 0.5) : 0.0);
                         const double z = z_at(o, A.tab, t + toff);
                         if (is == 0) {   // stamp centre: is the whole exposure out of transit?
                             if (fabs(z) > skip_beyond) {
