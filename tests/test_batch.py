@@ -68,3 +68,63 @@ def test_device_sampler_jobs_are_reproducible_and_agree_with_host_draws(gpu_engi
     # prior sampling), so this is a sanity band, not a parity check
     assert np.max(np.abs(a["lnZ"][probable] - host["lnZ"][probable])) < 3.0
     assert a["FPP"] < 0.05 and host["FPP"] < 0.05
+
+
+def test_get_engine_is_created_once_under_concurrent_first_use(monkeypatch):
+    """calc_probs prepares scenarios in several threads; whichever asks first must not race
+    the others into creating a second engine (CUDA context)."""
+    import threading
+    import time as _t
+    from triceratops_b200 import engine as E
+
+    made = []
+
+    class Slow:
+        def __init__(self, device=None):
+            _t.sleep(0.2)
+            self.device = 0
+            made.append(self)
+
+    monkeypatch.setattr(E, "Engine", Slow)
+    monkeypatch.setattr(E, "_engine", None)
+    got = []
+    ths = [threading.Thread(target=lambda: got.append(E.get_engine())) for _ in range(6)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert len(made) == 1 and all(g is made[0] for g in got)
+
+
+def test_vet_many_reports_a_dead_worker_instead_of_waiting_forever(monkeypatch):
+    """A worker killed in native code never posts its end marker."""
+    from triceratops_b200 import batch
+
+    class FakeProc:
+        exitcode = -11
+
+        def __init__(self, *a, **k):
+            pass
+
+        def start(self):
+            pass
+
+        def is_alive(self):
+            return False
+
+        def join(self):
+            pass
+
+        def terminate(self):
+            pass
+
+    class FakeCtx:
+        Process = FakeProc
+
+        def Queue(self):
+            import queue
+            return queue.Queue()
+
+    monkeypatch.setattr(batch.mp, "get_context", lambda kind: FakeCtx())
+    with pytest.raises(RuntimeError, match="exited with code -11"):
+        batch.vet_many([{"ID": 1}], n_gpus=1, workers_per_gpu=1)

@@ -19,6 +19,7 @@ The result per job is {"ID", "FPP", "NFPP", "FPP_degenerate", "lnZ", "probs" (Da
 """
 import multiprocessing as mp
 import os
+import queue
 import time as _time
 
 import numpy as np
@@ -93,14 +94,25 @@ def vet_many(jobs, n_gpus=None, workers_per_gpu=4):
     results = [None] * len(jobs)
     done = 0
     error = None
-    while done < n_workers:
-        idx, res, err = out_q.get()
+    while done < n_workers and error is None:
+        try:
+            idx, res, err = out_q.get(timeout=5.0)
+        except queue.Empty:
+            # a worker that died (killed, crashed in native code) never reports: do not wait
+            dead = [p for p in procs if p.exitcode not in (None, 0)]
+            if dead:
+                error = "worker process exited with code %s" % dead[0].exitcode
+            continue
         if err is not None:
             error = err
         elif idx is None:
             done += 1
         else:
             results[idx] = res
+    if error:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
     for p in procs:
         p.join()
     if error:

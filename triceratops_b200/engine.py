@@ -16,14 +16,18 @@ from . import _cabi
 from ._cabi import tri_col, tri_eb_args, tri_result, tri_tp_args
 
 _engine = None
+_engine_lock = threading.Lock()
 
 
 def get_engine(device=None):
-    """Process-wide engine bound to `device` (default: LOCAL_RANK or 0)."""
+    """Process-wide engine bound to `device` (default: LOCAL_RANK or 0).  Safe to call from
+    several threads: the first caller creates it (CUDA context, orbit table), the others wait."""
     global _engine
     if _engine is None:
-        _engine = Engine(device)
-    elif device is not None and device != _engine.device:
+        with _engine_lock:
+            if _engine is None:
+                _engine = Engine(device)
+    if device is not None and device != _engine.device:
         raise RuntimeError("engine already bound to device %d" % _engine.device)
     return _engine
 

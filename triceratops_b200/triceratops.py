@@ -159,6 +159,7 @@ class target:
         waiting = collections.deque()      # (rows, pending scenario call)
         from . import marginal_likelihoods as _ml
         threads = _dispatch.scenario_threads() if _ml._sampler_mode() == "host" else 1
+        _dispatch.get_engine()     # created here, not by whichever scenario thread comes first
         chain = _dispatch.ScenarioChain(threads)
 
         def settle(keep):
