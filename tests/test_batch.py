@@ -1,5 +1,7 @@
 """Batch front-end: a job runs through the drop-in calc_probs; under a process group the job
 list (not the draws) is what gets distributed."""
+import os
+
 import numpy as np
 import pytest
 
@@ -128,3 +130,31 @@ def test_vet_many_reports_a_dead_worker_instead_of_waiting_forever(monkeypatch):
     monkeypatch.setattr(batch.mp, "get_context", lambda kind: FakeCtx())
     with pytest.raises(RuntimeError, match="exited with code -11"):
         batch.vet_many([{"ID": 1}], n_gpus=1, workers_per_gpu=1)
+
+
+@pytest.mark.gpu
+def test_first_engine_use_from_scenario_threads_in_a_fresh_process(trilegal_file):
+    """Regression: calc_probs as the very first engine use of a process (its scenario threads
+    used to race each other into creating the CUDA context)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys, os, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests'))\n"
+        "from conftest import TOI465, load_lc\n"
+        "from triceratops_b200 import synthetic as synth\n"
+        "from triceratops_b200.triceratops import target\n"
+        "t, f, s = load_lc('TOI465_01_lightcurve.csv')\n"
+        "stars = synth.stars_table(7, TOI465['T'], TOI465['J'], TOI465['H'], TOI465['K'],\n"
+        "                          TOI465['M'], TOI465['R'], TOI465['Teff'], TOI465['plx'],\n"
+        "                          n_neighbours=0)\n"
+        "tgt = target(7, stars=stars, trilegal_fname=%r)\n"
+        "np.random.seed(1)\n"
+        "tgt.calc_probs(t, f, s, TOI465['P'], N=50000, parallel=True, verbose=0)\n"
+        "print('FPP', float(tgt.FPP))\n" % (ROOT, ROOT, trilegal_file))
+    env = dict(os.environ, TRI_B200_SCENARIO_THREADS="4")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                         timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "FPP" in out.stdout
