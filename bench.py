@@ -136,8 +136,8 @@ def build_workload(N, seed):
     from triceratops_b200 import _dispatch
     tgt, t, f, s, lc = make_target()
     rec = _Recorder()
-    saved = _dispatch._engine_factory
-    _dispatch._engine_factory = lambda: rec
+    saved = _dispatch.get_engine
+    _dispatch.get_engine = lambda: rec
     t0 = time.perf_counter()
     try:
         np.random.seed(seed)
@@ -145,7 +145,7 @@ def build_workload(N, seed):
                        contrast_curve_file=os.path.join(GOLD, "TOI465_01_contrastcurve.csv"),
                        filt="K", N=N, parallel=True, verbose=0)
     finally:
-        _dispatch._engine_factory = saved
+        _dispatch.get_engine = saved
     host_s = time.perf_counter() - t0
     assert len(rec.calls) == 12, len(rec.calls)
     return rec.calls, lc.shape[0], host_s
@@ -388,6 +388,19 @@ def run_ours(args):
     ms_total = float(ms.item())
     clocks = sampler.stop() if rank == 0 else None
 
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"lib": os.environ.get("TRI_B200_LIB", "default"),
+                              "ms_per_step": ms_total / args.steps,
+                              "lnl_ms_per_step": stat["lnl_ms"] / args.steps,
+                              "geom_ms_per_step": stat["geom_ms"] / args.steps,
+                              "tail_ms_per_step": stat["lse_ms"] / args.steps,
+                              "launches_per_step": stat["launches"] / args.steps,
+                              "clocks": clocks, "lnZ_check": [float(x) for x in lnZ[:6]]}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- e2e: host buffers in, per-draw lnL out, copies inside the timed region
     for _ in range(max(1, min(args.warmup, 2))):
         one_step(host_calls, False, False)
@@ -571,6 +584,8 @@ def main():
     ap.add_argument("--cpu-draws", type=int, default=5000,
                     help="draws per scenario in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true",
+                    help="A/B runs: the device-resident leg only (no e2e, no calc_probs extras)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -15,7 +15,15 @@ import math
 import numpy as np
 
 from oracle import coracle
-from triceratops_b200._constants import G, Msun, Rearth, Rsun, ln2pi, pi
+
+# astropy >= 4.0 `constants.X.cgs.value` (CODATA 2018 / IAU 2015 nominal), which the reference
+# reads at likelihoods.py:17-21 and marginal_likelihoods.py:13-17 -- the checker's own copy
+G = 6.6743e-08
+Msun = 1.988409870698051e+33
+Rsun = 69570000000.0
+Rearth = 637810000.0
+pi = np.pi
+ln2pi = np.log(2 * pi)
 
 
 class _Res:
@@ -44,6 +52,49 @@ def _lse_record(lnw, N, res):
     return res
 
 
+def tp_mask(N, rp, P_orb, inc, ecc, argp, mtot, rhost, extra_mask=None):
+    """Geometric mask of a TP-type scenario (marginal_likelihoods.py:107-123) and the
+    semi-major axis [cm], numpy over all N draws."""
+    rp, P, inc, ecc, argp, mtot, rhost = [
+        _full(x, N) for x in (rp, P_orb, inc, ecc, argp, mtot, rhost)]
+    a = ((G * mtot * Msun) / (4 * pi ** 2) * (P * 86400) ** 2) ** (1 / 3)
+    e_corr = (1 + ecc * np.sin(argp * pi / 180)) / (1 - ecc ** 2)
+    Ptra = (rp * Rearth + rhost * Rsun) / a * e_corr
+    coll = (rp * Rearth + rhost * Rsun) > a * (1 - ecc)
+    inc_min = np.full(N, 90.)
+    ok = Ptra <= 1.
+    inc_min[ok] = np.arccos(Ptra[ok]) * 180. / pi
+    mask = (inc >= inc_min) & (coll == False)  # noqa: E712
+    if extra_mask is not None:
+        mask &= np.asarray(extra_mask, bool)
+    return mask, a
+
+
+def eb_masks(N, reb, q, P_orb, inc, ecc, argp, mtot, rhost, extra_mask=None):
+    """Masks and semi-major axes of the EB (q < 0.95, period P) and EBx2P (q >= 0.95, period
+    2P) branches (marginal_likelihoods.py:254-299): ((mask, a), (mask_twin, a_twin))."""
+    reb, q, P, inc, ecc, argp, mtot, rhost = [
+        _full(x, N) for x in (reb, q, P_orb, inc, ecc, argp, mtot, rhost)]
+    e_corr = (1 + ecc * np.sin(argp * pi / 180)) / (1 - ecc ** 2)
+    out = []
+    for twin in (False, True):
+        Pk = 2 * P if twin else P
+        a = ((G * mtot * Msun) / (4 * pi ** 2) * (Pk * 86400) ** 2) ** (1 / 3)
+        Ptra = (reb * Rsun + rhost * Rsun) / a * e_corr
+        if twin:
+            coll = (2 * rhost * Rsun) > a * (1 - ecc)
+        else:
+            coll = (reb * Rsun + rhost * Rsun) > a * (1 - ecc)
+        inc_min = np.full(N, 90.)
+        ok = Ptra <= 1.
+        inc_min[ok] = np.arccos(Ptra[ok]) * 180. / pi
+        mask = (inc >= inc_min) & (coll == False) & ((q >= 0.95) if twin else (q < 0.95))  # noqa: E712
+        if extra_mask is not None:
+            mask &= np.asarray(extra_mask, bool)
+        out.append((mask, a))
+    return tuple(out)
+
+
 class OracleEngine:
     device = -1
 
@@ -57,16 +108,7 @@ class OracleEngine:
         t, f, s, exptime, ns = self.lc
         rp, P, inc, ecc, argp, mtot, rhost, u1, u2, cfr = [
             _full(x, N) for x in (rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr)]
-        a = ((G * mtot * Msun) / (4 * pi ** 2) * (P * 86400) ** 2) ** (1 / 3)
-        e_corr = (1 + ecc * np.sin(argp * pi / 180)) / (1 - ecc ** 2)
-        Ptra = (rp * Rearth + rhost * Rsun) / a * e_corr
-        coll = (rp * Rearth + rhost * Rsun) > a * (1 - ecc)
-        inc_min = np.full(N, 90.)
-        ok = Ptra <= 1.
-        inc_min[ok] = np.arccos(Ptra[ok]) * 180. / pi
-        mask = (inc >= inc_min) & (coll == False)  # noqa: E712
-        if extra_mask is not None:
-            mask &= np.asarray(extra_mask, bool)
+        mask, a = tp_mask(N, rp, P, inc, ecc, argp, mtot, rhost, extra_mask)
         lnL = np.full(N, -np.inf)
         if mask.any():
             lnL[mask] = -0.5 * ln2pi - np.log(s) - coracle.lnL_TP_p(
@@ -82,22 +124,11 @@ class OracleEngine:
         t, f, s, exptime, ns = self.lc
         reb, ebfr, q, P, inc, ecc, argp, mtot, rhost, u1, u2, cfr = [
             _full(x, N) for x in (reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr)]
-        e_corr = (1 + ecc * np.sin(argp * pi / 180)) / (1 - ecc ** 2)
         out = []
+        masks = eb_masks(N, reb, q, P, inc, ecc, argp, mtot, rhost, extra_mask)
         for twin in (False, True):
             Pk = 2 * P if twin else P
-            a = ((G * mtot * Msun) / (4 * pi ** 2) * (Pk * 86400) ** 2) ** (1 / 3)
-            Ptra = (reb * Rsun + rhost * Rsun) / a * e_corr
-            if twin:
-                coll = (2 * rhost * Rsun) > a * (1 - ecc)
-            else:
-                coll = (reb * Rsun + rhost * Rsun) > a * (1 - ecc)
-            inc_min = np.full(N, 90.)
-            ok = Ptra <= 1.
-            inc_min[ok] = np.arccos(Ptra[ok]) * 180. / pi
-            mask = (inc >= inc_min) & (coll == False) & ((q >= 0.95) if twin else (q < 0.95))  # noqa: E712
-            if extra_mask is not None:
-                mask &= np.asarray(extra_mask, bool)
+            mask, a = masks[int(twin)]
             lnL = np.full(N, -np.inf)
             if mask.any():
                 fn = coracle.lnL_EB_twin_p if twin else coracle.lnL_EB_p
@@ -212,13 +243,24 @@ class OracleEngine:
 _instance = OracleEngine()
 
 
-def install():
-    """Route triceratops_b200's host layer to the oracle stand-in (tests only)."""
+_saved_get_engine = None
+
+
+def install(instance=None):
+    """Route triceratops_b200's host layer to the oracle stand-in by patching
+    `_dispatch.get_engine` from outside (tests, bench.py's CPU arm)."""
+    global _saved_get_engine
     from triceratops_b200 import _dispatch
-    _dispatch._engine_factory = lambda: _instance
-    return _instance
+    if _saved_get_engine is None:
+        _saved_get_engine = _dispatch.get_engine
+    eng = instance if instance is not None else _instance
+    _dispatch.get_engine = lambda: eng
+    return eng
 
 
 def uninstall():
-    from triceratops_b200 import _dispatch, engine
-    _dispatch._engine_factory = engine.get_engine
+    global _saved_get_engine
+    from triceratops_b200 import _dispatch
+    if _saved_get_engine is not None:
+        _dispatch.get_engine = _saved_get_engine
+        _saved_get_engine = None

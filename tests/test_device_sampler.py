@@ -70,10 +70,10 @@ class _Capture:
 @pytest.fixture()
 def capture():
     cap = _Capture()
-    saved = _dispatch._engine_factory
-    _dispatch._engine_factory = lambda: cap
+    saved = _dispatch.get_engine
+    _dispatch.get_engine = lambda: cap
     yield cap
-    _dispatch._engine_factory = saved
+    _dispatch.get_engine = saved
     triceratops_b200.set_sampler("host")
 
 

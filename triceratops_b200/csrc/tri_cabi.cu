@@ -140,7 +140,8 @@ struct Slot {
     LsePartial* h_lse_out = nullptr;           // pinned [2]
     TopkState* d_topk = nullptr;               // [2]
     TopkState* h_topk = nullptr;               // pinned [2]
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // geometry | lnl | lse
+    unsigned int* d_hist16 = nullptr;          // [2][kTopkBins], zero between calls
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // geometry | lnl | finalize
     cudaEvent_t copied = nullptr, done = nullptr;
     int launches = 0;
     // the call in flight
@@ -242,11 +243,9 @@ int lnl_grid() { return g.sm_count * std::max(1, g.lnl_blocks_per_sm); }
 size_t lnl_smem_bytes() { return g.lnl_smem; }
 
 struct Scratch {
-    double *a = nullptr, *p = nullptr, *lnl = nullptr, *lnl_twin = nullptr;
+    double *a = nullptr, *p = nullptr, *lnl = nullptr, *lnl_twin = nullptr, *cval = nullptr;
     int64_t* items = nullptr;
-    uint8_t *mask = nullptr, *mask_twin = nullptr;
-    LsePartial* partials = nullptr;
-    int n_partials = 0;
+    LsePartial* partials = nullptr;   // [2][lnl_grid()]
 };
 
 int lse_blocks(int64_t N) {
@@ -258,9 +257,8 @@ size_t scratch_bytes(int64_t N, bool eb) {
     size_t n = (size_t)N;
     size_t b = 0;
     b += (n * 8 + 256) * (eb ? 4 : 2);   // a, lnl (+ p, lnl_twin)
-    b += n * 8 + 256;                    // items
-    b += (n + 256) * 2;                  // masks
-    b += (size_t)lse_blocks(N) * sizeof(LsePartial) * 2 + 512;
+    b += (n * 8 + 256) * 2;              // items, cval
+    b += (size_t)lnl_grid() * sizeof(LsePartial) * 2 + 512;
     return b + 4096;
 }
 
@@ -274,16 +272,6 @@ void finish_result(const LsePartial& r, int64_t N, tri_result* out) {
     else out->lnZ = r.m + std::log(r.s) - std::log((double)N);
 }
 
-int launch_lse(Slot& S, const double* lnl, Col lnprior, int64_t N, LsePartial* partials,
-               LsePartial* out, cudaStream_t s) {
-    int nb = lse_blocks(N);
-    lse_partial_kernel<<<nb, kLseThreads, 0, s>>>(lnl, lnprior, N, partials);
-    lse_final_kernel<<<1, 32, 0, s>>>(partials, nb, out);
-    S.launches += 2;
-    CU(cudaGetLastError());
-    return TRI_OK;
-}
-
 int launch_lnl(Slot& S, LnlArgs& A, cudaStream_t s) {
     size_t smem = lnl_smem_bytes();
     lnl_kernel<<<lnl_grid(), kLnlThreads, smem, s>>>(A);
@@ -292,20 +280,28 @@ int launch_lnl(Slot& S, LnlArgs& A, cudaStream_t s) {
     return TRI_OK;
 }
 
-// top-K of lnl on the device into (d_idx, d_val); the state record of `slot` receives n_out
-int launch_topk(Slot& S, const double* lnl, int64_t N, int64_t cap, int branch, int64_t* d_idx,
-                double* d_val, cudaStream_t s) {
-    TopkState* st = S.d_topk + branch;
-    int nb = (int)std::max<int64_t>(1, std::min<int64_t>((N + 4095) / 4096,
-                                                         4 * (int64_t)g.sm_count));
-    topk_init_kernel<<<1, 256, 0, s>>>(st, (unsigned long long)cap);
-    for (int pass = 0; pass < 8; ++pass) {
-        topk_hist_kernel<<<nb, kTopkThreads, 0, s>>>(lnl, N, st, pass);
-        topk_scan_kernel<<<1, 32, 0, s>>>(st, pass);
+// evidence records and best draws of the call's branches: one block per branch
+int launch_finalize(Slot& S, const Scratch& W, int64_t N, int branches, const tri_result* r,
+                    cudaStream_t s) {
+    FinalizeArgs F{};
+    F.partials = W.partials;
+    F.n_partials = lnl_grid();
+    F.lse_out = S.d_lse_out;
+    F.items = W.items;
+    F.cval = W.cval;
+    F.cap = N;
+    F.count_dev = S.d_counters + 0;
+    F.hist16 = S.d_hist16;
+    for (int b = 0; b < branches; ++b) {
+        S.want_top[b] = r[b].top_cap > 0 && r[b].top_idx && r[b].top_lnL;
+        F.top_cap[b] = S.want_top[b] ? r[b].top_cap : 0;
+        F.top_idx[b] = r[b].top_idx;
+        F.top_val[b] = r[b].top_lnL;
     }
-    topk_collect_above_kernel<<<nb, kTopkThreads, 0, s>>>(lnl, N, st, d_idx, d_val, cap);
-    topk_collect_ties_kernel<<<1, 1024, 0, s>>>(lnl, N, st, d_idx, d_val, cap);
-    S.launches += 19;
+    if (branches == 1) S.want_top[1] = false;
+    F.st = S.d_topk;
+    finalize_kernel<<<branches, kFinThreads, 0, s>>>(F);
+    S.launches += 1;
     CU(cudaGetLastError());
     return TRI_OK;
 }
@@ -322,7 +318,8 @@ int enqueue_tp(Slot& S, const tri_tp_args& a, const tri_result& r, cudaStream_t 
     W.a = S.scratch.take<double>(N);
     W.lnl = r.lnL_out ? r.lnL_out : S.scratch.take<double>(N);
     W.items = S.scratch.take<int64_t>(N);
-    W.partials = S.scratch.take<LsePartial>(lse_blocks(N));
+    W.cval = S.scratch.take<double>(N);
+    W.partials = S.scratch.take<LsePartial>(2 * (size_t)lnl_grid());
     S.launches = 0;
     CU(cudaMemsetAsync(S.d_counters, 0, 8 * sizeof(unsigned long long), s));
     CU(cudaEventRecord(S.ev[0], s));
@@ -350,18 +347,14 @@ int enqueue_tp(Slot& S, const tri_tp_args& a, const tri_result& r, cudaStream_t 
     A.items = W.items; A.items_cap = N; A.count = 0; A.count_dev = S.d_counters + 0;
     A.next = S.d_counters + 2;
     A.out = W.lnl; A.out_twin = nullptr; A.counters = S.d_counters + 4;
+    A.lnprior = to_col(a.lnprior); A.lse_partials = W.partials; A.cval = W.cval;
+    A.hist16 = S.d_hist16;
     rc = launch_lnl(S, A, s);
     if (rc) return rc;
     CU(cudaEventRecord(S.ev[2], s));
-    rc = launch_lse(S, W.lnl, to_col(a.lnprior), N, W.partials, S.d_lse_out, s);
+    rc = launch_finalize(S, W, N, 1, &r, s);
     if (rc) return rc;
-    S.want_top[0] = r.top_cap > 0 && r.top_idx && r.top_lnL;
-    S.want_top[1] = false;
-    if (S.want_top[0]) {
-        rc = launch_topk(S, W.lnl, N, r.top_cap, 0, r.top_idx, r.top_lnL, s);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(S.h_topk, S.d_topk, sizeof(TopkState), cudaMemcpyDeviceToHost, s));
-    }
+    CU(cudaMemcpyAsync(S.h_topk, S.d_topk, sizeof(TopkState), cudaMemcpyDeviceToHost, s));
     S.lnl[0] = W.lnl; S.lnl[1] = nullptr;
     CU(cudaEventRecord(S.ev[3], s));
     CU(cudaMemcpyAsync(S.h_lse_out, S.d_lse_out, sizeof(LsePartial), cudaMemcpyDeviceToHost, s));
@@ -383,8 +376,8 @@ int enqueue_eb(Slot& S, const tri_eb_args& a, const tri_result r[2], cudaStream_
     W.lnl = r[0].lnL_out ? r[0].lnL_out : S.scratch.take<double>(N);
     W.lnl_twin = r[1].lnL_out ? r[1].lnL_out : S.scratch.take<double>(N);
     W.items = S.scratch.take<int64_t>(N);
-    W.n_partials = lse_blocks(N);
-    W.partials = S.scratch.take<LsePartial>(2 * W.n_partials);
+    W.cval = S.scratch.take<double>(N);
+    W.partials = S.scratch.take<LsePartial>(2 * (size_t)lnl_grid());
     S.launches = 0;
     CU(cudaMemsetAsync(S.d_counters, 0, 8 * sizeof(unsigned long long), s));
     CU(cudaEventRecord(S.ev[0], s));
@@ -413,24 +406,14 @@ int enqueue_eb(Slot& S, const tri_eb_args& a, const tri_result r[2], cudaStream_
     A.items = W.items; A.items_cap = N; A.count = 0; A.count_dev = S.d_counters + 0;
     A.next = S.d_counters + 2;
     A.out = W.lnl; A.out_twin = W.lnl_twin; A.counters = S.d_counters + 4;
+    A.lnprior = to_col(a.lnprior); A.lse_partials = W.partials; A.cval = W.cval;
+    A.hist16 = S.d_hist16;
     rc = launch_lnl(S, A, s);
     if (rc) return rc;
     CU(cudaEventRecord(S.ev[2], s));
-    rc = launch_lse(S, W.lnl, to_col(a.lnprior), N, W.partials, S.d_lse_out, s);
+    rc = launch_finalize(S, W, N, 2, r, s);
     if (rc) return rc;
-    rc = launch_lse(S, W.lnl_twin, to_col(a.lnprior), N, W.partials + W.n_partials,
-                    S.d_lse_out + 1, s);
-    if (rc) return rc;
-    for (int b = 0; b < 2; ++b) {
-        S.want_top[b] = r[b].top_cap > 0 && r[b].top_idx && r[b].top_lnL;
-        if (S.want_top[b]) {
-            rc = launch_topk(S, b ? W.lnl_twin : W.lnl, N, r[b].top_cap, b, r[b].top_idx,
-                             r[b].top_lnL, s);
-            if (rc) return rc;
-        }
-    }
-    if (S.want_top[0] || S.want_top[1])
-        CU(cudaMemcpyAsync(S.h_topk, S.d_topk, 2 * sizeof(TopkState), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(S.h_topk, S.d_topk, 2 * sizeof(TopkState), cudaMemcpyDeviceToHost, s));
     S.lnl[0] = W.lnl; S.lnl[1] = W.lnl_twin;
     CU(cudaEventRecord(S.ev[3], s));
     CU(cudaMemcpyAsync(S.h_lse_out, S.d_lse_out, 2 * sizeof(LsePartial), cudaMemcpyDeviceToHost,
@@ -479,7 +462,7 @@ void finish_slot(Slot& S, tri_result* out) {
             ? (int64_t)std::min<unsigned long long>(S.h_topk[b].n_out,
                                                     (unsigned long long)r.top_cap)
             : 0;
-        r.n_evaluated = S.want_top[b] ? (int64_t)S.h_topk[b].n_finite : -1;
+        r.n_evaluated = (int64_t)S.h_topk[b].n_finite;
         if (S.host && S.want_top[b]) {
             std::memcpy(r.top_idx, S.h_tidx[b], (size_t)r.n_top * 8);
             std::memcpy(r.top_lnL, S.h_tval[b], (size_t)r.n_top * 8);
@@ -581,6 +564,8 @@ int tri_init(int device) {
         CU(cudaMallocHost(&S.h_lse_out, 2 * sizeof(LsePartial)));
         CU(cudaMallocHost(&S.h_counters, 8 * sizeof(unsigned long long)));
         CU(cudaMalloc(&S.d_topk, 2 * sizeof(TopkState)));
+        CU(cudaMalloc(&S.d_hist16, 2 * (size_t)kTopkBins * sizeof(unsigned int)));
+        CU(cudaMemset(S.d_hist16, 0, 2 * (size_t)kTopkBins * sizeof(unsigned int)));
         CU(cudaMallocHost(&S.h_topk, 2 * sizeof(TopkState)));
         for (auto& ev : S.ev) CU(cudaEventCreate(&ev));
         CU(cudaEventCreateWithFlags(&S.copied, cudaEventDisableTiming));
@@ -611,6 +596,7 @@ int tri_shutdown(void) {
         cudaFreeHost(S.h_lse_out);
         cudaFreeHost(S.h_counters);
         cudaFree(S.d_topk);
+        cudaFree(S.d_hist16);
         cudaFreeHost(S.h_topk);
         if (S.scratch.base) cudaFree(S.scratch.base);
         if (S.staging.base) cudaFree(S.staging.base);
@@ -1084,10 +1070,12 @@ int tri_log_mean_exp(const double* logw, int64_t n, tri_result* out) {
     double* d = S.staging.take<double>(n);
     LsePartial* parts = S.staging.take<LsePartial>(lse_blocks(n));
     CU(cudaMemcpyAsync(d, logw, (size_t)n * 8, cudaMemcpyHostToDevice, s));
-    int launches_before = S.launches;
-    rc = launch_lse(S, d, Col{nullptr, 0}, n, parts, S.d_lse_out, s);
-    if (rc) return rc;
-    S.launches = launches_before;
+    {
+        int nb = lse_blocks(n);
+        lse_partial_kernel<<<nb, kLseThreads, 0, s>>>(d, Col{nullptr, 0}, n, parts);
+        lse_final_kernel<<<1, kLseThreads, 0, s>>>(parts, nb, S.d_lse_out);
+        CU(cudaGetLastError());
+    }
     CU(cudaMemcpyAsync(S.h_lse_out, S.d_lse_out, sizeof(LsePartial), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     finish_result(S.h_lse_out[0], n, out);

@@ -173,310 +173,7 @@ __global__ void geometry_eb_kernel(GeomEb g) {
     }
 }
 
-// ---- light curve + chi^2 ---------------------------------------------------------------------
-struct LnlArgs {
-    LightCurve lc;
-    OrbitTable tab;
-    int eb;                  // 0 TP-type, 1 EB-type
-    int companion_is_host;
-    int raw;                 // 1: store +0.5 chi^2 (the lnL_*_p seam), +inf on the depth cut
-                             // 0: store -0.5 ln(2 pi) - ln(sigma) - 0.5 chi^2 (marginal_likelihoods.py:130)
-    int twin_uniform;        // twin flag when items == nullptr
-    Col body;                // R_p [R_earth] (TP) or R_EB [R_sun] (EB)
-    Col ebfr;                // EB flux ratio (EB only)
-    Col P, inc, a, rhost, u1, u2, ecc, argp, cfr;
-    const int64_t* items;    // nullptr: identity list 0..count-1
-    int64_t count;             // number of work items when count_dev == nullptr
-    const unsigned long long* count_dev;  // else read from device memory (written by geometry):
-                                          // count_dev[0] items at the front of `items`,
-                                          // count_dev[3] at the back (handed out last)
-    int64_t items_cap;         // capacity of `items` (the back grows down from items_cap - 1)
-    unsigned long long* next;  // work-queue cursor
-    double* out;             // lnL of the (EB) branch, indexed by sample
-    double* out_twin;        // lnL of the twin branch (fused EB only)
-    unsigned long long* counters;  // optional [4]: stamps inside transit windows, stamps whose
-                                   // sub-exposures were evaluated (window minus centre-probe
-                                   // skips), interior-case points, limb/edge-case points
-    // simulate mode (simulate_TP_transit_p / simulate_EB_transit_p, likelihoods.py:302-439):
-    double* model_out;       // optional [count][npts] diluted model flux, caller's stamp order
-    double* secdepth_out;    // optional [count] secondary-eclipse depth (EB-type)
-    const int* perm;         // sorted stamp j -> caller's stamp index
-    int scalar_rule;         // 1: radius-ratio rules of the scalar simulate_EB_transit
-                             // (likelihoods.py:121-123, :137) instead of the vectorised ones
-};
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-__device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-constexpr int kLnlThreads = 128;
-#ifndef TRI_LNL_MIN_BLOCKS
-#define TRI_LNL_MIN_BLOCKS 6       // 80 registers per thread: 24 warps per SM (A/B: 4->137, 5->130, 6->128, 7->128, 8->130 ms)
-#endif
-constexpr int kLnlMinBlocks = TRI_LNL_MIN_BLOCKS;
-
-constexpr int kToffTable = 64;
-
-__global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs A) {
-    extern __shared__ double smem[];
-    // Stage the folded light curve once per block when it fits (else read through L1/L2).
-    LightCurve lc = A.lc;
-    if (A.lc.time == nullptr) return;
-    {
-        size_t need = (size_t)(3 * lc.npts + 1) * sizeof(double);
-        unsigned dyn;
-        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-        if (need <= dyn) {
-            double* st = smem;
-            double* sf = smem + lc.npts;
-            double* sp = smem + 2 * lc.npts;
-            for (int j = threadIdx.x; j < lc.npts; j += blockDim.x) {
-                st[j] = A.lc.time[j];
-                sf[j] = A.lc.flux[j];
-            }
-            for (int j = threadIdx.x; j <= lc.npts; j += blockDim.x) sp[j] = A.lc.prefix[j];
-            __syncthreads();
-            lc.time = st;
-            lc.flux = sf;
-            lc.prefix = sp;
-        }
-    }
-    // sub-exposure offsets of the observed light curve (the same for every draw)
-    __shared__ double s_toff[kToffTable];
-    const bool toff_tab = lc.nsamples < kToffTable;
-    if (toff_tab) {
-        const double inv = 1.0 / lc.nsamples;
-        for (int is = threadIdx.x; is <= lc.nsamples; is += blockDim.x)
-            s_toff[is] = is ? lc.exptime * ((is - 0.5) * inv - 0.5) : 0.0;
-        __syncthreads();
-    }
-    const int lane = threadIdx.x & 31;
-    const double sigma = lc.sigma;
-    // the Gaussian constant, once per light curve (marginal_likelihoods.py:130)
-    const double lnorm = -0.5 * log(2.0 * kPi) - log(sigma);
-    unsigned long long n_stamps = 0;
-    unsigned n_interior = 0, n_limb = 0;   // per lane; flushed per draw
-    unsigned n_skip = 0;                    // per lane: window stamps the centre probe dismissed
-    unsigned long long n_int_tot = 0, n_limb_tot = 0;
-    const int64_t n_front = A.count_dev ? (int64_t)A.count_dev[0] : A.count;
-    const int64_t count = n_front + (A.count_dev ? (int64_t)A.count_dev[3] : 0);
-
-#pragma unroll 1
-    for (;;) {
-        unsigned long long w = 0;
-        if (lane == 0) w = atomicAdd(A.next, 1ull);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if ((int64_t)w >= count) break;
-        int64_t item = !A.items ? (((int64_t)w << 1) | A.twin_uniform)
-                     : ((int64_t)w < n_front ? A.items[w]
-                                             : A.items[A.items_cap - 1 - ((int64_t)w - n_front)]);
-        const int64_t i = item >> 1;
-        const int twin = (int)(item & 1);
-
-        // ---- per-sample constants (every lane computes the same values)
-        const double P = A.P.at(i), e = A.ecc.at(i), argp = A.argp.at(i);
-        const double rhost = A.rhost.at(i);
-        const double a_rs = A.a.at(i) / (rhost * kRsun);          // likelihoods.py:343 / :409
-        const double inc = A.inc.at(i) * (kPi / 180.0);            // :344 / :410
-        const double cfr = A.cfr.at(i);
-        const double F_comp = cfr / (1.0 - cfr);
-        const double u1 = A.u1.at(i), u2 = A.u2.at(i);
-        double k_pri, k_sec = 0.0, F_EB = 0.0;
-        Dilution D;
-        if (!A.eb) {
-            k_pri = A.body.at(i) * kRearth / (rhost * kRsun);      // :340
-            D.two_stage = false;
-            D.d1 = 0.0;
-            D.d2 = A.companion_is_host ? 1.0 / F_comp : F_comp / 1.0;   // :352-357
-        } else {
-            const double reb = A.body.at(i);
-            const double fr = A.ebfr.at(i);
-            F_EB = fr / (1.0 - fr);
-            k_pri = reb / rhost;
-            if (!A.scalar_rule) {
-                if ((k_pri - 1.0) < 1e-6) k_pri *= 0.999;          // :405-406 (no abs: every k <= 1)
-                k_sec = rhost / reb;                               // :417-418
-                if ((k_sec - 1.0) < 1e-6) k_sec *= 0.999;
-            } else {
-                if (fabs(k_pri - 1.0) < 1e-6) k_pri *= 0.999;      // :121-123
-                k_sec = 1.0 / k_pri;                               // :137
-            }
-            D.two_stage = true;
-            if (A.companion_is_host) {                              // :427-432
-                D.d1 = F_EB / F_comp;
-                D.d2 = 1.0 / (F_comp + F_EB);
-            } else {                                                // :433-438
-                D.d1 = F_EB / 1.0;
-                D.d2 = F_comp / (1.0 + F_EB);
-            }
-        }
-        double* outp = (twin && A.out_twin) ? A.out_twin : A.out;
-
-        // Two passes through ONE copy of the model code: pass 0 (EB-type only) is the
-        // 25-stamp secondary eclipse on [-0.05, 0.05] d with the roles swapped and no
-        // supersampling (likelihoods.py:417-423), reduced with a minimum; pass 1 is the
-        // observed light curve, reduced to chi^2.
-        double chi = 0.0;
-        bool cut = false;
-        int jlo = 0, jhi = 0;
-#pragma unroll 1
-        for (int pass = A.eb ? 0 : 1; pass < 2; ++pass) {
-            const bool primary = (pass == 1);
-            const double k = primary ? k_pri : k_sec;
-            // w = (90 - argp) pi/180, + 180 deg for the secondary          :345 / :419
-            const double w_rad = primary ? (90.0 - argp) * (kPi / 180.0)
-                                         : (90.0 - argp + 180.0) * (kPi / 180.0);
-            Orbit o;
-            orbit_setup(o, A.tab, k, P, a_rs, inc, e, w_rad);
-            Limb L;
-            limb_setup(L, u1, u2, k);
-            const int ns = primary ? lc.nsamples : 1;
-            const double exptime = primary ? lc.exptime : 0.0;
-            const double inv_ns = 1.0 / ns;
-            if (primary) {
-                // time stamps that can be in transit
-                jlo = 0;
-                jhi = lc.npts;
-                Window win;
-                if (transit_window(o, A.tab, a_rs, P, lc, win)) {
-                    double half = 0.5 * lc.exptime;
-                    jlo = lower_bound(lc.time, lc.npts, win.t_lo - half);
-                    jhi = lower_bound(lc.time, lc.npts, win.t_hi + half);
-                    if (jhi < jlo) jhi = jlo;
-                }
-                if (A.model_out) {   // outside the window the model is exactly 1
-                    double* row = A.model_out + (size_t)w * lc.npts;
-                    for (int j = lane; j < lc.npts; j += 32)
-                        if (j < jlo || j >= jhi) row[A.perm[j]] = 1.0;
-                }
-            } else {
-                jlo = 0;
-                jhi = 25;
-            }
-            // centre probe (see max_projected_speed): only worth it with supersampling
-            const bool probe = primary && ns > 1 && !o.table_clamped;
-            const double skip_beyond =
-                1.0 + k + max_projected_speed(o, a_rs) * (0.5 * exptime) + 1e-9;
-            double red = primary ? 0.0 : INFINITY;
-            // lane <-> time stamp, serial over sub-exposures.  Full rounds take 16 stamps from
-            // the front of the window and 16 from its back: ingress and egress mirror each
-            // other, so the two halves of the warp are in the same occultation case (limb or
-            // interior) at the same time instead of one half waiting for the other.  The
-            // remainder (< 32 stamps, in the middle) forms the last round, where 2 (<= 16 stamps)
-            // or 4 (<= 8) lanes share one stamp's sub-exposures.
-            const int n_full = (jhi - jlo) >> 5;
-            const int mid_lo = jlo + 16 * n_full, rem = (jhi - jlo) - 32 * n_full;
-#pragma unroll 1
-            for (int r = 0; r < n_full + (rem > 0 ? 1 : 0); ++r) {
-                int gsh = 0, j, sub = 0;
-                bool have = true;
-                bool mirror = false;
-                if (r < n_full) {
-                    mirror = lane >= 16;
-                    j = mirror ? jhi - 16 * r - 1 - (lane - 16) : jlo + 16 * r + lane;
-                } else {
-                    gsh = (primary && ns >= 4) ? (rem <= 8 ? 2 : (rem <= 16 ? 1 : 0)) : 0;
-                    j = mid_lo + (lane >> gsh);
-                    sub = lane & ((1 << gsh) - 1);
-                    have = (lane >> gsh) < rem;
-                }
-                double acc = 0.0;
-                if (have) {
-                    const double t = primary ? lc.time[j]
-                                             : ((j == 24) ? 0.05 : -0.05 + j * ((0.05 - -0.05) / 24.0));
-                    // this lane's sub-exposures: is_lo .. is_hi of 1 .. ns
-                    const int is_lo = 1 + ((sub * ns) >> gsh), is_hi = ((sub + 1) * ns) >> gsh;
-#pragma unroll 1
-                    for (int is = probe ? 0 : is_lo; is <= is_hi; ++is) {
-                        // sub-exposure offset exptime ((is - 1/2)/ns - 1/2), tabulated per block
-                        // (the back half of a paired round runs its sub-exposures backwards in
-                        // time, the mirror image of the front half)
-                        const int iso = (mirror && is) ? ns + 1 - is : is;
-                        const double toff = toff_tab ? (primary ? s_toff[iso] : 0.0)
-                                                     : (iso ? exptime * ((iso - 0.5) * inv_ns - 0.5) : 0.0);
-                        const double z = z_at(o, A.tab, t + toff);
-                        if (is == 0) {   // stamp centre: is the whole exposure out of transit?
-                            if (fabs(z) > skip_beyond) {
-                                acc = (double)(is_hi - is_lo + 1);
-                                n_skip += (sub == 0);
-                                break;
-                            }
-                            is = is_lo - 1;
-                            continue;
-                        }
-                        int cls = 0;   // work class of SURVEY.md 8(d): 1 interior, 2 limb-crossing
-                        acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L, cls);
-                        n_interior += (unsigned)(primary && cls == 1);
-                        n_limb += (unsigned)(primary && cls == 2);
-                    }
-                }
-                if (gsh) {   // (warp-uniform) the lanes of a stamp pool their sub-exposure sums
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                    if (gsh == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                }
-                if (have && sub == 0) {
-                    const double m = acc / ns;
-                    if (primary) {
-                        const double md = dilute(D, m);
-                        if (A.model_out) A.model_out[(size_t)w * lc.npts + A.perm[j]] = md;
-                        const double r = lc.flux[j] - md;
-                        red = fma(r, r, red);
-                    } else {
-                        red = fmin(red, m);
-                    }
-                }
-            }
-            if (!primary) {
-                double sec = warp_min(red);
-                if (A.companion_is_host) sec = (sec + F_comp / F_EB) / (1.0 + F_comp / F_EB);
-                else sec = (sec + 1.0 / F_EB) / (1.0 + 1.0 / F_EB);
-                const double sd = 1.0 - (sec + D.d2) / (1.0 + D.d2);
-                if (A.secdepth_out && lane == 0) A.secdepth_out[w] = sd;
-                cut = !twin && !(sd < 1.5 * sigma);                 // :535-538
-                if (cut) break;
-            } else {
-                chi = warp_sum(red);
-            }
-        }
-        if (cut) {
-            if (lane == 0) outp[i] = A.raw ? INFINITY : -INFINITY;
-            continue;
-        }
-        chi += (lc.prefix[jlo] - lc.prefix[0]) + (lc.prefix[lc.npts] - lc.prefix[jhi]);
-        if (lane == 0) {
-            double half_chi2 = 0.5 * (chi / (sigma * sigma));       // likelihoods.py:486
-            outp[i] = A.raw ? half_chi2 : lnorm - half_chi2;
-            n_stamps += (unsigned long long)(jhi - jlo);
-        }
-        n_int_tot += n_interior;
-        n_limb_tot += n_limb;
-        n_interior = n_limb = 0;
-    }
-    if (A.counters) {
-        unsigned long long n_skip_tot = n_skip;
-        for (int o = 16; o > 0; o >>= 1) {
-            n_skip_tot += __shfl_xor_sync(0xffffffffu, n_skip_tot, o);
-            n_int_tot += __shfl_xor_sync(0xffffffffu, n_int_tot, o);
-            n_limb_tot += __shfl_xor_sync(0xffffffffu, n_limb_tot, o);
-        }
-        if (lane == 0) {
-            atomicAdd(A.counters + 0, n_stamps);   // stamps inside the transit windows
-            atomicAdd(A.counters + 1, n_stamps - n_skip_tot);
-            atomicAdd(A.counters + 2, n_int_tot);
-            atomicAdd(A.counters + 3, n_limb_tot);
-        }
-    }
-}
-
-// ---- log-mean-exp ----------------------------------------------------------------------------
+// ---- log-mean-exp pieces (used by the light-curve kernel's epilogue) ---------------------------
 struct LsePartial {
     double m;      // running max of the finite entries (-inf if none)
     double s;      // sum of exp(x - m)
@@ -508,6 +205,693 @@ __device__ __forceinline__ void lse_merge(LsePartial& a, const LsePartial& b) {
     }
 }
 
+// order-preserving integer image of a double: larger double -> larger key
+__device__ __forceinline__ unsigned long long topk_key(double x) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+constexpr int kTopkBins = 1 << 16;   // histogram over the leading 16 key bits (sign, exponent,
+                                     // four mantissa bits), filled by the light-curve kernel
+
+// ---- light curve + chi^2 ---------------------------------------------------------------------
+struct LnlArgs {
+    LightCurve lc;
+    OrbitTable tab;
+    int eb;                  // 0 TP-type, 1 EB-type
+    int companion_is_host;
+    int raw;                 // 1: store +0.5 chi^2 (the lnL_*_p seam), +inf on the depth cut
+                             // 0: store -0.5 ln(2 pi) - ln(sigma) - 0.5 chi^2 (marginal_likelihoods.py:130)
+    int twin_uniform;        // twin flag when items == nullptr
+    Col body;                // R_p [R_earth] (TP) or R_EB [R_sun] (EB)
+    Col ebfr;                // EB flux ratio (EB only)
+    Col P, inc, a, rhost, u1, u2, ecc, argp, cfr;
+    const int64_t* items;    // nullptr: identity list 0..count-1
+    int64_t count;             // number of work items when count_dev == nullptr
+    const unsigned long long* count_dev;  // else read from device memory (written by geometry):
+                                          // count_dev[0] items at the front of `items`,
+                                          // count_dev[3] at the back (handed out last)
+    int64_t items_cap;         // capacity of `items` (the back grows down from items_cap - 1)
+    unsigned long long* next;  // work-queue cursor
+    double* out;             // lnL of the (EB) branch, indexed by sample
+    double* out_twin;        // lnL of the twin branch (fused EB only)
+    unsigned long long* counters;  // optional [4]: stamps inside transit windows, stamps whose
+                                   // sub-exposures were evaluated (window minus centre-probe
+                                   // skips), interior-case points, limb/edge-case points
+    // fused evidence epilogue (marginal_likelihoods.py:154 / :568, _numerics.py:12-51): every warp
+    // keeps a running (max, scaled sum) of lnL + lnprior over the draws it evaluates, the block
+    // merges its warps and writes one record per branch; finalize_kernel merges the blocks
+    Col lnprior;             // ptr nullptr: none
+    LsePartial* lse_partials;  // nullptr: off; else [2][gridDim.x] (branch-major)
+    double* cval;            // optional [items_cap]: lnL of work item `slot`, in the slot order of
+                             // `items` (the dense input of the best-draw selection)
+    unsigned int* hist16;    // optional [2][kTopkBins]: counts of finite lnL per leading key bits
+    // simulate mode (simulate_TP_transit_p / simulate_EB_transit_p, likelihoods.py:302-439):
+    double* model_out;       // optional [count][npts] diluted model flux, caller's stamp order
+    double* secdepth_out;    // optional [count] secondary-eclipse depth (EB-type)
+    const int* perm;         // sorted stamp j -> caller's stamp index
+    int scalar_rule;         // 1: radius-ratio rules of the scalar simulate_EB_transit
+                             // (likelihoods.py:121-123, :137) instead of the vectorised ones
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+constexpr int kLnlThreads = 128;
+constexpr int kLnlWarps = kLnlThreads / 32;
+#ifndef TRI_LNL_MIN_BLOCKS
+#define TRI_LNL_MIN_BLOCKS 8       // 64 registers per thread: 32 warps per SM
+#endif
+constexpr int kLnlMinBlocks = TRI_LNL_MIN_BLOCKS;
+
+constexpr int kToffTable = 64;
+
+// One draw's constants, ONE copy per warp in shared memory.  Every lane of the warp works on
+// the same draw, so these values are warp-uniform; held in registers they cost 32 copies and
+// (at 6 resident blocks per SM) ~45 doubles of local-memory spills per thread.  The hot loop
+// reads them through a volatile reference: one LDS broadcast per use, on the load/store pipe,
+// which the FP64-bound loop leaves idle.
+struct WarpDraw {
+    Orbit o;
+    Limb L;
+    double skip_beyond;   // centre probe: |z| beyond which a whole exposure is out of transit
+    double d1, d2;        // dilution (likelihoods.py:352-357 / :427-438)
+    int two_stage;
+};
+
+struct LnlShared {
+    WarpDraw draw[kLnlWarps];
+    LsePartial lse[kLnlWarps][2];
+    unsigned long long cnt[kLnlWarps][4];   // diagnostic counters of the warp
+    double toff[kToffTable];
+    const double* time;
+    const double* flux;
+    const double* prefix;
+    double lnorm;
+};
+
+__global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs A) {
+    extern __shared__ double smem[];
+    __shared__ LnlShared S;
+    if (A.lc.time == nullptr) return;
+    const int npts = A.lc.npts;
+    // Stage the folded light curve once per block when it fits (else read through L1/L2).
+    {
+        size_t need = (size_t)(3 * npts + 1) * sizeof(double);
+        unsigned dyn;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        if (need <= dyn) {
+            double* st = smem;
+            double* sf = smem + npts;
+            double* sp = smem + 2 * npts;
+            for (int j = threadIdx.x; j < npts; j += blockDim.x) {
+                st[j] = A.lc.time[j];
+                sf[j] = A.lc.flux[j];
+            }
+            for (int j = threadIdx.x; j <= npts; j += blockDim.x) sp[j] = A.lc.prefix[j];
+            if (threadIdx.x == 0) { S.time = st; S.flux = sf; S.prefix = sp; }
+        } else if (threadIdx.x == 0) {
+            S.time = A.lc.time; S.flux = A.lc.flux; S.prefix = A.lc.prefix;
+        }
+    }
+    // sub-exposure offsets of the observed light curve (the same for every draw)
+    const bool toff_tab = A.lc.nsamples < kToffTable;
+    if (toff_tab) {
+        const double inv = 1.0 / A.lc.nsamples;
+        for (int is = threadIdx.x; is <= A.lc.nsamples; is += blockDim.x)
+            S.toff[is] = is ? A.lc.exptime * ((is - 0.5) * inv - 0.5) : 0.0;
+    }
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        S.lse[warp][0] = LsePartial{-INFINITY, 0.0, 0, 0};
+        S.lse[warp][1] = LsePartial{-INFINITY, 0.0, 0, 0};
+        for (int c = 0; c < 4; ++c) S.cnt[warp][c] = 0;
+    }
+    // the Gaussian constant, once per light curve (marginal_likelihoods.py:130)
+    if (threadIdx.x == 0) S.lnorm = -0.5 * log(2.0 * kPi) - log(A.lc.sigma);
+    __syncthreads();
+    WarpDraw& wd = S.draw[warp];
+    const volatile WarpDraw& vd = S.draw[warp];
+    const volatile LnlShared& VS = S;
+    const int64_t n_front = A.count_dev ? (int64_t)A.count_dev[0] : A.count;
+    const int64_t count = n_front + (A.count_dev ? (int64_t)A.count_dev[3] : 0);
+
+#pragma unroll 1
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(A.next, 1ull);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if ((int64_t)w >= count) break;
+        // slot of this work item in `items` (and in `cval`)
+        const int64_t slot = ((int64_t)w < n_front) ? (int64_t)w
+                                                    : A.items_cap - 1 - ((int64_t)w - n_front);
+        const int64_t item = !A.items ? (((int64_t)w << 1) | A.twin_uniform) : A.items[slot];
+        const int64_t i = item >> 1;
+        const int twin = (int)(item & 1);
+
+        // Two passes through ONE copy of the model code: pass 0 (EB-type only) is the
+        // 25-stamp secondary eclipse on [-0.05, 0.05] d with the roles swapped and no
+        // supersampling (likelihoods.py:417-423), reduced with a minimum; pass 1 is the
+        // observed light curve, reduced to chi^2.
+        double chi = 0.0;
+        bool cut = false;
+        int jlo = 0, jhi = 0;
+        unsigned n_interior = 0, n_limb = 0;   // per lane, this draw
+        unsigned n_skip = 0;                    // per lane: stamps the centre probe dismissed
+#pragma unroll 1
+        for (int pass = A.eb ? 0 : 1; pass < 2; ++pass) {
+            const bool primary = (pass == 1);
+            const int ns = primary ? A.lc.nsamples : 1;
+            bool probe;
+            {
+                // ---- per-sample constants (every lane computes the same values); nothing of
+                // this block stays in registers across the stamp loop
+                const double P = A.P.at(i), e = A.ecc.at(i), argp = A.argp.at(i);
+                const double rhost = A.rhost.at(i);
+                const double a_rs = A.a.at(i) / (rhost * kRsun);          // likelihoods.py:343 / :409
+                const double inc = A.inc.at(i) * (kPi / 180.0);            // :344 / :410
+                const double cfr = A.cfr.at(i);
+                const double F_comp = cfr / (1.0 - cfr);
+                double k_pri, k_sec = 0.0, d1, d2, F_EB;
+                int two_stage;
+                if (!A.eb) {
+                    k_pri = A.body.at(i) * kRearth / (rhost * kRsun);      // :340
+                    two_stage = 0;
+                    d1 = 0.0;
+                    d2 = A.companion_is_host ? 1.0 / F_comp : F_comp / 1.0;   // :352-357
+                } else {
+                    const double reb = A.body.at(i);
+                    const double fr = A.ebfr.at(i);
+                    F_EB = fr / (1.0 - fr);
+                    k_pri = reb / rhost;
+                    if (!A.scalar_rule) {
+                        if ((k_pri - 1.0) < 1e-6) k_pri *= 0.999;          // :405-406 (no abs: every k <= 1)
+                        k_sec = rhost / reb;                               // :417-418
+                        if ((k_sec - 1.0) < 1e-6) k_sec *= 0.999;
+                    } else {
+                        if (fabs(k_pri - 1.0) < 1e-6) k_pri *= 0.999;      // :121-123
+                        k_sec = 1.0 / k_pri;                               // :137
+                    }
+                    two_stage = 1;
+                    if (A.companion_is_host) {                              // :427-432
+                        d1 = F_EB / F_comp;
+                        d2 = 1.0 / (F_comp + F_EB);
+                    } else {                                                // :433-438
+                        d1 = F_EB / 1.0;
+                        d2 = F_comp / (1.0 + F_EB);
+                    }
+                }
+                const double k = primary ? k_pri : k_sec;
+                // w = (90 - argp) pi/180, + 180 deg for the secondary          :345 / :419
+                const double w_rad = primary ? (90.0 - argp) * (kPi / 180.0)
+                                             : (90.0 - argp + 180.0) * (kPi / 180.0);
+                Orbit o;
+                orbit_setup(o, A.tab, k, P, a_rs, inc, e, w_rad);
+                Limb L;
+                limb_setup(L, A.u1.at(i), A.u2.at(i), k);
+                const double exptime = primary ? A.lc.exptime : 0.0;
+                if (primary) {
+                    // time stamps that can be in transit
+                    jlo = 0;
+                    jhi = npts;
+                    Window win;
+                    if (transit_window(o, A.tab, a_rs, P, A.lc, win)) {
+                        double half = 0.5 * A.lc.exptime;
+                        const double* tp = VS.time;
+                        jlo = lower_bound(tp, npts, win.t_lo - half);
+                        jhi = lower_bound(tp, npts, win.t_hi + half);
+                        if (jhi < jlo) jhi = jlo;
+                    }
+                } else {
+                    jlo = 0;
+                    jhi = 25;
+                }
+                // centre probe (see max_projected_speed): only worth it with supersampling
+                probe = primary && ns > 1 && !o.table_clamped;
+                const double skip_beyond =
+                    1.0 + k + max_projected_speed(o, a_rs) * (0.5 * exptime) + 1e-9;
+                __syncwarp();
+                if (lane == 0) {
+                    wd.o = o;
+                    wd.L = L;
+                    wd.skip_beyond = skip_beyond;
+                    wd.d1 = d1;
+                    wd.d2 = d2;
+                    wd.two_stage = two_stage;
+                }
+                __syncwarp();
+            }
+            if (probe) {
+                // Trim the window: stamps at its two ends whose whole exposure is out of transit
+                // (centre probe) have model == 1 exactly and go to the prefix sums.  Lanes 0-15
+                // walk in from the front, lanes 16-31 from the back, 16 stamps a side per step.
+#pragma unroll 1
+                for (;;) {
+                    const bool back = lane >= 16;
+                    const int j = back ? jhi - 1 - (lane - 16) : jlo + lane;
+                    bool keep = false;
+                    if (j >= jlo && j < jhi) {
+                        const double* tp = VS.time;
+                        keep = !(fabs(z_at(vd.o, A.tab, tp[j])) > vd.skip_beyond);
+                    }
+                    const unsigned b = __ballot_sync(0xffffffffu, keep);
+                    const unsigned bf = b & 0xffffu, bb = b >> 16;
+                    jlo += bf ? (__ffs(bf) - 1) : 16;
+                    jhi -= bb ? (__ffs(bb) - 1) : 16;
+                    if (jlo >= jhi) { jhi = jlo = (jlo < npts ? jlo : npts); break; }
+                    if (bf && bb) break;
+                }
+            }
+            if (primary && A.model_out) {   // outside the window the model is exactly 1
+                double* row = A.model_out + (size_t)w * npts;
+                for (int j = lane; j < npts; j += 32)
+                    if (j < jlo || j >= jhi) row[A.perm[j]] = 1.0;
+            }
+            double red = primary ? 0.0 : INFINITY;
+            // lane <-> time stamp, serial over sub-exposures.  Full rounds take 16 stamps from
+            // the front of the window and 16 from its back: ingress and egress mirror each
+            // other, so the two halves of the warp are in the same occultation case (limb or
+            // interior) at the same time instead of one half waiting for the other.  The
+            // remainder (< 32 stamps, in the middle) forms the last round, where 2 (<= 16 stamps)
+            // or 4 (<= 8) lanes share one stamp's sub-exposures.
+            const int n_full = (jhi - jlo) >> 5;
+            const int rem = (jhi - jlo) - 32 * n_full;
+#pragma unroll 1
+            for (int r = 0; r < n_full + (rem > 0 ? 1 : 0); ++r) {
+                int gsh = 0, j, sub = 0;
+                bool have = true;
+                bool mirror = false;
+                if (r < n_full) {
+                    mirror = lane >= 16;
+                    j = mirror ? jhi - 16 * r - 1 - (lane - 16) : jlo + 16 * r + lane;
+                } else {
+                    gsh = (primary && ns >= 4) ? (rem <= 8 ? 2 : (rem <= 16 ? 1 : 0)) : 0;
+                    j = jlo + 16 * n_full + (lane >> gsh);
+                    sub = lane & ((1 << gsh) - 1);
+                    have = (lane >> gsh) < rem;
+                }
+                double acc = 0.0;
+                if (have) {
+                    double t;
+                    if (primary) {
+                        const double* tp = VS.time;
+                        t = tp[j];
+                    } else {
+                        t = (j == 24) ? 0.05 : -0.05 + j * ((0.05 - -0.05) / 24.0);
+                    }
+                    // this lane's sub-exposures: is_lo .. is_hi of 1 .. ns
+                    const int is_lo = 1 + ((sub * ns) >> gsh), is_hi = ((sub + 1) * ns) >> gsh;
+#pragma unroll 1
+                    for (int is = probe ? 0 : is_lo; is <= is_hi; ++is) {
+                        // sub-exposure offset exptime ((is - 1/2)/ns - 1/2), tabulated per block
+                        // (the back half of a paired round runs its sub-exposures backwards in
+                        // time, the mirror image of the front half)
+                        const int iso = (mirror && is) ? ns + 1 - is : is;
+                        double toff = 0.0;
+                        if (primary)
+                            toff = toff_tab ? S.toff[iso]
+                                            : (iso ? A.lc.exptime * ((iso - 0.5) / ns - 0.5) : 0.0);
+                        const double z = z_at(vd.o, A.tab, t + toff);
+                        if (is == 0) {   // stamp centre: is the whole exposure out of transit?
+                            if (fabs(z) > vd.skip_beyond) {
+                                acc = (double)(is_hi - is_lo + 1);
+                                n_skip += (sub == 0);
+                                break;
+                            }
+                            is = is_lo - 1;
+                            continue;
+                        }
+                        int cls = 0;   // work class of SURVEY.md 8(d): 1 interior, 2 limb-crossing
+                        const double k = vd.o.k;
+                        acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, vd.L, cls);
+                        n_interior += (unsigned)(primary && cls == 1);
+                        n_limb += (unsigned)(primary && cls == 2);
+                    }
+                }
+                if (gsh) {   // (warp-uniform) the lanes of a stamp pool their sub-exposure sums
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    if (gsh == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                }
+                if (have && sub == 0) {
+                    double m = acc / ns;
+                    if (primary) {
+                        if (vd.two_stage) m = (m + vd.d1) / (1.0 + vd.d1);
+                        const double d2 = vd.d2;
+                        const double md = (m + d2) / (1.0 + d2);
+                        if (A.model_out) A.model_out[(size_t)w * npts + A.perm[j]] = md;
+                        const double* fp = VS.flux;
+                        const double rr = fp[j] - md;
+                        red = fma(rr, rr, red);
+                    } else {
+                        red = fmin(red, m);
+                    }
+                }
+            }
+            if (!primary) {
+                double sec = warp_min(red);
+                const double cfr = A.cfr.at(i), fr = A.ebfr.at(i);
+                const double F_comp = cfr / (1.0 - cfr), F_EB = fr / (1.0 - fr);
+                if (A.companion_is_host) sec = (sec + F_comp / F_EB) / (1.0 + F_comp / F_EB);
+                else sec = (sec + 1.0 / F_EB) / (1.0 + 1.0 / F_EB);
+                const double d2 = vd.d2;
+                const double sd = 1.0 - (sec + d2) / (1.0 + d2);
+                if (A.secdepth_out && lane == 0) A.secdepth_out[w] = sd;
+                cut = !twin && !(sd < 1.5 * A.lc.sigma);                 // :535-538
+                if (cut) break;
+            } else {
+                chi = warp_sum(red);
+            }
+        }
+        double* outp = (twin && A.out_twin) ? A.out_twin : A.out;
+        double val;
+        if (cut) {
+            val = A.raw ? INFINITY : -INFINITY;
+        } else {
+            const double* pre = VS.prefix;
+            chi += (pre[jlo] - pre[0]) + (pre[npts] - pre[jhi]);
+            const double sigma = A.lc.sigma;
+            const double half_chi2 = 0.5 * (chi / (sigma * sigma));       // likelihoods.py:486
+            val = A.raw ? half_chi2 : S.lnorm - half_chi2;
+        }
+        if (A.counters) {
+            unsigned long long c_skip = n_skip, c_int = n_interior, c_limb = n_limb;
+            for (int o = 16; o > 0; o >>= 1) {
+                c_skip += __shfl_xor_sync(0xffffffffu, c_skip, o);
+                c_int += __shfl_xor_sync(0xffffffffu, c_int, o);
+                c_limb += __shfl_xor_sync(0xffffffffu, c_limb, o);
+            }
+            if (lane == 0 && !cut) {
+                S.cnt[warp][0] += (unsigned long long)(jhi - jlo);
+                S.cnt[warp][1] += (unsigned long long)(jhi - jlo) - c_skip;
+                S.cnt[warp][2] += c_int;
+                S.cnt[warp][3] += c_limb;
+            }
+        }
+        if (lane == 0) {
+            outp[i] = val;
+            if (A.cval) A.cval[slot] = val;
+            if (A.lse_partials) {
+                // the evidence epilogue: ln-weight = lnL + lnprior of this draw
+                double x = val;
+                if (A.lnprior.p) x += A.lnprior.at(i);
+                lse_push(S.lse[warp][twin], x);
+                if (A.hist16 && isfinite(val))
+                    atomicAdd(A.hist16 + twin * kTopkBins + (int)(topk_key(val) >> 48), 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (A.lse_partials) {
+            for (int b = 0; b < 2; ++b) {
+                LsePartial a = S.lse[0][b];
+                for (int wv = 1; wv < kLnlWarps; ++wv) lse_merge(a, S.lse[wv][b]);
+                A.lse_partials[(size_t)b * gridDim.x + blockIdx.x] = a;
+            }
+        }
+        if (A.counters) {
+            for (int c = 0; c < 4; ++c) {
+                unsigned long long v = 0;
+                for (int wv = 0; wv < kLnlWarps; ++wv) v += S.cnt[wv][c];
+                if (v) atomicAdd(A.counters + c, v);
+            }
+        }
+    }
+}
+
+// ---- evidence + best draws: one block per scenario branch --------------------------------------
+// (1) merges the per-block (max, scaled-sum) records of lnl_kernel in block order;
+// (2) selects the best draws (reference marginal_likelihoods.py:152-153: the head of
+//     (-lnL).argsort()) among the work items of the call.  The order is that of a stable sort
+//     by (-lnL, index): a radix select on the composite (key of lnL, complemented index), which
+//     has no ties.  The first two digits come for free from the 16-bit histogram lnl_kernel
+//     filled; one pass over the work items then appends everything above the K-th value's
+//     bucket to the output and parks the bucket's own entries in shared memory, where the
+//     remaining digits are resolved (in global memory when the bucket does not fit: many equal
+//     values).  NaN and -inf never qualify.
+struct TopkState {
+    unsigned long long n_finite;       // finite entries
+    unsigned long long n_out;          // entries written to the output
+};
+
+struct FinalizeArgs {
+    const LsePartial* partials;   // [branches][n_partials]
+    int n_partials;
+    LsePartial* lse_out;          // [branches]
+    const int64_t* items;         // (draw index << 1) | branch, dense at the front and at the back
+    const double* cval;           // lnL per work item, same slots
+    int64_t cap;                  // capacity of items / cval
+    const unsigned long long* count_dev;   // [0] items at the front, [3] at the back
+    unsigned int* hist16;         // [branches][kTopkBins]; left zeroed for the next call
+    int64_t top_cap[2];
+    int64_t* top_idx[2];
+    double* top_val[2];
+    TopkState* st;                // [branches]
+};
+
+constexpr int kFinThreads = 1024;
+constexpr int kFinCand = 2048;     // bucket entries that fit in shared memory
+constexpr int kIdxBits = 40;       // draw indices below 2^40
+
+struct Composite {   // what the selection orders by: (key of lnL, complemented index), descending
+    unsigned long long hi, lo;
+};
+
+__device__ __forceinline__ unsigned comp_digit(const Composite& c, int d) {
+    // digits 0..7: key bytes from the top; 8..12: the 40 index bits
+    return d < 8 ? (unsigned)((c.hi >> (56 - 8 * d)) & 0xffu)
+                 : (unsigned)((c.lo >> (kIdxBits - 8 - 8 * (d - 8))) & 0xffu);
+}
+
+__device__ __forceinline__ bool comp_match(const Composite& c, const Composite& prefix,
+                                           const Composite& mask) {
+    return (c.hi & mask.hi) == prefix.hi && (c.lo & mask.lo) == prefix.lo;
+}
+
+__device__ __forceinline__ Composite make_comp(double v, int64_t idx) {
+    return Composite{topk_key(v), (~(unsigned long long)idx) & ((1ull << kIdxBits) - 1ull)};
+}
+
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs F) {
+    const int br = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ LsePartial sh_lse[kFinThreads / 32];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long sh_u64[kFinThreads / 32];
+    __shared__ unsigned long long cand_hi[kFinCand];
+    __shared__ unsigned long long cand_lo[kFinCand];
+    __shared__ unsigned int sh_bucket, sh_ncand, sh_nout, sh_digit;
+    __shared__ unsigned long long sh_above, sh_need, sh_nfinite;
+
+    // ---- (1) evidence: merge the blocks' records in block order (fixed tree)
+    {
+        LsePartial a{-INFINITY, 0.0, 0, 0};
+        const LsePartial* p = F.partials + (size_t)br * F.n_partials;
+        // contiguous chunk per thread keeps the block order
+        const int per = (F.n_partials + kFinThreads - 1) / kFinThreads;
+        for (int q = tid * per; q < (tid + 1) * per && q < F.n_partials; ++q) lse_merge(a, p[q]);
+        // warp tree, then warp 0 over the warps: lower lanes / warps first
+        for (int o = 1; o < 32; o <<= 1) {
+            LsePartial b;
+            b.m = __shfl_down_sync(0xffffffffu, a.m, o);
+            b.s = __shfl_down_sync(0xffffffffu, a.s, o);
+            b.n_finite = __shfl_down_sync(0xffffffffu, a.n_finite, o);
+            b.n_posinf = __shfl_down_sync(0xffffffffu, a.n_posinf, o);
+            if ((tid & 31) + o < 32) lse_merge(a, b);
+        }
+        if ((tid & 31) == 0) sh_lse[tid >> 5] = a;
+        __syncthreads();
+        if (tid == 0) {
+            LsePartial r = sh_lse[0];
+            for (int wv = 1; wv < kFinThreads / 32; ++wv) lse_merge(r, sh_lse[wv]);
+            F.lse_out[br] = r;
+        }
+    }
+
+    // ---- (2) best draws
+    unsigned int* h16 = F.hist16 + (size_t)br * kTopkBins;
+    constexpr int kPer = kTopkBins / kFinThreads;   // bins per thread: [tid*kPer, (tid+1)*kPer)
+    unsigned long long c_t = 0;
+    {
+        const uint4* h4 = reinterpret_cast<const uint4*>(h16 + tid * kPer);
+#pragma unroll 4
+        for (int q = 0; q < kPer / 4; ++q) {
+            uint4 v = h4[q];
+            c_t += (unsigned long long)v.x + v.y + v.z + v.w;
+        }
+    }
+    // entries in higher bins than this thread's: suffix sums over lanes, then over warps
+    unsigned long long suf = c_t;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long v = __shfl_down_sync(0xffffffffu, suf, o);
+        if ((tid & 31) + o < 32) suf += v;
+    }
+    if ((tid & 31) == 0) sh_u64[tid >> 5] = suf;   // total of the warp
+    __syncthreads();
+    unsigned long long above_t = suf - c_t;
+    unsigned long long total = 0;
+    for (int wv = 0; wv < kFinThreads / 32; ++wv) {
+        if (wv > (tid >> 5)) above_t += sh_u64[wv];
+        total += sh_u64[wv];
+    }
+    const unsigned long long K = total < (unsigned long long)(F.top_cap[br] > 0 ? F.top_cap[br] : 0)
+                                     ? total : (unsigned long long)(F.top_cap[br] > 0 ? F.top_cap[br] : 0);
+    if (tid == 0) { sh_nfinite = total; sh_ncand = 0; sh_nout = 0; sh_bucket = 0; sh_above = 0; sh_need = 0; }
+    __syncthreads();
+    if (K > 0 && above_t < K && K <= above_t + c_t) {   // exactly one thread
+        unsigned long long above = above_t;
+        for (int q = kPer - 1; q >= 0; --q) {
+            const unsigned long long c = h16[tid * kPer + q];
+            if (above + c >= K) {
+                sh_bucket = (unsigned)(tid * kPer + q);
+                sh_above = above;
+                sh_need = K - above;
+                break;
+            }
+            above += c;
+        }
+    }
+    __syncthreads();
+    {   // leave the histogram clean for the next call
+        uint4* h4 = reinterpret_cast<uint4*>(h16 + tid * kPer);
+#pragma unroll 4
+        for (int q = 0; q < kPer / 4; ++q) h4[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (K == 0) {
+        if (tid == 0) { F.st[br].n_finite = sh_nfinite; F.st[br].n_out = 0; }
+        return;
+    }
+    const unsigned bucket = sh_bucket;
+    const unsigned long long need = sh_need;          // entries wanted from the bucket (>= 1)
+    const int64_t n_front = (int64_t)F.count_dev[0], n_back = (int64_t)F.count_dev[3];
+    const int64_t n_items = n_front + n_back;
+    int64_t* out_idx = F.top_idx[br];
+    double* out_val = F.top_val[br];
+    const int64_t top_cap = F.top_cap[br];
+    const bool two = gridDim.x > 1;
+    // one pass over the work items: above the bucket -> output; in the bucket -> candidates
+    for (int64_t e = tid; e < n_items; e += kFinThreads) {
+        const int64_t slot = e < n_front ? e : F.cap - 1 - (e - n_front);
+        const int64_t item = F.items[slot];
+        if (two && (int)(item & 1) != br) continue;
+        const double v = F.cval[slot];
+        if (!isfinite(v)) continue;
+        const unsigned bin = (unsigned)(topk_key(v) >> 48);
+        if (bin > bucket) {
+            unsigned pos = atomicAdd(&sh_nout, 1u);
+            if ((int64_t)pos < top_cap) { out_idx[pos] = item >> 1; out_val[pos] = v; }
+        } else if (bin == bucket) {
+            unsigned pos = atomicAdd(&sh_ncand, 1u);
+            if (pos < (unsigned)kFinCand) {
+                Composite c = make_comp(v, item >> 1);
+                cand_hi[pos] = c.hi;
+                cand_lo[pos] = c.lo;
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned n_cand = sh_ncand;
+    const bool in_smem = n_cand <= (unsigned)kFinCand;
+    // radix select of the `need`-th largest composite among the bucket's entries: digits 2..12
+    Composite prefix{(unsigned long long)bucket << 48, 0ull}, mask{0xffffull << 48, 0ull};
+    unsigned long long k_rem = need;
+    unsigned long long n_match = n_cand;     // entries matching the prefix so far
+#pragma unroll 1
+    for (int d = 2; d < 13 && n_match > k_rem; ++d) {
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        if (in_smem) {
+            for (unsigned e = tid; e < n_cand; e += kFinThreads) {
+                Composite c{cand_hi[e], cand_lo[e]};
+                if (comp_match(c, prefix, mask)) atomicAdd(&hist[comp_digit(c, d)], 1u);
+            }
+        } else {
+            for (int64_t e = tid; e < n_items; e += kFinThreads) {
+                const int64_t slot = e < n_front ? e : F.cap - 1 - (e - n_front);
+                const int64_t item = F.items[slot];
+                if (two && (int)(item & 1) != br) continue;
+                const double v = F.cval[slot];
+                if (!isfinite(v)) continue;
+                Composite c = make_comp(v, item >> 1);
+                if (comp_match(c, prefix, mask)) atomicAdd(&hist[comp_digit(c, d)], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long above = 0;
+            unsigned dg = 0, cnt = 0;
+            for (int b = 255; b >= 0; --b) {
+                cnt = hist[b];
+                if (above + cnt >= k_rem && cnt > 0) { dg = (unsigned)b; break; }
+                above += cnt;
+            }
+            sh_digit = dg;
+            sh_above = above;
+            sh_need = cnt;
+        }
+        __syncthreads();
+        const unsigned dg = sh_digit;
+        if (d < 8) {
+            prefix.hi |= (unsigned long long)dg << (56 - 8 * d);
+            mask.hi |= 0xffull << (56 - 8 * d);
+        } else {
+            prefix.lo |= (unsigned long long)dg << (kIdxBits - 8 - 8 * (d - 8));
+            mask.lo |= 0xffull << (kIdxBits - 8 - 8 * (d - 8));
+        }
+        k_rem -= sh_above;
+        n_match = sh_need;
+        __syncthreads();
+    }
+    // every entry matching (prefix, mask) is wanted now (n_match <= k_rem; composites are
+    // distinct, so the digits run out with n_match == k_rem == 1 at the latest), plus the
+    // bucket's entries above it
+    auto wanted = [&](const Composite& c) {
+        if ((c.hi & mask.hi) != prefix.hi) return (c.hi & mask.hi) > prefix.hi;
+        if ((c.lo & mask.lo) != prefix.lo) return (c.lo & mask.lo) > prefix.lo;
+        return true;
+    };
+    if (in_smem) {
+        for (unsigned e = tid; e < n_cand; e += kFinThreads) {
+            Composite c{cand_hi[e], cand_lo[e]};
+            if (!wanted(c)) continue;
+            unsigned pos = atomicAdd(&sh_nout, 1u);
+            if ((int64_t)pos >= top_cap) continue;
+            unsigned long long u = c.hi;
+            u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;   // inverse of topk_key
+            out_idx[pos] = (int64_t)((~c.lo) & ((1ull << kIdxBits) - 1ull));
+            out_val[pos] = __longlong_as_double((long long)u);
+        }
+    } else {
+        for (int64_t e = tid; e < n_items; e += kFinThreads) {
+            const int64_t slot = e < n_front ? e : F.cap - 1 - (e - n_front);
+            const int64_t item = F.items[slot];
+            if (two && (int)(item & 1) != br) continue;
+            const double v = F.cval[slot];
+            if (!isfinite(v)) continue;
+            Composite c = make_comp(v, item >> 1);
+            if ((unsigned)(c.hi >> 48) != bucket || !wanted(c)) continue;
+            unsigned pos = atomicAdd(&sh_nout, 1u);
+            if ((int64_t)pos < top_cap) { out_idx[pos] = item >> 1; out_val[pos] = v; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        F.st[br].n_finite = sh_nfinite;
+        F.st[br].n_out = sh_nout < (unsigned long long)top_cap ? sh_nout : (unsigned long long)top_cap;
+    }
+}
+
+// ---- standalone log-mean-exp of an array (tri_log_mean_exp, _numerics.py:12-51) ----------------
 constexpr int kLseThreads = 256;
 
 // one partial per block over a contiguous slice: deterministic for a given grid
@@ -532,151 +916,21 @@ lse_partial_kernel(const double* lnl, Col lnprior, int64_t N, LsePartial* partia
     if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
 }
 
-__global__ void lse_final_kernel(const LsePartial* partials, int n, LsePartial* out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// merges up to a few thousand partials with one block (fixed tree: deterministic)
+__global__ void __launch_bounds__(kLseThreads)
+lse_final_kernel(const LsePartial* partials, int n, LsePartial* out) {
+    __shared__ LsePartial sh[kLseThreads];
     LsePartial a{-INFINITY, 0.0, 0, 0};
-    for (int b = 0; b < n; ++b) lse_merge(a, partials[b]);
-    *out = a;
-}
-
-// ---- best draws: top-K of lnL on the device (reference marginal_likelihoods.py:152-153) --------
-// Radix select on the order-preserving integer image of the doubles: eight 8-bit passes find the
-// exact K-th largest finite value T; everything above T is appended by the whole grid, ties at
-// T are taken in index order by one block, so the selection equals a stable sort by
-// (-lnL, index).  NaN and -inf never qualify.
-struct TopkState {
-    unsigned long long prefix, mask;   // key bits fixed so far
-    unsigned long long k_remaining;    // rank still to resolve inside the current bucket
-    unsigned long long n_finite;       // finite entries seen in pass 0
-    unsigned long long n_out;          // entries written to the output
-    unsigned long long n_ties;         // tie slots to fill with keys == prefix
-    unsigned long long n_equal;        // entries whose key == prefix
-    unsigned int hist[256];
-};
-
-__device__ __forceinline__ unsigned long long topk_key(double x) {
-    unsigned long long u = (unsigned long long)__double_as_longlong(x);
-    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);   // larger double -> larger key
-}
-
-__device__ __forceinline__ bool topk_valid(double x) { return isfinite(x); }
-
-constexpr int kTopkThreads = 256;
-
-__global__ void topk_init_kernel(TopkState* st, unsigned long long k) {
-    if (threadIdx.x < 256) st->hist[threadIdx.x] = 0;
-    if (threadIdx.x == 0) {
-        st->prefix = 0; st->mask = 0; st->k_remaining = k; st->n_finite = 0; st->n_out = 0;
-        st->n_ties = 0; st->n_equal = 0;
-    }
-}
-
-__global__ void __launch_bounds__(kTopkThreads)
-topk_hist_kernel(const double* lnl, int64_t N, TopkState* st, int pass) {
-    __shared__ unsigned int h[256];
-    h[threadIdx.x] = 0;
+    const int per = (n + kLseThreads - 1) / kLseThreads;
+    for (int q = threadIdx.x * per; q < (int)(threadIdx.x + 1) * per && q < n; ++q)
+        lse_merge(a, partials[q]);
+    sh[threadIdx.x] = a;
     __syncthreads();
-    const unsigned long long prefix = st->prefix, mask = st->mask;
-    const int shift = 56 - 8 * pass;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        double x = lnl[i];
-        if (!topk_valid(x)) continue;
-        unsigned long long key = topk_key(x);
-        if ((key & mask) == prefix) atomicAdd(&h[(key >> shift) & 0xff], 1u);
-    }
-    __syncthreads();
-    if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
-}
-
-__global__ void topk_scan_kernel(TopkState* st, int pass) {
-    if (threadIdx.x != 0) return;
-    const int shift = 56 - 8 * pass;
-    unsigned long long total = 0;
-    for (int b = 0; b < 256; ++b) total += st->hist[b];
-    if (pass == 0) {
-        st->n_finite = total;
-        if (st->k_remaining > total) st->k_remaining = total;   // fewer finite entries than K
-    }
-    unsigned long long need = st->k_remaining, above = 0, in_bucket = 0;
-    int bucket = 0;
-    for (int b = 255; b >= 0; --b) {
-        unsigned long long c = st->hist[b];
-        if (above + c >= need && c > 0) { bucket = b; in_bucket = c; break; }
-        above += c;
-    }
-    if (need == 0) bucket = 255;
-    st->prefix |= (unsigned long long)bucket << shift;
-    st->mask |= 0xffull << shift;
-    st->k_remaining = need - above;     // rank inside the chosen bucket
-    if (pass == 7) {
-        st->n_ties = st->k_remaining;   // how many entries equal to T are wanted ...
-        st->n_equal = in_bucket;        // ... out of this many
-    }
-    for (int b = 0; b < 256; ++b) st->hist[b] = 0;
-}
-
-// entries strictly above the threshold (and the ones equal to it when all of them are wanted,
-// the usual case of a unique K-th value): order does not matter, they are sorted afterwards
-__global__ void __launch_bounds__(kTopkThreads)
-topk_collect_above_kernel(const double* lnl, int64_t N, TopkState* st, int64_t* out_idx,
-                          double* out_val, int64_t cap) {
-    if (st->n_finite == 0) return;
-    const unsigned long long T = st->prefix;
-    const bool all_ties = st->n_equal <= st->n_ties;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        double x = lnl[i];
-        if (!topk_valid(x)) continue;
-        unsigned long long key = topk_key(x);
-        if (key < T || (key == T && !all_ties)) continue;
-        unsigned long long pos = atomicAdd(&st->n_out, 1ull);
-        if ((int64_t)pos < cap) { out_idx[pos] = i; out_val[pos] = x; }
-    }
-}
-
-// entries equal to the threshold, lowest indices first (one block walks the array in order)
-__global__ void __launch_bounds__(1024)
-topk_collect_ties_kernel(const double* lnl, int64_t N, TopkState* st, int64_t* out_idx,
-                         double* out_val, int64_t cap) {
-    __shared__ unsigned int warp_cnt[32];
-    __shared__ unsigned long long base_sh;
-    __shared__ long long want_sh;
-    if (st->n_finite == 0 || st->n_equal <= st->n_ties) return;   // nothing left to order
-    const unsigned long long T = st->prefix;
-    if (threadIdx.x == 0) { base_sh = st->n_out; want_sh = (long long)st->n_ties; }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int64_t start = 0; start < N; start += blockDim.x) {
-        long long want = want_sh;
-        if (want <= 0) break;
-        int64_t i = start + threadIdx.x;
-        bool hit = false;
-        double x = 0.0;
-        if (i < N) { x = lnl[i]; hit = topk_valid(x) && topk_key(x) == T; }
-        unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) warp_cnt[wid] = __popc(bal);
-        __syncthreads();
-        unsigned before = 0, total = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-            unsigned c = warp_cnt[w];
-            if (w < wid) before += c;
-            total += c;
-        }
-        unsigned rank = before + __popc(bal & ((1u << lane) - 1u));
-        if (hit && (long long)rank < want) {
-            unsigned long long pos = base_sh + rank;
-            if ((int64_t)pos < cap) { out_idx[pos] = i; out_val[pos] = x; }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned take = total < (unsigned long long)want ? total : (unsigned)want;
-            base_sh += take;
-            want_sh = want - take;
-        }
+    for (int o = kLseThreads / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) lse_merge(sh[threadIdx.x], sh[threadIdx.x + o]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) st->n_out = base_sh;
+    if (threadIdx.x == 0) *out = sh[0];
 }
 
 // ---- FITPACK B-spline evaluation (device sampler: stellar relations, funcs.py:54-140) ----------

@@ -270,8 +270,13 @@ TRI_HD void orbit_setup(Orbit& o, const OrbitTable& T, double k, double p, doubl
     o.row1 = o.row0 + kTableNm;
 }
 
+// The functions of the hot loop take the orbit / limb record as a template parameter: the
+// kernel keeps ONE copy per warp in shared memory and reads it through a `volatile` reference,
+// so that every field is fetched (LDS, warp broadcast) where it is used instead of living in
+// 32 x 2 registers for the whole draw; each field is read once per evaluation.
 // table part of the true anomaly: f(M) for M already reduced to [0, 2 pi)
-TRI_HD double ta_from_ma(const Orbit& o, const OrbitTable& T, double ma) {
+template <class OrbitT>
+TRI_HD double ta_from_ma(const OrbitT& o, const OrbitTable& T, double ma) {
     double x, s;
     if (ma < kPi) { x = ma; s = 1.0; } else { x = kTwoPi - ma; s = -1.0; }
     // the blend is continuous across cells, so x*inv_dm landing one cell off the oracle's
@@ -279,18 +284,22 @@ TRI_HD double ta_from_ma(const Orbit& o, const OrbitTable& T, double ma) {
     int im = (int)floor(x * T.inv_dm);
     if (im > kTableNm - 2) im = kTableNm - 2;
     double am = (x - im * T.dm) * T.inv_dm;
+    const double* r0 = o.row0;
+    const double* r1 = o.row1;
+    const double ae = o.ae;
 #if defined(__CUDA_ARCH__)
-    double t00 = __ldg(o.row0 + im), t01 = __ldg(o.row0 + im + 1);
-    double t10 = __ldg(o.row1 + im), t11 = __ldg(o.row1 + im + 1);
+    double t00 = __ldg(r0 + im), t01 = __ldg(r0 + im + 1);
+    double t10 = __ldg(r1 + im), t11 = __ldg(r1 + im + 1);
 #else
-    double t00 = o.row0[im], t01 = o.row0[im + 1], t10 = o.row1[im], t11 = o.row1[im + 1];
+    double t00 = r0[im], t01 = r0[im + 1], t10 = r1[im], t11 = r1[im + 1];
 #endif
-    double d = t00 * (1.0 - o.ae) * (1.0 - am) + t10 * o.ae * (1.0 - am)
-             + t01 * (1.0 - o.ae) * am + t11 * o.ae * am;
+    double d = t00 * (1.0 - ae) * (1.0 - am) + t10 * ae * (1.0 - am)
+             + t01 * (1.0 - ae) * am + t11 * ae * am;
     return ma + s * d;
 }
 
-TRI_HD double mean_anomaly(const Orbit& o, double t) {
+template <class OrbitT>
+TRI_HD double mean_anomaly(const OrbitT& o, double t) {
     double x = (t - o.c0) * o.n_rate;
     double ma = fma(-kTwoPi, floor(x * kInvTwoPi), x);
     if (ma < 0.0) ma += kTwoPi;
@@ -298,7 +307,8 @@ TRI_HD double mean_anomaly(const Orbit& o, double t) {
     return ma;
 }
 
-TRI_HD double z_from_ta(const Orbit& o, double ta) {
+template <class OrbitT>
+TRI_HD double z_from_ta(const OrbitT& o, double ta) {
     double st, ct;
     sincos_small(ta, st, ct);
     double swt = o.sinw * ct + o.cosw * st;  // sin(w + f)
@@ -306,7 +316,8 @@ TRI_HD double z_from_ta(const Orbit& o, double ta) {
     return swt < 0.0 ? -z : z;
 }
 
-TRI_HD double z_at(const Orbit& o, const OrbitTable& T, double t) {
+template <class OrbitT>
+TRI_HD double z_at(const OrbitT& o, const OrbitTable& T, double t) {
     return z_from_ta(o, ta_from_ma(o, T, mean_anomaly(o, t)));
 }
 
@@ -380,7 +391,8 @@ TRI_HD void limb_setup(Limb& L, double u1, double u2, double k) {
 //     reciprocal: no square root or extra division is needed for them.
 // `cls` receives the work class of SURVEY.md 8(d): 0 = trivial (out of transit, behind the
 // star, total eclipse), 1 = interior (z <= 1 - k), 2 = limb-crossing.
-TRI_HD double occult_quad(double z, double k, const Limb& L, int& cls) {
+template <class LimbT>
+TRI_HD double occult_quad(double z, double k, const LimbT& L, int& cls) {
     cls = 0;
     if (fabs(z - k) < 1e-6) z += 1e-6;
     if (z > 1.0 + k || z < 0.0) return 1.0;
@@ -472,7 +484,8 @@ TRI_HD double occult_quad(double z, double k, const Limb& L, int& cls) {
     return 1.0 - (L.c_le * le + L.c_ld * ld + L.u2 * ed) * L.inv_omega;
 }
 
-TRI_HD double occult_quad(double z, double k, const Limb& L) {
+template <class LimbT>
+TRI_HD double occult_quad(double z, double k, const LimbT& L) {
     int cls;
     return occult_quad(z, k, L, cls);
 }
