@@ -186,6 +186,11 @@ int tri_dev_splev(const double* t, const double* c, int32_t n, int32_t k, const 
 /* Measured FP64 FMA issue rate of this GPU [DFMA/s] (roofline denominator). */
 int tri_fp64_peak(double* dfma_per_s);
 
+/* Work accounting (off by default): when on, evaluations also count the work classes of the
+ * roofline model -- n_stamps, n_interior, n_limb of tri_result -- in the hot loop (about 1.5 %
+ * slower); when off those three fields are 0.  bench.py turns it on for one untimed pass. */
+int tri_set_counting(int32_t on);
+
 /* SM count of the bound device. */
 int tri_sm_count(int32_t* n);
 

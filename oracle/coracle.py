@@ -37,6 +37,7 @@ def lib():
         L.tro_log_mean_exp.restype = ctypes.c_double
         L.tro_log_mean_exp.argtypes = [_D, ctypes.c_int64]
         L.tro_num_threads.restype = ctypes.c_int
+        L.tro_set_num_threads.argtypes = [ctypes.c_int]
         L.tro_make_table.argtypes = [_D, _D, _D]
         L.tro_model.argtypes = [ctypes.c_int64, _D] + [ctypes.c_double] * 9 + [ctypes.c_int, _D]
         L.tro_lnl_tp.argtypes = ([ctypes.c_int64, _D, _D, ctypes.c_double, ctypes.c_double,
@@ -134,3 +135,8 @@ def log_mean_exp(logw):
 
 def num_threads():
     return lib().tro_num_threads()
+
+
+def set_num_threads(n):
+    """Threads of the OpenMP loops over draws (0 = the process-wide OpenMP setting)."""
+    lib().tro_set_num_threads(int(n))

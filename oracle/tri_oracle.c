@@ -22,6 +22,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+int tro_num_threads(void);
+
 #define TRO_NE 256
 #define TRO_NM 512
 #define TRO_MAX_E 0.95
@@ -265,7 +267,7 @@ void tro_lnl_tp(int64_t npts, const double* time, const double* flux, double sig
                 int companion_is_host, double* out, int64_t* counts) {
     tro_make_table(0, 0, 0);
     int64_t c0 = 0, c1 = 0, c2 = 0;
-#pragma omp parallel for schedule(dynamic, 16) reduction(+ : c0, c1, c2)
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : c0, c1, c2) num_threads(tro_num_threads())
     for (int64_t i = 0; i < n; i++) {
         int64_t cnt[3] = {0, 0, 0};
         double F_comp = cfr[i] / (1 - cfr[i]);
@@ -302,7 +304,7 @@ void tro_lnl_eb(int64_t npts, const double* time, const double* flux, double sig
     double tsec[25];
     linspace(-0.05, 0.05, 25, tsec);
     int64_t c0 = 0, c1 = 0, c2 = 0;
-#pragma omp parallel for schedule(dynamic, 16) reduction(+ : c0, c1, c2)
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : c0, c1, c2) num_threads(tro_num_threads())
     for (int64_t i = 0; i < n; i++) {
         int64_t cnt[3] = {0, 0, 0};
         double F_target = 1;
@@ -371,11 +373,17 @@ double tro_log_mean_exp(const double* logw, int64_t n) {
     return m + log(s) - log((double)n);
 }
 
+/* Threads of the OpenMP loops over draws: 0 = the process-wide OpenMP setting.  bench.py's CPU
+ * arms set it to the host's core count (torchrun exports OMP_NUM_THREADS=1 for every rank). */
+static int g_threads = 0;
+
+void tro_set_num_threads(int n) { g_threads = n > 0 ? n : 0; }
+
 int tro_num_threads(void) {
     int n = 1;
 #ifdef _OPENMP
     extern int omp_get_max_threads(void);
-    n = omp_get_max_threads();
+    n = g_threads > 0 ? g_threads : omp_get_max_threads();
 #endif
     return n;
 }

@@ -149,16 +149,24 @@ void hc_lnl(int eb, int64_t npts, const double* time_sorted, const double* flux_
         const bool probe = nsamples > 1 && !o.table_clamped;
         const double skip_beyond =
             1.0 + k + max_projected_speed(o, a_rs) * (0.5 * exptime) + 1e-9;
+        const double half_ma = o.table_clamped
+            ? 1e30 : o.n_rate * (0.5 * exptime) * (1.0 + 1e-9) + 1e-12;
         for (int j = jlo; j < jhi; j++) {
             double t = lc.time[j], acc = 0.0;
-            for (int is = probe ? 0 : 1; is <= nsamples; ++is) {
-                double toff = is ? exptime * ((is - 0.5) * inv_ns - 0.5) : 0.0;
-                double z = z_at(o, g_tab, t + toff);
-                if (is == 0) {
-                    if (std::fabs(z) > skip_beyond) { acc = (double)nsamples; if (stats) stats[2]++; break; }
-                    continue;
+            // as lnl_kernel: generic evaluation at the stamp centre, sub-exposures expanded
+            // around it (z_sub) unless the exposure straddles a half-turn of the table
+            StampOrbit so;
+            bool fast;
+            const double zc = stamp_centre(o, g_tab, t, half_ma, so, fast);
+            if (probe && std::fabs(zc) > skip_beyond) {
+                acc = (double)nsamples;
+                if (stats) stats[2]++;
+            } else {
+                for (int is = 1; is <= nsamples; ++is) {
+                    double toff = exptime * ((is - 0.5) * inv_ns - 0.5);
+                    double z = fast ? z_sub(o, g_tab, so, toff) : z_at(o, g_tab, t + toff);
+                    acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
                 }
-                acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, L);
             }
             double m = dilute(D, acc / nsamples);
             double r = lc.flux[j] - m;

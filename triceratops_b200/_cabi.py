@@ -58,7 +58,7 @@ EXPORTS = ("tri_init", "tri_shutdown", "tri_last_error", "tri_set_lightcurve", "
            "tri_simulate_tp", "tri_simulate_eb",
            "tri_fetch_lnl", "tri_log_mean_exp", "tri_last_timing", "tri_fp64_peak", "tri_sm_count",
            "tri_submit_tp", "tri_submit_eb", "tri_submit_tp_dev", "tri_submit_eb_dev", "tri_wait",
-           "tri_dev_splev")
+           "tri_dev_splev", "tri_set_counting")
 
 _lib = None
 
@@ -113,6 +113,7 @@ def load():
     L.tri_last_timing.argtypes = [c_double_p, c_double_p, c_double_p,
                                   ctypes.POINTER(ctypes.c_int32)]
     L.tri_fp64_peak.argtypes = [c_double_p]
+    L.tri_set_counting.argtypes = [ctypes.c_int32]
     L.tri_sm_count.argtypes = [ctypes.POINTER(ctypes.c_int32)]
     _lib = L
     return L

@@ -48,9 +48,8 @@ def _host_lib():
         _lib_tried = True
         if os.path.exists(_build.HOST_SO_PATH):
             L = ctypes.CDLL(_build.HOST_SO_PATH)
-            L.trih_splev.argtypes = [_D, ctypes.c_int, _D, ctypes.c_int, _D, _D, ctypes.c_int64]
-            if hasattr(L, "trih_set_threads"):
-                L.trih_set_threads(ctypes.c_int(N_THREADS))
+            L.trih_splev.argtypes = [_D, ctypes.c_int, _D, ctypes.c_int, _D, _D, ctypes.c_int64,
+                                     ctypes.c_int]
             _lib = L
     return _lib
 
@@ -67,7 +66,7 @@ def splev(spline, x):
     x = np.ascontiguousarray(x)
     y = np.empty_like(x)
     rc = L.trih_splev(t.ctypes.data_as(_D), t.size, c.ctypes.data_as(_D), int(k),
-                      x.ctypes.data_as(_D), y.ctypes.data_as(_D), x.size)
+                      x.ctypes.data_as(_D), y.ctypes.data_as(_D), x.size, N_THREADS)
     if rc != 0:
         return spline(x)
     return y

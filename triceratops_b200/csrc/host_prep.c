@@ -14,14 +14,17 @@
 #define KMAX 5
 
 int trih_splev(const double* t, int n, const double* c, int k, const double* x, double* y,
-               int64_t m) {
+               int64_t m, int nthreads) {
     if (k < 1 || k > KMAX || n < 2 * (k + 1)) return -1;
     const int k1 = k + 1;
     const int nk1 = n - k1;
     /* 1-based knot/coefficient access as in the Fortran original */
     const double* T = t - 1;
     const double* C = c - 1;
-#pragma omp parallel for schedule(static)
+    /* the thread count is the caller's, per call: the process-wide OpenMP setting (torch, BLAS,
+     * the OMP_NUM_THREADS=1 that torchrun exports) is left alone */
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
     for (int64_t i = 0; i < m; i++) {
         const double arg = x[i];
         /* knot interval T(l) <= arg < T(l+1), clamped to [k1, nk1] (extrapolation uses the end
@@ -57,24 +60,4 @@ int trih_splev(const double* t, int n, const double* c, int k, const double* x, 
         y[i] = sp;
     }
     return 0;
-}
-
-int trih_num_threads(void) {
-#ifdef _OPENMP
-    extern int omp_get_max_threads(void);
-    return omp_get_max_threads();
-#else
-    return 1;
-#endif
-}
-
-/* Launchers such as torchrun export OMP_NUM_THREADS=1 for every rank; the Python side decides
- * how many host threads a rank may use (cores / ranks on the node) and says so here. */
-void trih_set_threads(int n) {
-#ifdef _OPENMP
-    extern void omp_set_num_threads(int);
-    if (n > 0) omp_set_num_threads(n);
-#else
-    (void)n;
-#endif
 }

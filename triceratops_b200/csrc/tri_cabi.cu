@@ -166,6 +166,7 @@ struct Ctx {
     int device = -1;
     int sm_count = 0;
     int lnl_blocks_per_sm = 0;
+    bool count_work = false;   // tri_set_counting: run the instantiation with work counters
     size_t lnl_smem = 0;   // dynamic shared memory used to stage the light curve (0 = none)
     cudaStream_t stream = nullptr;        // kernels and result read-back
     cudaStream_t copy_stream = nullptr;   // host columns -> staging (overlaps the kernels)
@@ -274,7 +275,8 @@ void finish_result(const LsePartial& r, int64_t N, tri_result* out) {
 
 int launch_lnl(Slot& S, LnlArgs& A, cudaStream_t s) {
     size_t smem = lnl_smem_bytes();
-    lnl_kernel<<<lnl_grid(), kLnlThreads, smem, s>>>(A);
+    if (g.count_work) lnl_kernel<true><<<lnl_grid(), kLnlThreads, smem, s>>>(A);
+    else lnl_kernel<false><<<lnl_grid(), kLnlThreads, smem, s>>>(A);
     S.launches += 1;
     CU(cudaGetLastError());
     return TRI_OK;
@@ -573,7 +575,7 @@ int tri_init(int device) {
     }
     // occupancy of the persistent light-curve kernel
     int bps = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lnl_kernel, kLnlThreads, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, lnl_kernel<false>, kLnlThreads, 0));
     g.lnl_blocks_per_sm = std::max(1, bps);
     g.lnl_smem = 0;
     g.ready = true;
@@ -612,6 +614,13 @@ int tri_shutdown(void) {
     cudaStreamDestroy(g.copy_stream);
     cudaStreamDestroy(g.stream);
     g = Ctx{};
+    return TRI_OK;
+}
+
+int tri_set_counting(int32_t on) {
+    int rc = need_ready(false);
+    if (rc) return rc;
+    g.count_work = on != 0;
     return TRI_OK;
 }
 
@@ -679,10 +688,10 @@ int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, dou
     {
         int bps0 = 0, bps1 = 0;
         size_t need = (size_t)(3 * (size_t)npts + 1) * sizeof(double);
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps0, lnl_kernel, kLnlThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps0, lnl_kernel<false>, kLnlThreads, 0));
         g.lnl_smem = 0;
         if (need <= 48 * 1024) {
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps1, lnl_kernel, kLnlThreads, need));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps1, lnl_kernel<false>, kLnlThreads, need));
             if (bps1 >= bps0) g.lnl_smem = need;
         }
         g.lnl_blocks_per_sm = std::max(1, bps0);

@@ -266,10 +266,13 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
-constexpr int kLnlThreads = 128;
+#ifndef TRI_LNL_THREADS
+#define TRI_LNL_THREADS 128
+#endif
+constexpr int kLnlThreads = TRI_LNL_THREADS;
 constexpr int kLnlWarps = kLnlThreads / 32;
 #ifndef TRI_LNL_MIN_BLOCKS
-#define TRI_LNL_MIN_BLOCKS 8       // 64 registers per thread: 32 warps per SM
+#define TRI_LNL_MIN_BLOCKS (1024 / TRI_LNL_THREADS)   // 64 registers per thread: 32 warps per SM
 #endif
 constexpr int kLnlMinBlocks = TRI_LNL_MIN_BLOCKS;
 
@@ -284,6 +287,7 @@ struct WarpDraw {
     Orbit o;
     Limb L;
     double skip_beyond;   // centre probe: |z| beyond which a whole exposure is out of transit
+    double half_ma;       // half an exposure in mean anomaly (+ margin): n * exptime / 2
     double d1, d2;        // dilution (likelihoods.py:352-357 / :427-438)
     int two_stage;
 };
@@ -299,6 +303,11 @@ struct LnlShared {
     double lnorm;
 };
 
+// kCount: also count the work classes of SURVEY.md 8(d) (window stamps, evaluated stamps,
+// interior and limb points) into A.counters -- the roofline accounting of bench.py and the
+// n_stamps / n_interior / n_limb diagnostics; the production instantiation leaves them out of
+// the hot loop.
+template <bool kCount>
 __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs A) {
     extern __shared__ double smem[];
     __shared__ LnlShared S;
@@ -445,6 +454,9 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                     wd.o = o;
                     wd.L = L;
                     wd.skip_beyond = skip_beyond;
+                    // table_clamped orbits (e >= 0.95) always take the generic path
+                    wd.half_ma = o.table_clamped ? 1e30
+                                                 : o.n_rate * (0.5 * exptime) * (1.0 + 1e-9) + 1e-12;
                     wd.d1 = d1;
                     wd.d2 = d2;
                     wd.two_stage = two_stage;
@@ -511,31 +523,36 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                     }
                     // this lane's sub-exposures: is_lo .. is_hi of 1 .. ns
                     const int is_lo = 1 + ((sub * ns) >> gsh), is_hi = ((sub + 1) * ns) >> gsh;
+                    // the centre of the exposure: generic orbit evaluation; the sub-exposures
+                    // are expanded around it (tri_model.cuh, z_sub)
+                    StampOrbit so;
+                    bool fast;
+                    const double zc = stamp_centre(vd.o, A.tab, t, vd.half_ma, so, fast);
+                    if (probe && fabs(zc) > vd.skip_beyond) {
+                        // the whole exposure is out of transit: model == 1
+                        acc = (double)(is_hi - is_lo + 1);
+                        if (kCount) n_skip += (sub == 0);
+                    } else {
 #pragma unroll 1
-                    for (int is = probe ? 0 : is_lo; is <= is_hi; ++is) {
-                        // sub-exposure offset exptime ((is - 1/2)/ns - 1/2), tabulated per block
-                        // (the back half of a paired round runs its sub-exposures backwards in
-                        // time, the mirror image of the front half)
-                        const int iso = (mirror && is) ? ns + 1 - is : is;
-                        double toff = 0.0;
-                        if (primary)
-                            toff = toff_tab ? S.toff[iso]
-                                            : (iso ? A.lc.exptime * ((iso - 0.5) / ns - 0.5) : 0.0);
-                        const double z = z_at(vd.o, A.tab, t + toff);
-                        if (is == 0) {   // stamp centre: is the whole exposure out of transit?
-                            if (fabs(z) > vd.skip_beyond) {
-                                acc = (double)(is_hi - is_lo + 1);
-                                n_skip += (sub == 0);
-                                break;
+                        for (int is = is_lo; is <= is_hi; ++is) {
+                            // sub-exposure offset exptime ((is - 1/2)/ns - 1/2), tabulated per
+                            // block (the back half of a paired round runs its sub-exposures
+                            // backwards in time, the mirror image of the front half)
+                            const int iso = mirror ? ns + 1 - is : is;
+                            double toff = 0.0;
+                            if (primary)
+                                toff = toff_tab ? S.toff[iso]
+                                                : A.lc.exptime * ((iso - 0.5) / ns - 0.5);
+                            const double z = fast ? z_sub(vd.o, A.tab, so, toff)
+                                                  : z_at(vd.o, A.tab, t + toff);
+                            int cls = 0;   // work class of SURVEY.md 8(d): 1 interior, 2 limb-crossing
+                            const double k = vd.o.k;
+                            acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, vd.L, cls);
+                            if (kCount) {
+                                n_interior += (unsigned)(primary && cls == 1);
+                                n_limb += (unsigned)(primary && cls == 2);
                             }
-                            is = is_lo - 1;
-                            continue;
                         }
-                        int cls = 0;   // work class of SURVEY.md 8(d): 1 interior, 2 limb-crossing
-                        const double k = vd.o.k;
-                        acc += (z > 1.0 + k) ? 1.0 : occult_quad(z, k, vd.L, cls);
-                        n_interior += (unsigned)(primary && cls == 1);
-                        n_limb += (unsigned)(primary && cls == 2);
                     }
                 }
                 if (gsh) {   // (warp-uniform) the lanes of a stamp pool their sub-exposure sums
@@ -583,7 +600,7 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
             const double half_chi2 = 0.5 * (chi / (sigma * sigma));       // likelihoods.py:486
             val = A.raw ? half_chi2 : S.lnorm - half_chi2;
         }
-        if (A.counters) {
+        if (kCount && A.counters) {
             unsigned long long c_skip = n_skip, c_int = n_interior, c_limb = n_limb;
             for (int o = 16; o > 0; o >>= 1) {
                 c_skip += __shfl_xor_sync(0xffffffffu, c_skip, o);
@@ -619,7 +636,7 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                 A.lse_partials[(size_t)b * gridDim.x + blockIdx.x] = a;
             }
         }
-        if (A.counters) {
+        if (kCount && A.counters) {
             for (int c = 0; c < 4; ++c) {
                 unsigned long long v = 0;
                 for (int wv = 0; wv < kLnlWarps; ++wv) v += S.cnt[wv][c];

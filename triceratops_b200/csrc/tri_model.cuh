@@ -38,16 +38,20 @@ constexpr double kRsun = 69570000000.0;
 constexpr double kRearth = 637810000.0;
 
 // Reciprocal, reciprocal square root and square root for operands that are known to be normal
-// and well scaled (radius ratios, separations, AGM iterates): hardware seed + Newton steps,
-// without the IEEE slow paths (subnormals, correct rounding).  Accurate to ~1 ulp, which is far
-// inside the 1e-9 tolerance on lnL; on the host (tests/hostcheck) they are the exact operations.
+// and well scaled (radius ratios, separations, AGM iterates): hardware seed (MUFU.RCP64H /
+// RSQ64H, relative error e0 <= 2^-20) + ONE third-order correction step, without the IEEE slow
+// paths (subnormals, correct rounding):
+//   1/x       y (1 + e + e^2),             e = 1 - x y       residual e^3   (3 FP64 ops)
+//   1/sqrt x  y (1 + e/2 + 3 e^2/8),       e = 1 - x y^2     residual 5e^3/16 (5 FP64 ops)
+// i.e. ~2^-60 before rounding, ~1 ulp after it: far inside the 1e-9 tolerance on lnL (the
+// second-order Newton pairs they replace cost 4 and 8 ops); on the host (tests/hostcheck) they
+// are the exact operations.
 TRI_HD double fast_rcp(double x) {
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
     return fma(y, e, y);
 #else
     return 1.0 / x;
@@ -58,21 +62,27 @@ TRI_HD double fast_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x * y, y, 1.0);
-    y = fma(y * 0.5, e, y);
-    e = fma(-x * y, y, 1.0);
-    return fma(y * 0.5, e, y);
+    double e = fma(-(x * y), y, 1.0);
+    double p = fma(0.375, e, 0.5) * e;
+    return fma(y, p, y);
 #else
     return 1.0 / sqrt(x);
+#endif
+}
+
+// sqrt(x) for x > 0 (no zero / negative handling: AGM iterates)
+TRI_HD double fast_sqrt_pos(double x) {
+#if defined(__CUDA_ARCH__)
+    return x * fast_rsqrt(x);
+#else
+    return sqrt(x);
 #endif
 }
 
 // sqrt(x) for x >= 0 (0 -> 0, negative -> NaN as with sqrt)
 TRI_HD double fast_sqrt(double x) {
 #if defined(__CUDA_ARCH__)
-    double y = fast_rsqrt(x);
-    double s = x * y;
-    s = fma(fma(-s, s, x), 0.5 * y, s);
+    double s = x * fast_rsqrt(x);
     return x == 0.0 ? 0.0 : s;
 #else
     return sqrt(x);
@@ -236,6 +246,7 @@ struct Orbit {
     double ae;         // table blend weight in e
     const double* row0;
     const double* row1;
+    double esw, ecw;   // e sin w, e cos w: 1 + e cos f = 1 + ecw cos(w+f) + esw sin(w+f)
     bool table_clamped;  // e beyond the table: last cell extrapolated (monotonicity not guaranteed)
 };
 
@@ -268,6 +279,8 @@ TRI_HD void orbit_setup(Orbit& o, const OrbitTable& T, double k, double p, doubl
     o.ae = (e - T.de * ie) / T.de;
     o.row0 = T.tae + (size_t)ie * kTableNm;
     o.row1 = o.row0 + kTableNm;
+    o.esw = e * o.sinw;
+    o.ecw = e * o.cosw;
 }
 
 // The functions of the hot loop take the orbit / limb record as a template parameter: the
@@ -293,9 +306,12 @@ TRI_HD double ta_from_ma(const OrbitT& o, const OrbitTable& T, double ma) {
 #else
     double t00 = r0[im], t01 = r0[im + 1], t10 = r1[im], t11 = r1[im + 1];
 #endif
-    double d = t00 * (1.0 - ae) * (1.0 - am) + t10 * ae * (1.0 - am)
-             + t01 * (1.0 - ae) * am + t11 * ae * am;
-    return ma + s * d;
+    // bilinear blend as three lerps (6 FP64 ops; the oracle's four-product form differs from it
+    // by rounding only)
+    double c0 = fma(ae, t10 - t00, t00);
+    double c1 = fma(ae, t11 - t01, t01);
+    double d = fma(am, c1 - c0, c0);
+    return fma(s, d, ma);
 }
 
 template <class OrbitT>
@@ -321,6 +337,113 @@ TRI_HD double z_at(const OrbitT& o, const OrbitTable& T, double t) {
     return z_from_ta(o, ta_from_ma(o, T, mean_anomaly(o, t)));
 }
 
+// ---- sub-exposures of one time stamp ------------------------------------------------------------
+// The sub-exposures of a stamp lie within exptime/2 of its centre, so most of the orbit work of
+// z_at() can be shared: the mean anomaly is the centre's plus n*dt (no range reduction: the
+// caller checks once per stamp that the exposure stays inside one half-turn of the (e, M) table),
+// and sin / cos of w + f follow from the centre's by angle addition with the SMALL true-anomaly
+// difference d (two short Taylor polynomials, no quadrant logic).  The interpolated f(M) itself
+// is evaluated per sub-exposure exactly as in ta_from_ma(): table error is part of the model.
+// When d leaves the polynomials' range (long exposures on eccentric orbits) the base point
+// moves to the current sub-exposure.
+TRI_TABLE(kTaylor, 10,
+          -1.66666666666666666667e-01,  /* 0 sin: -1/3!  */
+          8.33333333333333333333e-03,   /* 1       1/5!  */
+          -1.98412698412698412698e-04,  /* 2      -1/7!  */
+          2.75573192239858906526e-06,   /* 3       1/9!  */
+          -2.50521083854417187751e-08,  /* 4      -1/11! */
+          -5.00000000000000000000e-01,  /* 5 cos: -1/2!  */
+          4.16666666666666666667e-02,   /* 6       1/4!  */
+          -1.38888888888888888889e-03,  /* 7      -1/6!  */
+          2.48015873015873015873e-05,   /* 8       1/8!  */
+          -2.75573192239858906526e-07)  /* 9      -1/10! */
+
+constexpr double kStampMaxDelta = 0.125;   // |d| beyond which the base point is moved
+                                           // (truncation: d^12/12! < 3e-20, d^13/13! < 3e-22)
+
+struct StampOrbit {
+    double ma_c;     // mean anomaly at the stamp centre, reduced to [0, 2 pi)
+    double ta_b;     // true anomaly of the base point
+    double S_b, C_b; // sin(w + ta_b), cos(w + ta_b)
+    bool upper;      // the exposure lies in [pi, 2 pi): the table is read mirrored
+};
+
+// z from sin(w+f), cos(w+f)
+template <class OrbitT>
+TRI_HD double z_from_sc(const OrbitT& o, double S, double C) {
+    double den = fma(o.ecw, C, fma(o.esw, S, 1.0));          // 1 + e cos f
+    double z = o.a1me2 * fast_rcp(den) * fast_sqrt(1.0 - S * S * o.sini2);
+    return S < 0.0 ? -z : z;
+}
+
+// Centre of a stamp: the generic evaluation (range reduction, table, full sincos); fills `so`
+// and returns z.  `fast` tells whether every sub-exposure within +-half_ma of the centre's mean
+// anomaly stays inside one half-turn, i.e. may use z_sub().
+template <class OrbitT>
+TRI_HD double stamp_centre(const OrbitT& o, const OrbitTable& T, double t, double half_ma,
+                           StampOrbit& so, bool& fast) {
+    const double ma = mean_anomaly(o, t);
+    const double ta = ta_from_ma(o, T, ma);
+    double st, ct;
+    sincos_small(ta, st, ct);
+    const double sw = o.sinw, cw = o.cosw;
+    so.ma_c = ma;
+    so.ta_b = ta;
+    so.S_b = sw * ct + cw * st;
+    so.C_b = cw * ct - sw * st;
+    so.upper = ma >= kPi;
+    const double lo = ma - half_ma, hi = ma + half_ma;
+    fast = so.upper ? (lo > kPi && hi < kTwoPi) : (lo > 0.0 && hi < kPi);
+    return z_from_sc(o, so.S_b, so.C_b);
+}
+
+// Sub-exposure at time offset `toff` from the centre of a stamp prepared by stamp_centre()
+// (only when it reported fast).
+template <class OrbitT>
+TRI_HD double z_sub(const OrbitT& o, const OrbitTable& T, StampOrbit& so, double toff) {
+    const double ma = fma(toff, o.n_rate, so.ma_c);
+    const double x = so.upper ? kTwoPi - ma : ma;
+    const double u = x * T.inv_dm;
+    const double fl = fmin(floor(u), (double)(kTableNm - 2));
+    const double am = u - fl;
+    const int im = (int)fl;
+    const double* r0 = o.row0;
+    const double* r1 = o.row1;
+    const double ae = o.ae;
+#if defined(__CUDA_ARCH__)
+    double t00 = __ldg(r0 + im), t01 = __ldg(r0 + im + 1);
+    double t10 = __ldg(r1 + im), t11 = __ldg(r1 + im + 1);
+#else
+    double t00 = r0[im], t01 = r0[im + 1], t10 = r1[im], t11 = r1[im + 1];
+#endif
+    const double c0 = fma(ae, t10 - t00, t00);
+    const double c1 = fma(ae, t11 - t01, t01);
+    const double d = fma(am, c1 - c0, c0);
+    const double ta = so.upper ? ma - d : ma + d;
+    const double dl = ta - so.ta_b;
+    double S, C;
+    if (fabs(dl) > kStampMaxDelta) {   // rare: move the base point here
+        double st, ct;
+        sincos_small(ta, st, ct);
+        const double sw = o.sinw, cw = o.cosw;
+        S = sw * ct + cw * st;
+        C = cw * ct - sw * st;
+        so.ta_b = ta;
+        so.S_b = S;
+        so.C_b = C;
+    } else {
+        const double* K = TRI_T(kTaylor);
+        const double z2 = dl * dl;
+        double sp = K[1] + z2 * (K[2] + z2 * (K[3] + z2 * K[4]));
+        sp = fma(dl * z2, fma(z2, sp, K[0]), dl);                  // sin d
+        double cp = K[6] + z2 * (K[7] + z2 * (K[8] + z2 * K[9]));
+        cp = fma(z2, fma(z2, cp, K[5]), 1.0);                      // cos d
+        S = fma(so.S_b, cp, so.C_b * sp);
+        C = fma(so.C_b, cp, -(so.S_b * sp));
+    }
+    return z_from_sc(o, S, C);
+}
+
 // ---------------------------------------------------------------- elliptic integrals
 // K and E from the complementary parameter m1 = 1 - q^2; they share its logarithm
 // (Hastings, A&S 17.3.34 / 17.3.36).
@@ -344,10 +467,11 @@ TRI_HD void ellke_m1(double m1, double& Kk, double& Ek) {
 TRI_HD double ellpicb(double kc, double p, double d) {
     double e = kc;
     double m0 = 1.0, c = 1.0;
+    const double tol = 1e-8;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int it = 0; it < 64; ++it) {
+    for (int it = 64; it > 0; --it) {   // (quadratic convergence: 2-6 sweeps; the bound never binds)
         double ip = fast_rcp(p);
         double f = c;
         c = fma(d, ip, c);
@@ -356,14 +480,11 @@ TRI_HD double ellpicb(double kc, double p, double d) {
         p = g + p;
         g = m0;
         m0 = kc + m0;
-        if (fabs(g - kc) > 1e-8 * g) {
-            kc = 2.0 * fast_sqrt(e);
-            e = kc * m0;
-        } else {
-            return kHalfPi * fma(c, m0, d) * fast_rcp(m0 * (m0 + p));
-        }
+        if (!(fabs(g - kc) > tol * g)) break;   // converged (or NaN)
+        kc = 2.0 * fast_sqrt_pos(e);
+        e = kc * m0;
     }
-    return 0.0;
+    return kHalfPi * fma(c, m0, d) * fast_rcp(m0 * (m0 + p));
 }
 
 // ---------------------------------------------------------------------- occultation

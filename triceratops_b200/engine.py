@@ -461,6 +461,11 @@ class Engine:
                 "launches": n.value}
 
     @_locked
+    def set_counting(self, on):
+        """Work counters of the roofline model (n_stamps, n_interior, n_limb) on / off."""
+        _cabi.check(self.lib.tri_set_counting(int(bool(on))))
+
+    @_locked
     def fp64_peak(self):
         v = ctypes.c_double()
         _cabi.check(self.lib.tri_fp64_peak(ctypes.byref(v)))
