@@ -98,6 +98,12 @@ def eb_masks(N, reb, q, P_orb, inc, ecc, argp, mtot, rhost, extra_mask=None):
 class OracleEngine:
     device = -1
 
+    @property
+    def torch_device(self):
+        """Device-sampler mode on the CPU stand-in: the prior draws are torch CPU tensors."""
+        import torch
+        return torch.device("cpu")
+
     def set_lightcurve(self, time, flux, sigma, exptime, nsamples):
         self.lc = (np.asarray(time, float), np.asarray(flux, float), float(sigma),
                    float(exptime), int(nsamples))

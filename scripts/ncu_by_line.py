@@ -18,7 +18,7 @@ import tempfile
 
 rep, so = sys.argv[1], sys.argv[2]
 launch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-KERNEL = "_ZN3tri10lnl_kernelENS_7LnlArgsE"
+KERNEL = "lnl_kernel"
 
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True,
@@ -29,7 +29,8 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture
 lines, cur, inside = [], ("?", 0), False
 for ln in dis.splitlines():
     if ln.startswith("//---") and ".text." in ln:
-        inside = KERNEL in ln
+        # the production instantiation (lnl_kernel<false>) when the kernel is a template
+        inside = KERNEL in ln and "ILb1E" not in ln
         continue
     if not inside:
         continue

@@ -187,7 +187,7 @@ def draw_eb_columns(N, seed, star=None):
                 mtot=star["M"] + masses, rhost=star["R"], u1=0.4338, u2=0.2008, cfr=0.0)
 
 
-def calc_probs_small(t, f, s, N=301, seed=77):
+def calc_probs_small(t, f, s, N=301, seed=77, full=False):
     """A short calc_probs (three target-star scenario calls) used by the multi-rank test."""
     from triceratops_b200 import synthetic as synth
     from triceratops_b200.triceratops import target
@@ -197,4 +197,4 @@ def calc_probs_small(t, f, s, N=301, seed=77):
     np.random.seed(seed)
     tgt.calc_probs(t, f, s, TOI465["P"], N=N, parallel=True, verbose=0,
                    drop_scenario=["PTP", "PEB", "STP", "SEB", "DEB", "BTP", "BEB"])
-    return tgt.lnZ.copy()
+    return tgt if full else tgt.lnZ.copy()

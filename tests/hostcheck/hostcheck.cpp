@@ -32,7 +32,7 @@ double ta_newton(double ma, double e) {
 
 void ensure_table() {
     if (!g_tae.empty()) return;
-    g_tae.resize((size_t)kTableNe * kTableNm);
+    g_tae.assign((size_t)kTableNe * kTableNm + 1, 0.0);   // (+1 padding, as tri_init)
     double de = kTableMaxE / (kTableNe - 1), dm = kPi / (kTableNm - 1);
     for (int i = 0; i < kTableNe; i++) {
         double e = (i == kTableNe - 1) ? kTableMaxE : i * de;

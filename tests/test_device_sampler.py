@@ -20,6 +20,7 @@ from triceratops_b200._ldc import grid_for
 class _Capture:
     """Stands where the engine stands and keeps the columns of every call."""
     device = -1
+    torch_device = torch.device("cpu")
 
     def __init__(self):
         self.calls = []

@@ -1,6 +1,8 @@
-"""Multi-rank path on CPU: world_size 2 over gloo.  Every rank makes the same host draws,
-evaluates its own contiguous slice and one all-gather merges the (max, scaled-sum) records and
-the best-draw candidates; the result must equal the single-process run."""
+"""Multi-rank path on CPU: world_size 2 over gloo.  Single lnZ_* calls: every rank makes the
+same host draws, evaluates its own contiguous slice and one all-gather merges the (max,
+scaled-sum) records and the best-draw candidates.  calc_probs: rank 0 draws and scatters every
+engine call's columns, ONE all-gather carries the records of all rows.  Either way the result
+must equal the single-process run."""
 import os
 import pickle
 import socket
@@ -55,10 +57,26 @@ def test_two_ranks_equal_one(tmp_path, oracle_engine, toi465_lc):
             np.testing.assert_allclose(a[k][:k_rows], b[k][:k_rows], rtol=1e-12, err_msg=k)
 
     from conftest import calc_probs_small
-    lnZ_cp = calc_probs_small(t, f, s)
-    assert np.isfinite(lnZ_cp).sum() >= 3
+    one = calc_probs_small(t, f, s, full=True)
+    lnZ_cp = one.lnZ
+    assert np.isfinite(lnZ_cp).sum() >= 3 and one.collectives is None
     for r in res:
         np.testing.assert_allclose(r["lnZ_cp"], lnZ_cp, rtol=0, atol=1e-9)
+        # the whole table reaches every rank, from one exchange of records (+ one scatter of
+        # draw columns per engine call: TTP, TEB, DTP)
+        np.testing.assert_allclose(r["cp"]["prob"], one.probs.prob.values, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(r["cp"]["R_p"], one.probs.R_p.values, rtol=1e-12)
+        np.testing.assert_allclose(r["cp"]["inc"], one.probs.inc.values, rtol=1e-12)
+        np.testing.assert_allclose(r["cp"]["u1"], one.u1, rtol=0, atol=0)
+        assert abs(r["cp"]["FPP"] - one.FPP) < 1e-9
+        assert r["cp"]["collectives"] == {"record_exchanges": 1, "scatters": 3}
+        # device-sampler mode: one exchange, no scatters; both ranks hold the same table and
+        # the evidences are finite where the host-sampler ones are
+        assert r["dev"]["collectives"] == {"record_exchanges": 1, "scatters": 0}
+        np.testing.assert_array_equal(r["dev"]["lnZ"], res[0]["dev"]["lnZ"])
+        np.testing.assert_array_equal(r["dev"]["R_p"], res[0]["dev"]["R_p"])
+        assert np.isfinite(r["dev"]["lnZ"][[0, 9]]).all()     # TP and DTP rows have support
+        assert abs(np.sum(r["dev"]["prob"]) - 1.0) < 1e-12
 
     for r in res:                       # both ranks hold the combined answer
         same(r["tp"], tp)

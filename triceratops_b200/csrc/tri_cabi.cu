@@ -548,7 +548,8 @@ int tri_init(int device) {
     CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     // orbit table
-    std::vector<double> es, ms, tae((size_t)kTableNe * kTableNm);
+    // (+1: z_sub may read one element behind the last row with weight 0, see tri_model.cuh)
+    std::vector<double> es, ms, tae((size_t)kTableNe * kTableNm + 1, 0.0);
     linspace(0.0, kTableMaxE, kTableNe, es);
     linspace(0.0, kPi, kTableNm, ms);
     for (int i = 0; i < kTableNe; i++)

@@ -266,13 +266,18 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
+// One warp per block: the per-draw record of the warp then sits at compile-time constant
+// shared-memory addresses.  24 resident blocks per SM = 80 registers per thread (A/B on B200,
+// ms per step of the headline workload: 128 threads x 6: 167.9, 128 x 8: 168.8, 32 x 24: 166.5,
+// 32 x 32: 165.6 -- the kernel is bound by the issue port, not by the number of warps, see
+// DESIGN.md).
 #ifndef TRI_LNL_THREADS
-#define TRI_LNL_THREADS 128
+#define TRI_LNL_THREADS 32
 #endif
 constexpr int kLnlThreads = TRI_LNL_THREADS;
 constexpr int kLnlWarps = kLnlThreads / 32;
 #ifndef TRI_LNL_MIN_BLOCKS
-#define TRI_LNL_MIN_BLOCKS (1024 / TRI_LNL_THREADS)   // 64 registers per thread: 32 warps per SM
+#define TRI_LNL_MIN_BLOCKS (768 / TRI_LNL_THREADS)
 #endif
 constexpr int kLnlMinBlocks = TRI_LNL_MIN_BLOCKS;
 
@@ -340,7 +345,8 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
             S.toff[is] = is ? A.lc.exptime * ((is - 0.5) * inv - 0.5) : 0.0;
     }
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // (one warp per block: every shared-memory address is a compile-time constant)
+    const int warp = kLnlWarps == 1 ? 0 : (int)(threadIdx.x >> 5);
     if (lane == 0) {
         S.lse[warp][0] = LsePartial{-INFINITY, 0.0, 0, 0};
         S.lse[warp][1] = LsePartial{-INFINITY, 0.0, 0, 0};

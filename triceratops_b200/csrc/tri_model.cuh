@@ -89,6 +89,28 @@ TRI_HD double fast_sqrt(double x) {
 #endif
 }
 
+// sqrt(max(x, 0)): 0 and the slightly negative arguments that rounding can leave in
+// 1 - sin^2(..) sin^2 i give 0 (x rsqrt(x) is NaN there and fmax returns its other operand)
+TRI_HD double fast_sqrt_clamped(double x) {
+#if defined(__CUDA_ARCH__)
+    return fmax(x * fast_rsqrt(x), 0.0);
+#else
+    return x > 0.0 ? sqrt(x) : 0.0;
+#endif
+}
+
+// high 32 bits of a double (sign, exponent, 20 mantissa bits): ordered like the value for
+// non-negative doubles
+TRI_HD unsigned hi_word(double x) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned)__double2hiint(x);
+#else
+    union { double d; unsigned long long u; } cv;
+    cv.d = x;
+    return (unsigned)(cv.u >> 32);
+#endif
+}
+
 // ---- polynomial tables in constant memory ------------------------------------------------------
 // Literal double constants cost two uniform-register moves each on sm_100a; adjacent entries of
 // a __constant__ table are fetched two at a time (LDCU.128).  The hot loop evaluates ~50
@@ -365,14 +387,15 @@ struct StampOrbit {
     double ma_c;     // mean anomaly at the stamp centre, reduced to [0, 2 pi)
     double ta_b;     // true anomaly of the base point
     double S_b, C_b; // sin(w + ta_b), cos(w + ta_b)
-    bool upper;      // the exposure lies in [pi, 2 pi): the table is read mirrored
+    double sgn, xoff; // table argument x = xoff + sgn * M: (0, +1) on [0, pi), (2 pi, -1) on
+                      // [pi, 2 pi) where the table is read mirrored; f = M + sgn * (f - M)(x)
 };
 
 // z from sin(w+f), cos(w+f)
 template <class OrbitT>
 TRI_HD double z_from_sc(const OrbitT& o, double S, double C) {
     double den = fma(o.ecw, C, fma(o.esw, S, 1.0));          // 1 + e cos f
-    double z = o.a1me2 * fast_rcp(den) * fast_sqrt(1.0 - S * S * o.sini2);
+    double z = o.a1me2 * fast_rcp(den) * fast_sqrt_clamped(1.0 - S * S * o.sini2);
     return S < 0.0 ? -z : z;
 }
 
@@ -391,9 +414,11 @@ TRI_HD double stamp_centre(const OrbitT& o, const OrbitTable& T, double t, doubl
     so.ta_b = ta;
     so.S_b = sw * ct + cw * st;
     so.C_b = cw * ct - sw * st;
-    so.upper = ma >= kPi;
+    const bool upper = ma >= kPi;
+    so.sgn = upper ? -1.0 : 1.0;
+    so.xoff = upper ? kTwoPi : 0.0;
     const double lo = ma - half_ma, hi = ma + half_ma;
-    fast = so.upper ? (lo > kPi && hi < kTwoPi) : (lo > 0.0 && hi < kPi);
+    fast = upper ? (lo > kPi && hi < kTwoPi) : (lo > 0.0 && hi < kPi);
     return z_from_sc(o, so.S_b, so.C_b);
 }
 
@@ -402,9 +427,12 @@ TRI_HD double stamp_centre(const OrbitT& o, const OrbitTable& T, double t, doubl
 template <class OrbitT>
 TRI_HD double z_sub(const OrbitT& o, const OrbitTable& T, StampOrbit& so, double toff) {
     const double ma = fma(toff, o.n_rate, so.ma_c);
-    const double x = so.upper ? kTwoPi - ma : ma;
+    // 0 < x < pi strictly (stamp_centre's check), so the cell index is at most kTableNm - 2
+    // except when x inv_dm rounds up to kTableNm - 1 exactly: the weight of the next cell is
+    // then 0 and the table carries one padding element behind its last row
+    const double x = fma(so.sgn, ma, so.xoff);
     const double u = x * T.inv_dm;
-    const double fl = fmin(floor(u), (double)(kTableNm - 2));
+    const double fl = floor(u);
     const double am = u - fl;
     const int im = (int)fl;
     const double* r0 = o.row0;
@@ -419,7 +447,7 @@ TRI_HD double z_sub(const OrbitT& o, const OrbitTable& T, StampOrbit& so, double
     const double c0 = fma(ae, t10 - t00, t00);
     const double c1 = fma(ae, t11 - t01, t01);
     const double d = fma(am, c1 - c0, c0);
-    const double ta = so.upper ? ma - d : ma + d;
+    const double ta = fma(so.sgn, d, ma);
     const double dl = ta - so.ta_b;
     double S, C;
     if (fabs(dl) > kStampMaxDelta) {   // rare: move the base point here
@@ -460,27 +488,33 @@ TRI_HD void ellke_m1(double m1, double& Kk, double& Ek) {
 
 // Bulirsch (1965) third-kind integral, started from kc = sqrt(1 - q^2), p = sqrt(n + 1) and
 // d = 1/p (the callers have closed forms for p and d, see occult_quad).  One reciprocal per
-// sweep instead of two divisions, and the oracle's convergence test |1 - kc/g| > 1e-8 written
-// without its division; the sweep count can only differ from the oracle's when the test is
-// within rounding of its threshold, where one more (quadratically convergent) sweep changes the
-// value below 1e-16.  NaN inputs fall through the test and return NaN, as in the oracle.
+// sweep instead of two divisions.  NaN inputs return NaN, as in the oracle (a NaN's high word
+// is above every threshold: one sweep).
 TRI_HD double ellpicb(double kc, double p, double d) {
+    // Sweeps until the oracle's test |1 - kc/g| <= 1e-8 holds: a function of the starting kc
+    // alone (the (m0, kc) pair is the AGM of (1, kc), scaled), so it is read off the high word
+    // of kc instead of being tested in every sweep (thresholds rounded up by one unit of the
+    // high word: a sweep too many changes the value by < 7e-16 relative, a sweep too few
+    // cannot happen).  kc < 2^-86 can only be kc == 0, where the oracle's loop never converges
+    // and returns 0 after its cap.
+    const unsigned h = hi_word(kc);
+    if (h < 0x3a900000u) return 0.0;
+    int it = 1 + (h < 0x3ff00000u) + (h < 0x3feffdafu) + (h < 0x3fee836eu) + (h < 0x3fe12ee9u)
+           + (h < 0x3fb5b7c9u) + (h < 0x3f5d95f7u) + (h < 0x3eab5a91u) + (h < 0x3d4761d4u);
     double e = kc;
     double m0 = 1.0, c = 1.0;
-    const double tol = 1e-8;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int it = 64; it > 0; --it) {   // (quadratic convergence: 2-6 sweeps; the bound never binds)
+    for (;;) {
         double ip = fast_rcp(p);
         double f = c;
         c = fma(d, ip, c);
         double g = e * ip;
         d = 2.0 * fma(f, g, d);
         p = g + p;
-        g = m0;
         m0 = kc + m0;
-        if (!(fabs(g - kc) > tol * g)) break;   // converged (or NaN)
+        if (--it == 0) break;
         kc = 2.0 * fast_sqrt_pos(e);
         e = kc * m0;
     }

@@ -32,11 +32,11 @@ def seed(value):
 
 
 def _device():
+    """The torch device of the engine's GPU (tests inject an engine whose `torch_device` says
+    otherwise; the CUDA engine has no such attribute)."""
     eng = _dispatch.get_engine()
-    d = getattr(eng, "device", 0)
-    if d is None or d < 0 or not torch.cuda.is_available():
-        return torch.device("cpu")       # oracle stand-in (tests)
-    return torch.device("cuda", d)
+    forced = getattr(eng, "torch_device", None)
+    return forced if forced is not None else torch.device("cuda", eng.device)
 
 
 def _begin(time, flux, sigma, exptime, nsamples, N):
@@ -45,16 +45,22 @@ def _begin(time, flux, sigma, exptime, nsamples, N):
     _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)   # applied with the submission
     dev = _device()
     lo, hi = _dispatch.shard_bounds(N)
+    d = _dispatch._dist()
+    if _state["seed"] is None and d is not None:
+        # unseeded run under a process group: torch's generators start from the same state in
+        # every process, so the ranks would all draw the SAME N/G samples.  One base seed is
+        # agreed on (rank 0's entropy) and every rank derives its own stream from it below.
+        box = [int(torch.seed()) % (2 ** 62)]
+        d.broadcast_object_list(box, src=0)
+        _state["seed"], _state["auto_seed"] = box[0], True
     if _state["seed"] is not None:
-        rank = 0
-        d = _dispatch._dist()
-        if d is not None:
-            rank = d.get_rank()
+        rank = d.get_rank() if d is not None else 0
         s = (int(_state["seed"]) * 1000003 + _state["calls"] * 7919 + rank) % (2 ** 63 - 1)
         torch.manual_seed(s)
         if dev.type == "cuda":
             torch.cuda.manual_seed(s)
     _state["calls"] += 1
+    _state["bounds"], _state["N_total"] = (lo, hi), int(N)
     return eng, dev, hi - lo
 
 
@@ -93,7 +99,13 @@ def _companion_q(n, M_s, molusc_file, dev):
     e = df["eccentricity"].values
     q = np.array(df[sma * (1 - e) > 10]["mass ratio"].values, dtype=float)
     q[q < 0.1 / M_s] = 0.1 / M_s
-    return dp._t(np.pad(q, (0, n - len(q)))[:n], dev)
+    # the table is padded to the TOTAL draw count and this rank takes its slice of it, as the
+    # host sampler does (marginal_likelihoods._companion_q): rows are neither dropped nor
+    # counted once per rank
+    lo, hi = _state["bounds"]
+    N = _state["N_total"]
+    q = q[:N]
+    return dp._t(np.pad(q, (0, N - len(q)))[lo:hi], dev)
 
 
 def _fluxratio(masses, M_s, filt="TESS"):
@@ -181,9 +193,8 @@ _KEYS = ('M_s', 'R_s', 'u1', 'u2', 'P_orb', 'inc', 'b', 'R_p', 'ecc', 'argp', 'M
 
 def _table(lb, dev, twin, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cfr, rps=None,
            masses=None, radii=None, fluxratios=None):
-    """Result dictionary (reference marginal_likelihoods.py:155-171) from this rank's best local
-    draws, merged across ranks."""
-    from .marginal_likelihoods import ScenarioResult
+    """This rank's half of a result dictionary (reference marginal_likelihoods.py:155-171): the
+    rows of its best local draws, registered for the merge across ranks (_finished)."""
     idx = torch.as_tensor(np.asarray(lb.idx, dtype=np.int64), device=dev)
     n = len(lb.idx)
     got = _take_rows(dict(M_host=M_host, R_host=R_host, u1=u1, u2=u2, P=P, mtot=mtot, inc=incs,
@@ -202,7 +213,12 @@ def _table(lb, dev, twin, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cf
         'fluxratio_EB': got.get("fluxratios", zeros),
         'fluxratio_comp': got["cfr"] if torch.is_tensor(cfr) else zeros,
     }
-    lnZ, n_pass, n_eval, merged = _dispatch.merge_tables(lb, local, _KEYS)
+    return _dispatch.TableExchange(lb, local, _KEYS)
+
+
+def _finished(exchange):
+    from .marginal_likelihoods import ScenarioResult
+    lnZ, n_pass, n_eval, merged = exchange.result()
     merged['lnZ'] = lnZ
     out = ScenarioResult(merged)
     out.n_pass, out.n_evaluated = n_pass, n_eval
@@ -216,11 +232,18 @@ def _run_tp(eng, dev, n, N, M_host, R_host, u1, u2, P, mtot, rps, incs, eccs, ar
                                rhost=R_host, u1=u1, u2=u2, cfr=cfr, lnprior=lnprior),
                           extra_mask, is_host, N_SAMPLES)
 
+    state = []
+
+    def prepare():
+        if not state:
+            lb = _dispatch.gather_local(p.result(), N, eng)
+            state.append(_table(lb, dev, False, M_host, R_host, u1, u2, P, mtot, incs, eccs,
+                                argps, cfr, rps=rps))
+
     def table():
-        lb = _dispatch.gather_local(p.result(), N, eng)
-        return _table(lb, dev, False, M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cfr,
-                      rps=rps)
-    return _dispatch.deliver(table)
+        prepare()
+        return _finished(state[0])
+    return _dispatch.deliver(table, prepare)
 
 
 def _run_eb(eng, dev, n, N, M_host, R_host, u1, u2, P, mtot, incs, qs, eccs, argps, masses, radii,
@@ -232,15 +255,21 @@ def _run_eb(eng, dev, n, N, M_host, R_host, u1, u2, P, mtot, incs, qs, eccs, arg
                           extra_mask, is_host, N_SAMPLES)
     common = (M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cfr)
     kw = dict(masses=masses, radii=radii, fluxratios=fluxratios)
-    both = []
+    state, done = [], {}
 
-    def tables():   # both branches at the first request, in a fixed order (collectives inside)
-        if not both:
+    def prepare():   # both branches at the first request, in a fixed order
+        if not state:
             r0, r1 = p.result()
-            both.append(_table(_dispatch.gather_local(r0, N, eng), dev, False, *common, **kw))
-            both.append(_table(_dispatch.gather_local(r1, N, eng), dev, True, *common, **kw))
-        return both
-    return _dispatch.deliver(lambda: tables()[0]), _dispatch.deliver(lambda: tables()[1])
+            state.append(_table(_dispatch.gather_local(r0, N, eng), dev, False, *common, **kw))
+            state.append(_table(_dispatch.gather_local(r1, N, eng), dev, True, *common, **kw))
+
+    def table(b):
+        prepare()
+        if not done:   # (collectives inside when no CallGroup is open: fixed order)
+            done[0], done[1] = _finished(state[0]), _finished(state[1])
+        return done[b]
+    return (_dispatch.deliver(lambda: table(0), prepare),
+            _dispatch.deliver(lambda: table(1), prepare))
 
 
 # ------------------------------------------------------------------------------- scenarios

@@ -251,7 +251,7 @@ def _run_tp(N, M_host, R_host, u1, u2, P, mtot, rps, incs, eccs, argps, cfr, lnp
                              lnprior=lnprior, extra_mask=extra_mask,
                              companion_is_host=companion_is_host)
     return _dispatch.deliver(lambda: _tp_result(pb.finish(), M_host, R_host, u1, u2, P, mtot,
-                                                incs, rps, eccs, argps, cfr))
+                                                incs, rps, eccs, argps, cfr), pb.prepare)
 
 
 def _run_eb(N, M_host, R_host, u1, u2, P, mtot, incs, qs, eccs, argps, masses, radii,
@@ -260,8 +260,8 @@ def _run_eb(N, M_host, R_host, u1, u2, P, mtot, incs, qs, eccs, argps, masses, r
                              u1, u2, cfr, lnprior=lnprior, extra_mask=extra_mask,
                              companion_is_host=companion_is_host)
     common = (M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, masses, radii, fluxratios, cfr)
-    return (_dispatch.deliver(lambda: _eb_result(pb.finish()[0], False, *common)),
-            _dispatch.deliver(lambda: _eb_result(pb.finish()[1], True, *common)))
+    return (_dispatch.deliver(lambda: _eb_result(pb.finish()[0], False, *common), pb.prepare),
+            _dispatch.deliver(lambda: _eb_result(pb.finish()[1], True, *common), pb.prepare))
 
 
 # ------------------------------------------------------------------- target-star scenarios

@@ -157,20 +157,36 @@ class target:
         # that the global generator is still consumed in the reference's order
         # (_dispatch.ScenarioChain).
         waiting = collections.deque()      # (rows, pending scenario call)
+        held = []                          # (rows, results) waiting for the group's exchange
         from . import marginal_likelihoods as _ml
-        threads = _dispatch.scenario_threads() if _ml._sampler_mode() == "host" else 1
-        _dispatch.get_engine()     # created here, not by whichever scenario thread comes first
+        host_sampler = _ml._sampler_mode() == "host"
+        threads = _dispatch.scenario_threads() if host_sampler else 1
+        eng = _dispatch.get_engine()   # created here, not by whichever scenario thread comes first
         chain = _dispatch.ScenarioChain(threads)
+        # Under a process group (one process per GPU) the evidence records and best-draw
+        # candidates of ALL rows are exchanged with one all-gather at the end; with numpy's
+        # draws rank 0 alone runs the scenario functions and scatters every engine call's
+        # columns, the other ranks evaluate their slices (_dispatch.CallGroup).
+        group = _dispatch.open_group(scatter=host_sampler)
+
+        def fill(rows, parts):
+            for j, res in zip(rows, parts):
+                res = _dispatch.resolve(res)
+                for k in _RESULT_KEYS:
+                    best[k][j] = res[k][0]
+                lnZ[j] = res["lnZ"]
 
         def settle(keep):
             while len(waiting) > keep:
                 rows, call = waiting.popleft()
                 out = call.result()
-                for j, res in zip(rows, out if isinstance(out, tuple) else (out,)):
-                    res = _dispatch.resolve(res)
-                    for k in _RESULT_KEYS:
-                        best[k][j] = res[k][0]
-                    lnZ[j] = res["lnZ"]
+                parts = out if isinstance(out, tuple) else (out,)
+                if group is None:
+                    fill(rows, parts)
+                else:   # the local half now (frees the engine's slot), the rest after the exchange
+                    for res in parts:
+                        _dispatch.prepare(res)
+                    held.append((rows, parts))
 
         def launch(row, ID, num, names, fn):
             """Start one lnZ_* call (one or two table rows) and read older results."""
@@ -193,9 +209,11 @@ class target:
                                "the online query of the reference is out of scope")
         trilegal_fname = self.trilegal_fname
 
+        follower = group is not None and group.scatter and not group.is_root
+        ok = False
         try:
             with _dispatch.deferring():
-                for i, ID in enumerate(filtered["ID"].values):
+                for i, ID in enumerate(filtered["ID"].values if not follower else ()):
                     star = {c: filtered[c].values[i] for c in _STAR_COLUMNS}
                     flux, flux_err = renorm_flux(flux_0, flux_err_0, star["fluxratio"])
                     M_s, R_s, Teff, plx = star["mass"], star["rad"], star["Teff"], star["plx"]
@@ -256,8 +274,28 @@ class target:
                         launch(row + 1, ID, 1, ("NEB", "NEBx2P"),
                                functools.partial(lnZ_TEB, *lc, M_s, R_s, Teff, Z, *tail))
                 settle(0)
+                ok = True
         finally:
             chain.close()
+            try:
+                if group is not None and group.scatter and group.is_root:
+                    group.finish_root(error=not ok)
+            finally:
+                if not ok:
+                    _dispatch.close_group()
+        try:
+            if follower:
+                targets, star_num, scenarios, best, lnZ = group.follow(eng)
+            elif group is not None:
+                group.exchange()
+                for rows, parts in held:
+                    fill(rows, parts)
+                if group.scatter:
+                    group.publish((targets, star_num, scenarios, best, lnZ))
+        finally:
+            self.collectives = None if group is None else {
+                "record_exchanges": group.collectives, "scatters": group.scatters}
+            _dispatch.close_group()
 
         relative_probs, status = _normalize_probabilities(lnZ)
         if status == 'anomaly':
