@@ -68,6 +68,12 @@ typedef struct {
     tri_col rhost, u1, u2, cfr, lnprior;
     const uint8_t* extra_mask;
     int32_t companion_is_host;
+    int32_t scalar_loop;  /* 1: the semantics of the reference's parallel=False loops
+                           * (marginal_likelihoods.py:313-339, likelihoods.py:121-123, :137):
+                           * a draw whose period-P transit probability exceeds 1 is skipped in
+                           * BOTH branches, the primary radius ratio is scaled by 0.999 only when
+                           * |k - 1| < 1e-6, and the secondary uses 1/k.  0: the vectorised
+                           * branch (parallel=True).  TP-type scenarios do not differ. */
 } tri_eb_args;
 
 /* Output of one scenario branch.  lnZ = m + ln(s) - ln(N) (-inf if no finite entry, +inf if any

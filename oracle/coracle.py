@@ -43,9 +43,9 @@ def lib():
         L.tro_lnl_tp.argtypes = ([ctypes.c_int64, _D, _D, ctypes.c_double, ctypes.c_double,
                                   ctypes.c_int, ctypes.c_int64] + [_D] * 10
                                  + [ctypes.c_int, _D, _I64])
-        L.tro_lnl_eb.argtypes = ([ctypes.c_int64, _D, _D, ctypes.c_double, ctypes.c_double,
-                                  ctypes.c_int, ctypes.c_int64] + [_D] * 11
-                                 + [ctypes.c_int, ctypes.c_int, _D, _D, _I64])
+        L.tro_lnl_eb_rule.argtypes = ([ctypes.c_int64, _D, _D, ctypes.c_double, ctypes.c_double,
+                                       ctypes.c_int, ctypes.c_int64] + [_D] * 11
+                                      + [ctypes.c_int, ctypes.c_int, ctypes.c_int, _D, _D, _I64])
         _lib = L
     return _lib
 
@@ -96,7 +96,8 @@ def lnL_TP_p(time, flux, sigma, R_p, P_orb, inc, a, R_s, u1, u2, ecc, argp,
 
 
 def _lnl_eb(twin, time, flux, sigma, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp,
-            companion_fluxratio, companion_is_host, exptime, nsamples, counts, secdepth):
+            companion_fluxratio, companion_is_host, exptime, nsamples, counts, secdepth,
+            scalar_rule=False):
     time, flux = _arr(time), _arr(flux)
     n = np.size(R_EB)
     A = [_arr(x, n) for x in (R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp,
@@ -104,28 +105,29 @@ def _lnl_eb(twin, time, flux, sigma, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1,
     out = np.empty(n)
     cp = counts.ctypes.data_as(_I64) if counts is not None else None
     sp = _p(secdepth) if secdepth is not None else None
-    lib().tro_lnl_eb(time.size, _p(time), _p(flux), float(sigma), float(exptime), int(nsamples),
-                     n, *[_p(x) for x in A], int(bool(companion_is_host)), int(twin), _p(out),
-                     sp, cp)
+    lib().tro_lnl_eb_rule(time.size, _p(time), _p(flux), float(sigma), float(exptime),
+                          int(nsamples), n, *[_p(x) for x in A], int(bool(companion_is_host)),
+                          int(twin), int(bool(scalar_rule)), _p(out), sp, cp)
     return out
 
 
 def lnL_EB_p(time, flux, sigma, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp,
              companion_fluxratio, companion_is_host=False, exptime=0.00139, nsamples=20,
-             counts=None, secdepth=None):
-    """Reference lnL_EB_p (likelihoods.py:490): +0.5 chi^2, +inf where secdepth >= 1.5 sigma."""
+             counts=None, secdepth=None, scalar_rule=False):
+    """Reference lnL_EB_p (likelihoods.py:490): +0.5 chi^2, +inf where secdepth >= 1.5 sigma.
+    scalar_rule: the radius-ratio rules of the scalar lnL_EB (likelihoods.py:121-123, :137)."""
     return _lnl_eb(0, time, flux, sigma, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc,
                    argp, companion_fluxratio, companion_is_host, exptime, nsamples, counts,
-                   secdepth)
+                   secdepth, scalar_rule)
 
 
 def lnL_EB_twin_p(time, flux, sigma, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc, argp,
                   companion_fluxratio, companion_is_host=False, exptime=0.00139, nsamples=20,
-                  counts=None, secdepth=None):
+                  counts=None, secdepth=None, scalar_rule=False):
     """Reference lnL_EB_twin_p (likelihoods.py:542)."""
     return _lnl_eb(1, time, flux, sigma, R_EB, EB_fluxratio, P_orb, inc, a, R_s, u1, u2, ecc,
                    argp, companion_fluxratio, companion_is_host, exptime, nsamples, counts,
-                   secdepth)
+                   secdepth, scalar_rule)
 
 
 def log_mean_exp(logw):

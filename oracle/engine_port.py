@@ -70,9 +70,11 @@ def tp_mask(N, rp, P_orb, inc, ecc, argp, mtot, rhost, extra_mask=None):
     return mask, a
 
 
-def eb_masks(N, reb, q, P_orb, inc, ecc, argp, mtot, rhost, extra_mask=None):
+def eb_masks(N, reb, q, P_orb, inc, ecc, argp, mtot, rhost, extra_mask=None, scalar_loop=False):
     """Masks and semi-major axes of the EB (q < 0.95, period P) and EBx2P (q >= 0.95, period
-    2P) branches (marginal_likelihoods.py:254-299): ((mask, a), (mask_twin, a_twin))."""
+    2P) branches (marginal_likelihoods.py:254-299): ((mask, a), (mask_twin, a_twin)).
+    scalar_loop: the reference's parallel=False loop (:313-339) `continue`s past BOTH branches
+    of a draw whose period-P transit probability exceeds 1."""
     reb, q, P, inc, ecc, argp, mtot, rhost = [
         _full(x, N) for x in (reb, q, P_orb, inc, ecc, argp, mtot, rhost)]
     e_corr = (1 + ecc * np.sin(argp * pi / 180)) / (1 - ecc ** 2)
@@ -91,6 +93,10 @@ def eb_masks(N, reb, q, P_orb, inc, ecc, argp, mtot, rhost, extra_mask=None):
         mask = (inc >= inc_min) & (coll == False) & ((q >= 0.95) if twin else (q < 0.95))  # noqa: E712
         if extra_mask is not None:
             mask &= np.asarray(extra_mask, bool)
+        if twin and scalar_loop:
+            mask &= Ptra_P <= 1.
+        if not twin:
+            Ptra_P = Ptra
         out.append((mask, a))
     return tuple(out)
 
@@ -126,12 +132,12 @@ class OracleEngine:
 
     def eval_eb(self, N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr,
                 lnprior=None, extra_mask=None, companion_is_host=False, want_lnL=True,
-                want_mask=False, n_best=0):
+                want_mask=False, n_best=0, scalar_loop=False):
         t, f, s, exptime, ns = self.lc
         reb, ebfr, q, P, inc, ecc, argp, mtot, rhost, u1, u2, cfr = [
             _full(x, N) for x in (reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr)]
         out = []
-        masks = eb_masks(N, reb, q, P, inc, ecc, argp, mtot, rhost, extra_mask)
+        masks = eb_masks(N, reb, q, P, inc, ecc, argp, mtot, rhost, extra_mask, scalar_loop)
         for twin in (False, True):
             Pk = 2 * P if twin else P
             mask, a = masks[int(twin)]
@@ -141,7 +147,7 @@ class OracleEngine:
                 lnL[mask] = -0.5 * ln2pi - np.log(s) - fn(
                     t, f, s, reb[mask], ebfr[mask], Pk[mask], inc[mask], a[mask], rhost[mask],
                     u1[mask], u2[mask], ecc[mask], argp[mask], cfr[mask], companion_is_host,
-                    exptime, ns)
+                    exptime, ns, scalar_rule=scalar_loop)
             res = _Res()
             res.N, res.lnL, res.mask, res.n_pass, res.n_stamps = N, lnL, mask, int(mask.sum()), 0
             out.append(_lse_record(lnL if lnprior is None else lnL + _full(lnprior, N), N, res))
@@ -171,10 +177,11 @@ class OracleEngine:
                            companion_is_host=companion_is_host, **c)
         return self._with_top(res, n_best)
 
-    def eval_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
+    def eval_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100,
+                        scalar_loop=False):
         c = {k: self._np(v) for k, v in cols.items()}
         r0, r1 = self.eval_eb(N, extra_mask=self._np(extra_mask),
-                              companion_is_host=companion_is_host, **c)
+                              companion_is_host=companion_is_host, scalar_loop=scalar_loop, **c)
         return self._with_top(r0, n_best), self._with_top(r1, n_best)
 
     # ---- simulate seam (likelihoods.py:302-439 and the scalar :27-160), via the C model ----

@@ -15,6 +15,9 @@ Fixtures (all seeds via np.random.seed, as the reference uses numpy's global RNG
                     reference, never called by it: marginal_likelihoods.py:2365-3178)
   simulate.npz      simulate_TP/EB_transit_p and the scalar simulate_TP/EB_transit (likelihoods.py)
   calc_probs.npz    target.calc_probs (triceratops.py:673-1485) on the 18-row configuration
+  lnz_scalar.npz    the ten lnZ_* functions through the reference's parallel=False loops (its
+                    default, triceratops.py:676) on draws that exercise what differs from the
+                    vectorised branch: near-contact binaries and equal radii
   model.npz         eval_quad / separation values of the restated model itself
 PARITY UNPINNED with respect to real pytransit (see oracle/quadmodel.py).
 """
@@ -144,6 +147,51 @@ def gen_kepler(ref, tri):
     np.savez_compressed(os.path.join(GOLD, "lnz_kepler10b.npz"), **out)
 
 
+N_SCALAR = 400
+
+
+def scalar_calls(star, N, tri, cc, lc):
+    """The calls of lnz_calls with parallel=False (positional argument 10 of `tail`)."""
+    t, f, s = lc
+    base = (t, f, s, star["P"], star["M"], star["R"], star["Teff"])
+    tail = (N, False, "TESS", False, 0.00139, 20)
+    mags = (star.get("T"), star.get("J"), star.get("H"), star.get("K"))
+    return {
+        "TTP": lambda m: m.lnZ_TTP(*base, 0.0, *tail),
+        "TEB": lambda m: m.lnZ_TEB(*base, 0.0, *tail),
+        "PTP": lambda m: m.lnZ_PTP(*base, 0.0, star["plx"], None, "TESS", *tail, None),
+        "PEBcc": lambda m: m.lnZ_PEB(*base, 0.0, star["plx"], cc, "K", *tail, None),
+        "STPcc": lambda m: m.lnZ_STP(*base, 0.0, star["plx"], cc, "K", *tail, None),
+        "SEB": lambda m: m.lnZ_SEB(*base, 0.0, star["plx"], None, "TESS", *tail, None),
+        "DTP": lambda m: m.lnZ_DTP(*base, 0.0, *mags, tri, None, "TESS", *tail),
+        "DEBcc": lambda m: m.lnZ_DEB(*base, 0.0, *mags, tri, cc, "J", *tail),
+        "BTPcc": lambda m: m.lnZ_BTP(*base, *mags, tri, cc, "H", *tail),
+        "BEB": lambda m: m.lnZ_BEB(*base, *mags, tri, None, "TESS", *tail),
+    }
+
+
+def gen_scalar(ref, tri):
+    """parallel=False: the reference's per-draw Python loops (marginal_likelihoods.py:139-150,
+    :313-339, ...) over the scalar lnL_TP / lnL_EB / lnL_EB_twin (likelihoods.py:163-299).  A
+    short-period star (P = 0.45 d around a 0.35 M_sun, 0.36 R_sun dwarf) makes the period-P
+    transit probability exceed 1 for part of the draws, which is where the scalar loop's
+    `continue` differs from the vectorised mask; TOI-465 covers the ordinary case."""
+    cc = os.path.join(GOLD, "TOI465_01_contrastcurve.csv")
+    lc = load_lc("TOI465_01_lightcurve.csv")
+    out = {"N": np.array(N_SCALAR), "seed": np.array(SEED)}
+    tight = dict(P=0.45, M=0.35, R=0.36, Teff=3400.0, plx=20.0, T=12.0, J=10.5, H=9.9, K=9.7)
+    for tag, star in (("toi465", TOI465), ("tight", tight)):
+        for name, fn in scalar_calls(star, N_SCALAR, tri, cc, lc).items():
+            np.random.seed(SEED)
+            flatten("%s/%s" % (tag, name), fn(ref.ml), out)
+            print("  lnZ scalar", tag, name,
+                  [float(out[k]) for k in out if k.startswith("%s/%s/" % (tag, name))
+                   and k.endswith("lnZ")])
+    for k, v in tight.items():
+        out["tight_star/" + k] = np.array(v)
+    np.savez_compressed(os.path.join(GOLD, "lnz_scalar.npz"), **out)
+
+
 def flatten(prefix, res, out):
     rs = res if isinstance(res, tuple) else (res,)
     for b, r in enumerate(rs):
@@ -184,9 +232,13 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "kepler":
         gen_kepler(ref, tri)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "scalar":
+        gen_scalar(ref, tri)
+        return
     synth.trilegal_table(tri, n=2500)
     gen_nearby(ref, tri)
     gen_simulate(ref)
+    gen_scalar(ref, tri)
     cc = os.path.join(GOLD, "TOI465_01_contrastcurve.csv")
 
     # ---- samplers / priors / relations ------------------------------------------------------

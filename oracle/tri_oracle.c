@@ -292,7 +292,17 @@ void tro_lnl_tp(int64_t npts, const double* time, const double* flux, double sig
 }
 
 /* lnL_EB_p (twin=0, +inf where secdepth >= 1.5 sigma) / lnL_EB_twin_p (twin=1).
- * secdepth_out (may be NULL) receives the per-sample secondary depth. */
+ * secdepth_out (may be NULL) receives the per-sample secondary depth.
+ * tro_lnl_eb_rule with scalar_rule = 1 is the scalar lnL_EB / lnL_EB_twin of the reference's
+ * parallel=False loops: |k - 1| < 1e-6 and secondary k = 1/k (likelihoods.py:121-123, :137). */
+void tro_lnl_eb_rule(int64_t npts, const double* time, const double* flux, double sigma,
+                     double exptime, int nsamples, int64_t n, const double* R_EB,
+                     const double* EB_fluxratio, const double* P_orb, const double* inc_deg,
+                     const double* a_cm, const double* R_s, const double* u1, const double* u2,
+                     const double* ecc, const double* argp_deg, const double* cfr,
+                     int companion_is_host, int twin, int scalar_rule, double* out,
+                     double* secdepth_out, int64_t* counts);
+
 void tro_lnl_eb(int64_t npts, const double* time, const double* flux, double sigma,
                 double exptime, int nsamples, int64_t n, const double* R_EB,
                 const double* EB_fluxratio, const double* P_orb, const double* inc_deg,
@@ -300,6 +310,18 @@ void tro_lnl_eb(int64_t npts, const double* time, const double* flux, double sig
                 const double* ecc, const double* argp_deg, const double* cfr,
                 int companion_is_host, int twin, double* out, double* secdepth_out,
                 int64_t* counts) {
+    tro_lnl_eb_rule(npts, time, flux, sigma, exptime, nsamples, n, R_EB, EB_fluxratio, P_orb,
+                    inc_deg, a_cm, R_s, u1, u2, ecc, argp_deg, cfr, companion_is_host, twin, 0,
+                    out, secdepth_out, counts);
+}
+
+void tro_lnl_eb_rule(int64_t npts, const double* time, const double* flux, double sigma,
+                double exptime, int nsamples, int64_t n, const double* R_EB,
+                const double* EB_fluxratio, const double* P_orb, const double* inc_deg,
+                const double* a_cm, const double* R_s, const double* u1, const double* u2,
+                const double* ecc, const double* argp_deg, const double* cfr,
+                int companion_is_host, int twin, int scalar_rule, double* out,
+                double* secdepth_out, int64_t* counts) {
     tro_make_table(0, 0, 0);
     double tsec[25];
     linspace(-0.05, 0.05, 25, tsec);
@@ -311,14 +333,15 @@ void tro_lnl_eb(int64_t npts, const double* time, const double* flux, double sig
         double F_comp = cfr[i] / (1 - cfr[i]);
         double F_EB = EB_fluxratio[i] / (1 - EB_fluxratio[i]);
         double k = R_EB[i] / R_s[i];
-        if ((k - 1.0) < 1e-6) k *= 0.999;
+        if (scalar_rule ? (fabs(k - 1.0) < 1e-6) : ((k - 1.0) < 1e-6)) k *= 0.999;
         double a = a_cm[i] / (R_s[i] * C_RSUN);
         double inc = inc_deg[i] * (PI / 180.);
         double w = (90 - argp_deg[i]) * (PI / 180.);
         double off = mean_anomaly_offset(ecc[i], w);
         /* secondary eclipse: roles swapped, 25 points, no supersampling */
         double ks = R_s[i] / R_EB[i];
-        if ((ks - 1.0) < 1e-6) ks *= 0.999;
+        if (scalar_rule) ks = 1 / k;
+        else if ((ks - 1.0) < 1e-6) ks *= 0.999;
         double ws = (90 - argp_deg[i] + 180) * (PI / 180.);
         double offs = mean_anomaly_offset(ecc[i], ws);
         double sec = INFINITY;

@@ -102,6 +102,47 @@ def lnz_calls(star, N, tri, cc, lc, mission="TESS", exptime=0.00139):
     return calls
 
 
+def scalar_calls(star, N, tri, cc, lc, parallel=False):
+    """The calls of oracle/gen_golden.py's lnz_scalar.npz (the reference's parallel=False
+    loops); parallel=True gives the vectorised semantics on the same draws."""
+    t, f, s = lc
+    base = (t, f, s, star["P"], star["M"], star["R"], star["Teff"])
+    tail = (N, parallel, "TESS", False, 0.00139, 20)
+    mags = (star.get("T"), star.get("J"), star.get("H"), star.get("K"))
+    return {
+        "TTP": lambda m: m.lnZ_TTP(*base, 0.0, *tail),
+        "TEB": lambda m: m.lnZ_TEB(*base, 0.0, *tail),
+        "PTP": lambda m: m.lnZ_PTP(*base, 0.0, star["plx"], None, "TESS", *tail, None),
+        "PEBcc": lambda m: m.lnZ_PEB(*base, 0.0, star["plx"], cc, "K", *tail, None),
+        "STPcc": lambda m: m.lnZ_STP(*base, 0.0, star["plx"], cc, "K", *tail, None),
+        "SEB": lambda m: m.lnZ_SEB(*base, 0.0, star["plx"], None, "TESS", *tail, None),
+        "DTP": lambda m: m.lnZ_DTP(*base, 0.0, *mags, tri, None, "TESS", *tail),
+        "DEBcc": lambda m: m.lnZ_DEB(*base, 0.0, *mags, tri, cc, "J", *tail),
+        "BTPcc": lambda m: m.lnZ_BTP(*base, *mags, tri, cc, "H", *tail),
+        "BEB": lambda m: m.lnZ_BEB(*base, *mags, tri, None, "TESS", *tail),
+    }
+
+
+SCALAR_NAMES = ["TTP", "TEB", "PTP", "PEBcc", "STPcc", "SEB", "DTP", "DEBcc", "BTPcc", "BEB"]
+
+
+def scalar_star(gold, tag):
+    if tag == "toi465":
+        return TOI465
+    return {k: float(gold["tight_star/" + k]) for k in ("P", "M", "R", "Teff", "plx", "T", "J",
+                                                        "H", "K")}
+
+
+class _Prefixed:
+    """View of a fixture under a key prefix (lnz_scalar.npz holds two stars)."""
+
+    def __init__(self, gold, prefix):
+        self.gold, self.prefix = gold, prefix
+
+    def __getitem__(self, key):
+        return self.gold[self.prefix + key]
+
+
 def nearby_calls(N, tri, lc):
     """The unknown / evolved nearby-star calls of oracle/gen_golden.py."""
     t, f, s = lc

@@ -5,7 +5,8 @@ draws (masks bit-exact, per-draw lnL to 1e-9)."""
 import numpy as np
 import pytest
 
-from conftest import KEP10, TOI465, check_against_golden, lnz_calls, nearby_calls
+from conftest import (KEP10, SCALAR_NAMES, TOI465, _Prefixed, check_against_golden, lnz_calls,
+                      nearby_calls, scalar_calls, scalar_star)
 
 import triceratops_b200.marginal_likelihoods as ml
 
@@ -32,6 +33,20 @@ def test_kepler_long_cadence(name, gpu_engine, golden, kepler10b_lc, trilegal_fi
                       mission="Kepler", exptime=0.0204)
     np.random.seed(int(g["seed"]))
     check_against_golden(name, calls[name](ml), g, lnz_atol=1e-6, arr_rtol=1e-9)
+
+
+@pytest.mark.parametrize("tag", ["toi465", "tight"])
+@pytest.mark.parametrize("name", SCALAR_NAMES)
+def test_parallel_false_matches_reference_scalar_loops(name, tag, gpu_engine, golden, toi465_lc,
+                                                       trilegal_file, contrast_file):
+    """parallel=False, the reference's default (triceratops.py:676): its per-draw loops over the
+    scalar likelihoods, reproduced by the engine's scalar_loop flag."""
+    g = golden("lnz_scalar.npz")
+    star = scalar_star(g, tag)
+    calls = scalar_calls(star, int(g["N"]), trilegal_file, contrast_file, toi465_lc)
+    np.random.seed(int(g["seed"]))
+    check_against_golden(name, calls[name](ml), _Prefixed(g, tag + "/"), lnz_atol=1e-6,
+                         arr_rtol=1e-9)
 
 
 def test_calc_probs_matches_reference_fixture(gpu_engine, golden, toi465_lc, trilegal_file,

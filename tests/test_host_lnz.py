@@ -5,7 +5,8 @@ isolates the host logic; the same comparisons run on the real engine in test_gpu
 import numpy as np
 import pytest
 
-from conftest import KEP10, TOI465, check_against_golden, lnz_calls, nearby_calls
+from conftest import (KEP10, SCALAR_NAMES, TOI465, _Prefixed, check_against_golden, lnz_calls,
+                      nearby_calls, scalar_calls, scalar_star)
 
 import triceratops_b200.marginal_likelihoods as ml
 
@@ -30,6 +31,33 @@ def test_kepler_long_cadence(name, oracle_engine, golden, kepler10b_lc, trilegal
                       mission="Kepler", exptime=0.0204)
     np.random.seed(int(g["seed"]))
     check_against_golden(name, calls[name](ml), g, lnz_atol=1e-9, arr_rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["toi465", "tight"])
+@pytest.mark.parametrize("name", SCALAR_NAMES)
+def test_parallel_false_reproduces_the_reference_scalar_loops(name, tag, oracle_engine, golden,
+                                                              toi465_lc, trilegal_file,
+                                                              contrast_file):
+    """parallel=False (the reference's default): per-draw loops over the scalar lnL_TP / lnL_EB /
+    lnL_EB_twin, marginal_likelihoods.py:139-150, :313-339, likelihoods.py:121-123, :137."""
+    g = golden("lnz_scalar.npz")
+    star = scalar_star(g, tag)
+    calls = scalar_calls(star, int(g["N"]), trilegal_file, contrast_file, toi465_lc)
+    np.random.seed(int(g["seed"]))
+    check_against_golden(name, calls[name](ml), _Prefixed(g, tag + "/"), lnz_atol=1e-9,
+                         arr_rtol=1e-12)
+
+
+def test_parallel_false_differs_from_parallel_true_where_the_reference_does(
+        oracle_engine, golden, toi465_lc, trilegal_file, contrast_file):
+    """The fixture is discriminating: on the tight binary the vectorised semantics give another
+    EBx2P evidence (draws whose period-P transit probability exceeds 1)."""
+    g = golden("lnz_scalar.npz")
+    star = scalar_star(g, "tight")
+    calls = scalar_calls(star, int(g["N"]), trilegal_file, contrast_file, toi465_lc, parallel=True)
+    np.random.seed(int(g["seed"]))
+    _, twin = calls["TEB"](ml)
+    assert abs(twin["lnZ"] - float(g["tight/TEB/1/lnZ"])) > 1e-3
 
 
 def test_period_range_is_sampled(oracle_engine, toi465_lc):

@@ -38,7 +38,8 @@ class tri_eb_args(ctypes.Structure):
     _fields_ = ([("N", ctypes.c_int64)]
                 + [(n, tri_col) for n in ("reb", "ebfr", "q", "P_orb", "inc", "ecc", "argp",
                                           "mtot", "rhost", "u1", "u2", "cfr", "lnprior")]
-                + [("extra_mask", ctypes.c_void_p), ("companion_is_host", ctypes.c_int32)])
+                + [("extra_mask", ctypes.c_void_p), ("companion_is_host", ctypes.c_int32),
+                   ("scalar_loop", ctypes.c_int32)])
 
 
 class tri_result(ctypes.Structure):

@@ -264,18 +264,18 @@ class CallGroup:
         cols.update({k: None for k in hdr["absent"]})
         mask = (mine[len(hdr["arrays"]), :n] != 0) if hdr["has_mask"] else None
         name = hdr["kind"] + "_tensors"
+        kw = dict(extra_mask=mask, companion_is_host=hdr["is_host"], n_best=N_BEST)
+        if hdr["scalar_loop"]:
+            kw["scalar_loop"] = True
         fn = getattr(eng, "submit_" + name, None)
         if fn is not None:
-            return fn(n, cols, extra_mask=mask, companion_is_host=hdr["is_host"],
-                      n_best=N_BEST, lightcurve=lc)
+            return fn(n, cols, lightcurve=lc, **kw)
         with _fallback_lock:     # stand-in engines (CPU tests): one call at a time
             if lc is not None:
                 eng.set_lightcurve(*lc)
-            return _Done(getattr(eng, "eval_" + name)(n, cols, extra_mask=mask,
-                                                      companion_is_host=hdr["is_host"],
-                                                      n_best=N_BEST))
+            return _Done(getattr(eng, "eval_" + name)(n, cols, **kw))
 
-    def scatter_submit(self, eng, kind, N, cols, extra_mask, is_host):
+    def scatter_submit(self, eng, kind, N, cols, extra_mask, is_host, scalar_loop=False):
         """Rank 0: announce one engine call, scatter its per-draw columns, evaluate the own
         slice.  Returns (pending, lo, hi, seq)."""
         import torch
@@ -296,7 +296,7 @@ class CallGroup:
             self.lc_key = key
             hdr = dict(op="call", seq=seq, kind=kind, N=N, arrays=arrays, scalars=scalars,
                        absent=absent, has_mask=extra_mask is not None, is_host=bool(is_host),
-                       bounds=bounds, chunk=chunk, ncol=ncol, lc=send_lc)
+                       scalar_loop=bool(scalar_loop), bounds=bounds, chunk=chunk, ncol=ncol, lc=send_lc)
             self._bcast(hdr)
             pin = self.device == "cuda"
             buf = torch.zeros((self.world, max(ncol, 1), chunk), dtype=torch.float64,
@@ -453,20 +453,21 @@ class PendingBranches:
         return self._out
 
 
-def _submit_sharded(kind, N, cols, extra_mask, companion_is_host):
+def _submit_sharded(kind, N, cols, extra_mask, companion_is_host, scalar_loop=False):
     eng = get_engine()
     g = _group
     if g is not None and g.scatter:
         # calc_probs under a process group, numpy draws: this is rank 0 (the others follow)
         pending, lo, hi, seq = g.scatter_submit(eng, kind, N, cols, extra_mask,
-                                                companion_is_host)
+                                                companion_is_host, scalar_loop)
         return PendingBranches(pending, lo, hi, N, eng, seq)
     lo, hi = shard_bounds(N)
     sl = {k: _slice(v, lo, hi) for k, v in cols.items()}
     lnprior = sl.pop("lnprior")
+    kw = {"scalar_loop": True} if scalar_loop else {}
     p = _submit(eng, kind, hi - lo, *sl.values(), lnprior=lnprior,
                 extra_mask=_mask_slice(extra_mask, lo, hi),
-                companion_is_host=companion_is_host, want_lnL=False, n_best=N_BEST)
+                companion_is_host=companion_is_host, want_lnL=False, n_best=N_BEST, **kw)
     return PendingBranches(p, lo, hi, N, eng)
 
 
@@ -478,10 +479,10 @@ def submit_tp(N, rp, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=No
 
 
 def submit_eb(N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr, lnprior=None,
-              extra_mask=None, companion_is_host=False):
+              extra_mask=None, companion_is_host=False, scalar_loop=False):
     cols = dict(reb=reb, ebfr=ebfr, q=q, P_orb=P_orb, inc=inc, ecc=ecc, argp=argp, mtot=mtot,
                 rhost=rhost, u1=u1, u2=u2, cfr=cfr, lnprior=lnprior)
-    return _submit_sharded("eb", N, cols, extra_mask, companion_is_host)
+    return _submit_sharded("eb", N, cols, extra_mask, companion_is_host, scalar_loop)
 
 
 def run_tp(*args, **kw):

@@ -389,6 +389,7 @@ int enqueue_eb(Slot& S, const tri_eb_args& a, const tri_result r[2], cudaStream_
     G.ecc = to_col(a.ecc); G.argp = to_col(a.argp); G.mtot = to_col(a.mtot);
     G.rhost = to_col(a.rhost);
     G.extra_mask = a.extra_mask;
+    G.scalar_loop = a.scalar_loop;
     G.a_out = W.a; G.p_out = W.p; G.lnl_out = W.lnl; G.lnl_twin_out = W.lnl_twin;
     G.mask_out = r[0].mask_out; G.mask_twin_out = r[1].mask_out;
     G.items = W.items; G.n_items = S.d_counters + 0;
@@ -408,6 +409,7 @@ int enqueue_eb(Slot& S, const tri_eb_args& a, const tri_result r[2], cudaStream_
     A.items = W.items; A.items_cap = N; A.count = 0; A.count_dev = S.d_counters + 0;
     A.next = S.d_counters + 2;
     A.out = W.lnl; A.out_twin = W.lnl_twin; A.counters = S.d_counters + 4;
+    A.scalar_rule = a.scalar_loop ? 1 : 0;
     A.lnprior = to_col(a.lnprior); A.lse_partials = W.partials; A.cval = W.cval;
     A.hist16 = S.d_hist16;
     rc = launch_lnl(S, A, s);

@@ -47,6 +47,7 @@ struct GeomEb {
     int64_t N;
     Col reb, q, P, inc, ecc, argp, mtot, rhost;
     const uint8_t* extra_mask;
+    int scalar_loop;    // parallel=False loop: Ptra(P) > 1 skips the twin branch too
     double* a_out;      // a (q < 0.95) or a_twin (q >= 0.95) of surviving draws
     double* p_out;      // P or 2P
     double* lnl_out;    // [N] EB branch, -inf default
@@ -156,6 +157,10 @@ __global__ void geometry_eb_kernel(GeomEb g) {
                 coll = (2.0 * rhost * kRsun) > a * (1.0 - ecc);
             }
             take = transits(inc, Ptra) && !coll;
+            // marginal_likelihoods.py:316-319: the scalar loop `continue`s before it reaches the
+            // twin branch when the period-P transit probability exceeds 1
+            if (twin && g.scalar_loop && !(rsum / semi_major_axis(mtot, P) * e_corr <= 1.0))
+                take = false;
             if (g.extra_mask) take = take && (g.extra_mask[i] != 0);
             g.lnl_out[i] = neg_inf();
             g.lnl_twin_out[i] = neg_inf();
@@ -267,17 +272,17 @@ __device__ __forceinline__ double warp_min(double v) {
 }
 
 // One warp per block: the per-draw record of the warp then sits at compile-time constant
-// shared-memory addresses.  24 resident blocks per SM = 80 registers per thread (A/B on B200,
-// ms per step of the headline workload: 128 threads x 6: 167.9, 128 x 8: 168.8, 32 x 24: 166.5,
-// 32 x 32: 165.6 -- the kernel is bound by the issue port, not by the number of warps, see
-// DESIGN.md).
+// shared-memory addresses.  32 resident blocks per SM = 64 registers per thread (A/B on B200,
+// ms per step of the headline workload: 128 threads x 6 blocks: 166.7, 32 x 24: 165.6,
+// 32 x 28: 163.8, 32 x 32: 163.8 -- the kernel is bound by the issue port, not by the number
+// of warps).
 #ifndef TRI_LNL_THREADS
 #define TRI_LNL_THREADS 32
 #endif
 constexpr int kLnlThreads = TRI_LNL_THREADS;
 constexpr int kLnlWarps = kLnlThreads / 32;
 #ifndef TRI_LNL_MIN_BLOCKS
-#define TRI_LNL_MIN_BLOCKS (768 / TRI_LNL_THREADS)
+#define TRI_LNL_MIN_BLOCKS (1024 / TRI_LNL_THREADS)
 #endif
 constexpr int kLnlMinBlocks = TRI_LNL_MIN_BLOCKS;
 

@@ -247,12 +247,13 @@ def _run_tp(eng, dev, n, N, M_host, R_host, u1, u2, P, mtot, rps, incs, eccs, ar
 
 
 def _run_eb(eng, dev, n, N, M_host, R_host, u1, u2, P, mtot, incs, qs, eccs, argps, masses, radii,
-            fluxratios, cfr, lnprior, extra_mask, is_host):
+            fluxratios, cfr, lnprior, extra_mask, is_host, scalar_loop=False):
+    kw = {"scalar_loop": True} if scalar_loop else {}
     p = _dispatch._submit(eng, "eb_tensors", n,
                           dict(reb=radii, ebfr=fluxratios, q=qs, P_orb=P, inc=incs, ecc=eccs,
                                argp=argps, mtot=mtot, rhost=R_host, u1=u1, u2=u2, cfr=cfr,
                                lnprior=lnprior),
-                          extra_mask, is_host, N_SAMPLES)
+                          extra_mask, is_host, N_SAMPLES, **kw)
     common = (M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, cfr)
     kw = dict(masses=masses, radii=radii, fluxratios=fluxratios)
     state, done = [], {}
@@ -293,7 +294,7 @@ def lnZ_TEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, N=1000000, parallel=Fal
     radii, _ = dp.stellar_relations(masses, R_s, Teff)
     fluxratios = _fluxratio(masses, M_s)
     return _run_eb(eng, dev, n, int(N), M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps,
-                   masses, radii, fluxratios, 0.0, None, None, False)
+                   masses, radii, fluxratios, 0.0, None, None, False, scalar_loop=not parallel)
 
 
 def lnZ_PTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_file=None,
@@ -338,7 +339,7 @@ def lnZ_PEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_fil
     lnprior = _bound_prior(dp.lnprior_bound_EB, M_s, plx, n, dev, molusc_file,
                            contrast_curve_file, cfr / (1 - cfr), cc_term)
     return _run_eb(eng, dev, n, int(N), M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps,
-                   masses, radii, fluxratios, cfr, lnprior, qs_comp != 0.0, False)
+                   masses, radii, fluxratios, cfr, lnprior, qs_comp != 0.0, False, scalar_loop=not parallel)
 
 
 def _companion_stars(n, M_s, R_s, Teff, Z, mission, qs_comp, Teff_cap):
@@ -393,7 +394,7 @@ def lnZ_SEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, plx, contrast_curve_fil
                            (cfr / (1 - cfr)) + (fluxratios / (1 - fluxratios)), cc_term)
     return _run_eb(eng, dev, n, int(N), masses_comp, radii_comp, u1s, u2s, P,
                    masses_comp + masses, incs, qs, eccs, argps, masses, radii, fluxratios, cfr,
-                   lnprior, qs_comp != 0.0, True)
+                   lnprior, qs_comp != 0.0, True, scalar_loop=not parallel)
 
 
 def _randint(lo, hi, n, dev):
@@ -432,7 +433,7 @@ def lnZ_DEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Z, Tmag, Jmag, Hmag, Kmag,
     lnprior = _background_prior(bg, n, dev, contrast_curve_file,
                                 2.5 * torch.log10(cfr / (1 - cfr)), bg.dmag(filt)[idxs])
     return _run_eb(eng, dev, n, int(N), M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps,
-                   masses, radii, fluxratios, cfr, lnprior, None, False)
+                   masses, radii, fluxratios, cfr, lnprior, None, False, scalar_loop=not parallel)
 
 
 def lnZ_BTP(time, flux, sigma, P_orb, M_s, R_s, Teff, Tmag, Jmag, Hmag, Kmag, trilegal_fname,
@@ -485,4 +486,4 @@ def lnZ_BEB(time, flux, sigma, P_orb, M_s, R_s, Teff, Tmag, Jmag, Hmag, Kmag, tr
     extra = (bg.loggs[idxs] >= 3.5) & (bg.Teffs[idxs] <= 10000)
     return _run_eb(eng, dev, n, int(N), host_masses, host_radii, u1c[idxs], u2c[idxs], P,
                    host_masses + masses, incs, qs, eccs, argps, masses, radii, fluxratios, cfr,
-                   lnprior, extra, True)
+                   lnprior, extra, True, scalar_loop=not parallel)

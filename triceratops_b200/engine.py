@@ -241,7 +241,9 @@ class Engine:
     @_locked
     def submit_eb(self, N, reb, ebfr, q, P_orb, inc, ecc, argp, mtot, rhost, u1, u2, cfr,
                   lnprior=None, extra_mask=None, companion_is_host=False, want_lnL=True,
-                  want_mask=False, n_best=0, lightcurve=None):
+                  want_mask=False, n_best=0, lightcurve=None, scalar_loop=False):
+        """EB-type counterpart of submit_tp.  scalar_loop=True evaluates with the semantics of
+        the reference's parallel=False loops (see tri_eb_args.scalar_loop)."""
         N = int(N)
         if lightcurve is not None:
             self.set_lightcurve(*lightcurve)
@@ -255,6 +257,7 @@ class Engine:
             setattr(a, name, self._col(val, N))
         a.extra_mask = self._mask(extra_mask, N)
         a.companion_is_host = int(bool(companion_is_host))
+        a.scalar_loop = int(bool(scalar_loop))
         rr = (tri_result * 2)()
         outs = []
         for b in range(2):
@@ -320,7 +323,7 @@ class Engine:
 
     @_locked
     def _submit_tensors(self, kind, N, cols, extra_mask, companion_is_host, n_best,
-                        lightcurve=None):
+                        lightcurve=None, scalar_loop=False):
         import torch
         N = int(N)
         if lightcurve is not None:
@@ -336,6 +339,8 @@ class Engine:
             keep.append(m)
             a.extra_mask = m.data_ptr()
         a.companion_is_host = int(bool(companion_is_host))
+        if kind == "eb":
+            a.scalar_loop = int(bool(scalar_loop))
         nb = 1 if kind == "tp" else 2
         rr = (tri_result * nb)()
         tops = []
@@ -374,9 +379,9 @@ class Engine:
                                     lightcurve)
 
     def submit_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100,
-                          lightcurve=None):
+                          lightcurve=None, scalar_loop=False):
         return self._submit_tensors("eb", N, cols, extra_mask, companion_is_host, n_best,
-                                    lightcurve)
+                                    lightcurve, scalar_loop)
 
     def eval_tp_tensors(self, *args, **kw):
         return self.submit_tp_tensors(*args, **kw).result()

@@ -13,10 +13,13 @@ Division of labour:
                     supersampled quadratic-limb-darkened light curve, secondary-eclipse cut,
                     chi^2, + companion prior, log-mean-exp.  Draws are sent UNMASKED.
 
-`parallel` is accepted for signature compatibility.  The engine always evaluates with the
-semantics of the reference's vectorised branch (parallel=True: lnL_TP_p / lnL_EB_p /
-lnL_EB_twin_p), which is the reference's production path; its scalar loop (parallel=False) is
-not numerically identical to it (likelihoods.py:121-123 vs :406) and is not reproduced.
+`parallel` selects the SEMANTICS, as in the reference, not the execution (always the GPU):
+parallel=True is the vectorised branch (lnL_TP_p / lnL_EB_p / lnL_EB_twin_p); parallel=False
+(the reference's default, triceratops.py:676) is its scalar loop, which differs for EB-type
+scenarios -- radius-ratio rules |k - 1| < 1e-6 and secondary 1/k (likelihoods.py:121-123, :137
+vs :406, :417-418), and a draw whose period-P transit probability exceeds 1 is skipped in both
+branches (marginal_likelihoods.py:316-319) -- and is reproduced by the engine's scalar_loop flag.
+TP-type scenarios give the same numbers either way.
 """
 import numpy as np
 from pandas import read_csv
@@ -255,10 +258,10 @@ def _run_tp(N, M_host, R_host, u1, u2, P, mtot, rps, incs, eccs, argps, cfr, lnp
 
 
 def _run_eb(N, M_host, R_host, u1, u2, P, mtot, incs, qs, eccs, argps, masses, radii,
-            fluxratios, cfr, lnprior, extra_mask, companion_is_host):
+            fluxratios, cfr, lnprior, extra_mask, companion_is_host, scalar_loop=False):
     pb = _dispatch.submit_eb(N, radii, fluxratios, qs, P, incs, eccs, argps, mtot, R_host,
                              u1, u2, cfr, lnprior=lnprior, extra_mask=extra_mask,
-                             companion_is_host=companion_is_host)
+                             companion_is_host=companion_is_host, scalar_loop=scalar_loop)
     common = (M_host, R_host, u1, u2, P, mtot, incs, eccs, argps, masses, radii, fluxratios, cfr)
     return (_dispatch.deliver(lambda: _eb_result(pb.finish()[0], False, *common), pb.prepare),
             _dispatch.deliver(lambda: _eb_result(pb.finish()[1], True, *common), pb.prepare))
@@ -310,7 +313,7 @@ def lnZ_TEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
     fluxratios = _fluxratio(masses, M_s)
     return _run_eb(N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses, radii,
-                   fluxratios, 0.0, None, None, False)
+                   fluxratios, 0.0, None, None, False, scalar_loop=not parallel)
 
 
 # ---------------------------------------------------------------- bound-companion scenarios
@@ -382,7 +385,7 @@ def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     lnprior = _bound_prior(lnprior_bound_EB, M_s, plx, N, molusc_file, contrast_curve_file,
                            fluxratios_comp / (1 - fluxratios_comp), cc_term)
     return _run_eb(N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses, radii,
-                   fluxratios, fluxratios_comp, lnprior, qs_comp != 0.0, False)
+                   fluxratios, fluxratios_comp, lnprior, qs_comp != 0.0, False, scalar_loop=not parallel)
 
 
 def _companion_stars(N, M_s, R_s, Teff, Z, mission, qs_comp, Teff_cap):
@@ -464,7 +467,7 @@ def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
                            + (fluxratios / (1 - fluxratios)), cc_term)
     return _run_eb(N, masses_comp, radii_comp, u1s, u2s, P, masses_comp + masses, incs, qs, eccs,
                    argps, masses, radii, fluxratios, fluxratios_comp, lnprior, qs_comp != 0.0,
-                   True)
+                   True, scalar_loop=not parallel)
 
 
 # --------------------------------------------------------------------- background scenarios
@@ -524,7 +527,7 @@ def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     lnprior = _background_prior(bg, N, contrast_curve_file,
                                 2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
     return _run_eb(N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses, radii,
-                   fluxratios, cfr, lnprior, None, False)
+                   fluxratios, cfr, lnprior, None, False, scalar_loop=not parallel)
 
 
 def lnZ_BTP(time: np.ndarray, flux: np.ndarray, sigma: float,
@@ -608,7 +611,7 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     extra = (bg.loggs[idxs] >= 3.5) & (bg.Teffs[idxs] <= 10000)
     return _run_eb(N, host_masses, host_radii, u1s_comp[idxs], u2s_comp[idxs], P,
                    host_masses + masses, incs, qs, eccs, argps, masses, radii, fluxratios, cfr,
-                   lnprior, extra, True)
+                   lnprior, extra, True, scalar_loop=not parallel)
 
 
 # ------------------------------------------------- nearby stars of unknown / evolved nature
@@ -683,7 +686,7 @@ def lnZ_NEB_unknown(time: np.ndarray, flux: np.ndarray, sigma: float,
     extra = (hosts.loggs[idxs] >= 3.5) & (hosts.Teffs[idxs] <= 10000)
     return _run_eb(N, host_masses, host_radii, hosts.u1s[idxs], hosts.u2s[idxs], P,
                    host_masses + masses, incs, qs, eccs, argps, masses, radii, fluxratios, 0.0,
-                   None, extra, False)
+                   None, extra, False, scalar_loop=not parallel)
 
 
 def _subgiant_mass(R_s):
@@ -728,6 +731,6 @@ def lnZ_NEB_evolved(time: np.ndarray, flux: np.ndarray, sigma: float,
     radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
     fluxratios = _fluxratio(masses, M_s)
     common = (N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses)
-    res, _ = _run_eb(*common, radii, fluxratios, 0.0, None, None, False)
-    _, res_twin = _run_eb(*common, np.full(N, float(R_s)), fluxratios, 0.0, None, None, False)
+    res, _ = _run_eb(*common, radii, fluxratios, 0.0, None, None, False, scalar_loop=not parallel)
+    _, res_twin = _run_eb(*common, np.full(N, float(R_s)), fluxratios, 0.0, None, None, False, scalar_loop=not parallel)
     return res, res_twin
