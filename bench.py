@@ -227,6 +227,11 @@ def run_ours(args):
     keep = []
     dev_calls, host_calls = [], []
     h2d_bytes = d2h_bytes = 0
+    # the engine-level leg keeps a second, page-locked copy of every column: skipped when that
+    # would pin more than 4 GB of host memory (N = 1e7)
+    col_bytes = sum(np.size(v) * 8 for c in calls for v in c["cols"].values()
+                    if v is not None and np.size(v) > 1)
+    engine_leg = col_bytes <= (4 << 30)
     for c in calls:
         struct = tri_tp_args if c["kind"] == "tp" else tri_eb_args
         da, ha = struct(), struct()
@@ -239,17 +244,22 @@ def run_ours(args):
             a = np.ascontiguousarray(np.asarray(val, dtype=np.float64).reshape(-1))
             stride = 0 if a.size == 1 and c["N"] != 1 else 1
             d = torch.from_numpy(a).cuda()
-            pt, pa = _pinned_like(torch, a)
-            keep += [d, pt]
+            keep.append(d)
             setattr(da, name, tri_col(d.data_ptr(), stride))
-            setattr(ha, name, tri_col(pa.ctypes.data, stride))
+            if engine_leg:
+                pt, pa = _pinned_like(torch, a)
+                keep.append(pt)
+                setattr(ha, name, tri_col(pa.ctypes.data, stride))
             h2d_bytes += a.nbytes
         if c["extra_mask"] is not None:
             m = np.ascontiguousarray(np.asarray(c["extra_mask"]).astype(np.uint8))
             d = torch.from_numpy(m).cuda()
-            pt, pa = _pinned_like(torch, m)
-            keep += [d, pt]
-            da.extra_mask, ha.extra_mask = d.data_ptr(), pa.ctypes.data
+            keep.append(d)
+            da.extra_mask = d.data_ptr()
+            if engine_leg:
+                pt, pa = _pinned_like(torch, m)
+                keep.append(pt)
+                ha.extra_mask = pa.ctypes.data
             h2d_bytes += m.nbytes
         nb = 1 if c["kind"] == "tp" else 2
         dres, hres = (tri_result * nb)(), (tri_result * nb)()
@@ -373,15 +383,17 @@ def run_ours(args):
     eng.set_counting(False)
 
     # ---- engine-level e2e: pinned host columns through tri_submit_* / tri_wait
-    for _ in range(max(1, min(args.warmup, 2))):
-        engine_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        lnZ_e2e = engine_step()
-    torch.cuda.synchronize()
-    engine_s = max_over_ranks(time.perf_counter() - t0)
-    assert np.allclose(lnZ, lnZ_e2e, rtol=0, atol=1e-9, equal_nan=True), "paths disagree"
+    engine_s = None
+    if engine_leg:
+        for _ in range(max(1, min(args.warmup, 2))):
+            engine_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            lnZ_e2e = engine_step()
+        torch.cuda.synchronize()
+        engine_s = max_over_ranks(time.perf_counter() - t0)
+        assert np.allclose(lnZ, lnZ_e2e, rtol=0, atol=1e-9, equal_nan=True), "paths disagree"
 
     # ---- e2e: the public call.  target.calc_probs with numpy's draws (parity mode), N_total
     # draws per scenario, sharded over the ranks by the package itself
@@ -479,11 +491,11 @@ def run_ours(args):
                        "(sequential generator), transforms, pinned staging + H2D, kernels, "
                        "best-draw tables, probabilities" % N_total,
                 "FPP": fpp, "NFPP": nfpp,
-                "engine": {"value": units_per_step * args.steps / engine_s,
-                           "ms_per_step": engine_s * 1e3 / args.steps,
-                           "api": "tri_submit_tp/eb + tri_wait on pinned host columns (draws "
-                                  "already made), up to %d calls in flight"
-                                  % _cabi.TRI_MAX_INFLIGHT},
+                "engine": None if engine_s is None else {
+                    "value": units_per_step * args.steps / engine_s,
+                    "ms_per_step": engine_s * 1e3 / args.steps,
+                    "api": "tri_submit_tp/eb + tri_wait on pinned host columns (draws already "
+                           "made), up to %d calls in flight" % _cabi.TRI_MAX_INFLIGHT},
                 "device_sampler": {"value": N_ROWS * N_total * npts / dwalls[-1],
                                    "ms_per_step": dwalls[-1] * 1e3,
                                    "FPP": float(dtgt.FPP), "NFPP": float(dtgt.NFPP),

@@ -6,7 +6,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libtriceratops_b200.so")
-HOST_SO_PATH = os.path.join(CSRC, "libtriceratops_host.so")   # prior-draw helpers (host_prep.c)
+HOST_SO_PATH = os.path.join(CSRC, "libtriceratops_host.so")   # prior-draw helpers (host_*.c)
 SOURCES = ["tri_cabi.cu"]
 HEADERS = ["tri_kernels.cuh", "tri_model.cuh", os.path.join("..", "..", "include", "triceratops_b200.h")]
 
@@ -35,14 +35,16 @@ def needs_build():
 
 def build_host(force=False):
     """gcc build of csrc/host_prep.c (OpenMP spline evaluation for the prior-draw preparation)."""
-    src = os.path.join(CSRC, "host_prep.c")
+    srcs = [os.path.join(CSRC, "host_prep.c"), os.path.join(CSRC, "host_rng.c")]
     if (not force and os.path.exists(HOST_SO_PATH)
-            and os.path.getmtime(HOST_SO_PATH) >= os.path.getmtime(src)):
+            and os.path.getmtime(HOST_SO_PATH) >= max(os.path.getmtime(s) for s in srcs)):
         return HOST_SO_PATH
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
-    base = [cc, "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c11"]
+    # -O3 for the vectorised MT19937 recurrence of host_rng.c (integer work; the spline code
+    # of host_prep.c keeps its operation order: no contraction, no fast-math)
+    base = [cc, "-O3", "-ffp-contract=off", "-fPIC", "-shared", "-std=gnu11"]
     for extra in (["-fopenmp"], []):
-        if subprocess.run(base + extra + ["-o", HOST_SO_PATH, src]).returncode == 0:
+        if subprocess.run(base + extra + ["-o", HOST_SO_PATH] + srcs).returncode == 0:
             return HOST_SO_PATH
     raise RuntimeError("could not build " + HOST_SO_PATH)
 

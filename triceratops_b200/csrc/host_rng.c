@@ -70,7 +70,7 @@ int trih_mt_rand(uint32_t* key, int32_t* pos, double* out, int64_t n) {
     if (!raw) return -1;
     memcpy(raw, key, MT_N * sizeof(uint32_t));
     mt_extend(raw, nblocks);
-    words_to_doubles(raw + *pos, out, n);
+    if (out) words_to_doubles(raw + *pos, out, n);    /* (NULL: skip the draws) */
     int64_t cursor = *pos + need;                           /* in words from raw[0] */
     int64_t blk = cursor / MT_N, off = cursor % MT_N;
     if (off == 0 && blk > 0) { blk -= 1; off = MT_N; }      /* numpy regenerates lazily */

@@ -24,7 +24,7 @@ TP-type scenarios give the same numbers either way.
 import numpy as np
 from pandas import read_csv
 
-from . import _dispatch
+from . import _dispatch, _fastrng
 from ._constants import G, Msun, Rsun, pi
 from ._ldc import grid_for
 from .funcs import (file_to_contrast_curve, flux_relation, stellar_relations, trilegal_results)
@@ -51,7 +51,7 @@ def _periods(P_orb, N):
     """Fixed period or uniform draws over a range (marginal_likelihoods.py:67-72).  Returns
     (per-draw array, or a float that the engine broadcasts; mean period for sample_ecc)."""
     if type(P_orb) not in [float, int]:
-        P = np.random.uniform(low=P_orb[0], high=P_orb[-1], size=N)
+        P = _fastrng.uniform(P_orb[0], P_orb[-1], N)
         return P, np.mean(P)
     # np.mean(np.full(N, P)) is what the reference hands to sample_ecc; it can differ from P in
     # the last bits, which only matters at the P <= 10 switch, so take the same route
@@ -79,6 +79,26 @@ def _impact(a, ecc, argp, inc, R_host):
     return r * np.cos(inc * pi / 180) / (R_host * Rsun)
 
 
+def _draw_ecc(N, planet, P_mean):
+    """sample_ecc(np.random.rand(N), planet, P_orb) of the reference (priors.py:134-155): the
+    uniform deviates are drawn and ignored, the eccentricities come from scipy.stats on numpy's
+    global generator -- Beta(0.867, 3.03) for planets, a power law for binaries."""
+    _fastrng.skip(N)
+    if planet:
+        return sample_ecc(_Len(N), planet=True, P_orb=P_mean)
+    return _fastrng.powerlaw_rvs(0.2 if P_mean <= 10 else 0.6, N)
+
+
+class _Len:
+    """Stands for an array of which only the length is used."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+
 class _PlanetDraws:
     """The deviates of a planet draw, taken from numpy's generator in the reference's order
     (rp, inc, ecc, argp; the eccentricity sampler draws from the generator itself).  The
@@ -86,10 +106,10 @@ class _PlanetDraws:
     the generator on (_dispatch.rng_done): they are deterministic."""
 
     def __init__(self, N, P_mean):
-        self.x_rp = np.random.rand(N)
-        self.x_inc = np.random.rand(N)
-        self.eccs = sample_ecc(np.random.rand(N), planet=True, P_orb=P_mean)
-        self.x_w = np.random.rand(N)
+        self.x_rp = _fastrng.rand(N)
+        self.x_inc = _fastrng.rand(N)
+        self.eccs = _draw_ecc(N, True, P_mean)
+        self.x_w = _fastrng.rand(N)
 
     def finish(self, host_masses, flatpriors):
         return (sample_rp(self.x_rp, host_masses, flatpriors), sample_inc(self.x_inc), self.eccs,
@@ -104,10 +124,10 @@ class _BinaryDraws:
     """Same for a stellar companion: inc, q, ecc, argp."""
 
     def __init__(self, N, P_mean):
-        self.x_inc = np.random.rand(N)
-        self.x_q = np.random.rand(N)
-        self.eccs = sample_ecc(np.random.rand(N), planet=False, P_orb=P_mean)
-        self.x_w = np.random.rand(N)
+        self.x_inc = _fastrng.rand(N)
+        self.x_q = _fastrng.rand(N)
+        self.eccs = _draw_ecc(N, False, P_mean)
+        self.x_w = _fastrng.rand(N)
 
     def finish(self, M_s):
         return sample_inc(self.x_inc), sample_q(self.x_q, M_s), self.eccs, sample_w(self.x_w)
@@ -119,7 +139,7 @@ class _CompanionDraw:
 
     def __init__(self, N, molusc_file):
         self.N, self.molusc_file = N, molusc_file
-        self.x = np.random.rand(N) if molusc_file is None else None
+        self.x = _fastrng.rand(N) if molusc_file is None else None
 
     def finish(self, M_s):
         if self.molusc_file is None:
@@ -130,7 +150,7 @@ class _CompanionDraw:
 def _companion_q(N, M_s, molusc_file):
     """Mass ratios of bound companions: prior draws or a MOLUSC table (e.g. :455-464)."""
     if molusc_file is None:
-        return sample_q_companion(np.random.rand(N), M_s)
+        return sample_q_companion(_fastrng.rand(N), M_s)
     df = read_csv(molusc_file)
     sma = df["semi-major axis(AU)"].values
     e = df["eccentricity"].values
@@ -488,7 +508,7 @@ def lnZ_DTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     P, P_mean = _periods(P_orb, N)
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
-    idxs = np.random.randint(0, bg.N_comp - 1, N)     # upper bound N_comp-1, as :1463
+    idxs = _fastrng.randint(0, bg.N_comp - 1, N)     # upper bound N_comp-1, as :1463
     draws = _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
     rps, incs, eccs, argps = draws.finish(np.full(N, M_s), flatpriors)
@@ -517,7 +537,7 @@ def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     draws = _BinaryDraws(N, P_mean)
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
-    idxs = np.random.randint(0, bg.N_comp - 1, N)     # :1672
+    idxs = _fastrng.randint(0, bg.N_comp - 1, N)     # :1672
     _dispatch.rng_done()
     incs, qs, eccs, argps = draws.finish(M_s)
     masses = qs * M_s
@@ -546,7 +566,7 @@ def lnZ_BTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
-    idxs = np.random.randint(0, bg.N_comp, N)         # :1926
+    idxs = _fastrng.randint(0, bg.N_comp, N)         # :1926
     draws = _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
     host_masses = bg.masses[idxs]
@@ -576,12 +596,12 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     N = int(N)
     _dispatch.use_lightcurve(time, flux, sigma, exptime, nsamples)
     P, P_mean = _periods(P_orb, N)
-    x_inc, x_q = np.random.rand(N), np.random.rand(N)
-    np.random.rand(N)                                 # q_comp: drawn and never used, as :2089
-    eccs = sample_ecc(np.random.rand(N), planet=False, P_orb=P_mean)
-    x_w = np.random.rand(N)
+    x_inc, x_q = _fastrng.rand(N), _fastrng.rand(N)
+    _fastrng.skip(N)                                  # q_comp: drawn and never used, as :2089
+    eccs = _draw_ecc(N, False, P_mean)
+    x_w = _fastrng.rand(N)
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
-    idxs = np.random.randint(0, bg.N_comp, N)         # :2139
+    idxs = _fastrng.randint(0, bg.N_comp, N)         # :2139
     _dispatch.rng_done()
     incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
     radii_comp = bg.radii()
@@ -656,7 +676,7 @@ def lnZ_NTP_unknown(time: np.ndarray, flux: np.ndarray, sigma: float,
     hosts = _PossibleHosts(trilegal_fname, Tmag, mission)
     if hosts.n == 0:
         return _no_hosts(with_b=False)
-    idxs = np.random.randint(0, hosts.n, N)
+    idxs = _fastrng.randint(0, hosts.n, N)
     host_masses = hosts.masses[idxs]
     rps, incs, eccs, argps = _draw_planet(N, host_masses, flatpriors, P_mean)
     extra = (hosts.loggs[idxs] >= 3.5) & (hosts.Teffs[idxs] <= 10000)
@@ -677,7 +697,7 @@ def lnZ_NEB_unknown(time: np.ndarray, flux: np.ndarray, sigma: float,
     hosts = _PossibleHosts(trilegal_fname, Tmag, mission)
     if hosts.n == 0:
         return _no_hosts(with_b=True)                           # a single dict, as :2665
-    idxs = np.random.randint(0, hosts.n, N)
+    idxs = _fastrng.randint(0, hosts.n, N)
     host_masses, host_radii = hosts.masses[idxs], hosts.radii[idxs]
     masses = qs * host_masses
     radii, _ = stellar_relations(masses, host_radii, hosts.Teffs[idxs])
