@@ -46,6 +46,23 @@ def test_rand_skip_uniform_randint_powerlaw(seed, n):
     assert got_state[2:] == want_state[2:]
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("n", [4096, 40_000, 300_007])
+def test_beta_rvs_is_scipys(seed, n):
+    """The chunk-parallel walk of numpy's legacy_beta: values, stream position and the cached
+    gaussian left in the state (odd seeds enter with one cached)."""
+    from scipy.stats import beta
+    out = []
+    for fn in (lambda: beta.rvs(0.867, 3.030, size=n), lambda: _fastrng.beta_rvs(0.867, 3.030, n)):
+        np.random.seed(seed)
+        np.random.rand(3)
+        if seed % 2:
+            np.random.standard_normal(1)
+        out.append((fn(), np.random.rand(5), np.random.standard_normal(3)))
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+
+
 def test_gaussian_cache_survives():
     """has_gauss / cached_gaussian of the legacy state pass through untouched."""
     np.random.seed(5)

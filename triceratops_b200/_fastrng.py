@@ -12,6 +12,9 @@ recurrence and hands the state back with `set_state()`:
     randint(low, high, n)   == np.random.randint(low, high, n)
     uniform(lo, hi, n)      == np.random.uniform(lo, hi, n)
     powerlaw_rvs(a, n)      == scipy.stats.powerlaw.rvs(a, size=n)
+    beta_rvs(a, b, n)       == scipy.stats.beta.rvs(a, b, size=n)   (a < 1 < b: the planets'
+                               eccentricity prior; numpy's rejection samplers walked in
+                               parallel chunks that are stitched where their states coincide)
 
 bit for bit.  The equality is verified against numpy itself the first time the module is used
 (on a copy of the state); if the check fails or the helper library is missing, the functions
@@ -44,6 +47,10 @@ def _load():
         L.trih_mt_rand.argtypes = [_U32, ctypes.POINTER(ctypes.c_int32), _D, ctypes.c_int64]
         L.trih_mt_randint.argtypes = [_U32, ctypes.POINTER(ctypes.c_int32), ctypes.c_int64,
                                       ctypes.c_uint32, _I64, ctypes.c_int64]
+        L.trih_legacy_beta.argtypes = [_U32, ctypes.POINTER(ctypes.c_int32),
+                                       ctypes.POINTER(ctypes.c_int32),
+                                       ctypes.POINTER(ctypes.c_double), ctypes.c_double,
+                                       ctypes.c_double, _D, ctypes.c_int64, ctypes.c_int]
     except (OSError, AttributeError):
         return None
     _lib = L
@@ -96,7 +103,14 @@ def _self_check():
             if b is None or not (np.array_equal(a, b) and np.array_equal(ai, bi)
                                  and np.array_equal(a2, b2)):
                 return False
-        return True
+        from scipy.stats import beta
+        np.random.seed(10)
+        np.random.standard_normal(1)          # a cached gaussian in the state
+        a, a2 = beta.rvs(0.867, 3.03, size=70_001), np.random.standard_normal(2)
+        np.random.seed(10)
+        np.random.standard_normal(1)
+        b, b2 = beta_rvs(0.867, 3.03, 70_001, _force=True), np.random.standard_normal(2)
+        return bool(np.array_equal(a, b) and np.array_equal(a2, b2))
     finally:
         np.random.set_state(saved)
 
@@ -152,3 +166,28 @@ def powerlaw_rvs(a, n):
         from scipy.stats import powerlaw
         return powerlaw.rvs(a, size=n)
     return pow(rand(n), 1.0 / a) * 1 + 0
+
+
+def beta_rvs(a, b, n, _force=False):
+    """scipy.stats.beta.rvs(a, b, size=n) on numpy's global generator (legacy_beta: two gamma
+    deviates by rejection).  The C walker covers a < 1 < b; anything else goes to scipy."""
+    n = int(n)
+    if (not _force and (n < MIN_N or _load() is None)) or not (0.0 < a < 1.0 < b):
+        from scipy.stats import beta
+        return beta.rvs(a, b, size=n)
+    st = np.random.get_state()
+    if st[0] != "MT19937":
+        from scipy.stats import beta
+        return beta.rvs(a, b, size=n)
+    from ._hostpar import N_THREADS
+    key, pos = np.array(st[1], dtype=np.uint32), ctypes.c_int32(int(st[2]))
+    has_gauss, gauss = ctypes.c_int32(int(st[3])), ctypes.c_double(float(st[4]))
+    out = np.empty(n)
+    rc = _lib.trih_legacy_beta(key.ctypes.data_as(_U32), ctypes.byref(pos),
+                               ctypes.byref(has_gauss), ctypes.byref(gauss), float(a), float(b),
+                               out.ctypes.data_as(_D), n, int(N_THREADS))
+    if rc != 0:     # (state untouched on failure)
+        from scipy.stats import beta
+        return beta.rvs(a, b, size=n)
+    np.random.set_state((st[0], key, int(pos.value), int(has_gauss.value), float(gauss.value)))
+    return out * 1 + 0       # rv_continuous.rvs: vals * scale + loc

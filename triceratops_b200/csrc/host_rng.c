@@ -108,3 +108,238 @@ int trih_mt_randint(uint32_t* key, int32_t* pos, int64_t low, uint32_t rng, int6
     free(raw);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * scipy.stats.beta.rvs(a, b, size=n) with a < 1 < b on numpy's legacy generator: the
+ * eccentricity prior of planets, Beta(0.867, 3.03) (reference priors.py:148).  numpy's
+ * legacy_beta draws Ga ~ Gamma(a) (rejection, two uniforms per attempt) and Gb ~ Gamma(b)
+ * (Marsaglia-Tsang on polar-method gaussians, one of every pair cached in the generator state)
+ * and returns Ga / (Ga + Gb): ~110 ns per sample of log / pow / sqrt, and sequential, because
+ * every accept / reject decides where in the stream the next sample starts.  It is the largest
+ * single item of a calc_probs call's host time (6 x 1e6 samples).
+ *
+ * The state of the sampler at a sample boundary is small: (position in the stream, which polar
+ * pair -- if any -- left a gaussian in the cache).  Two walks that reach the SAME state produce
+ * the same samples from there on.  So the stream is cut into chunks by position; every chunk is
+ * walked by its own thread with numpy's exact algorithm, starting from the guess "a sample
+ * starts here, cache empty"; afterwards the chunks are stitched in order: the true state at the
+ * start of a chunk is walked forward until it coincides with a boundary state the chunk's
+ * thread recorded (a few dozen samples: both walks hit every ~4.4th double, and the cache
+ * empties every other gaussian), and the thread's samples are adopted from there.  Same
+ * operations, same libm calls, no contraction: outputs and final generator state (position,
+ * cached gaussian) are bit-identical to numpy's; tests/test_fastrng.py and the self-check of
+ * _fastrng.py compare them.
+ * ------------------------------------------------------------------------------------------- */
+#include <math.h>
+
+static inline double dbl_at(const uint32_t* w, int64_t m) {
+    uint32_t a = temper(w[2 * m]) >> 5, b = temper(w[2 * m + 1]) >> 6;
+    return (a * 67108864.0 + b) / 9007199254740992.0;
+}
+
+typedef struct {
+    const uint32_t* w;    /* raw state words from the current position */
+    int64_t cap;          /* doubles available */
+    double a, bb, c;      /* shape a; b - 1/3; 1 / sqrt(9 (b - 1/3)) */
+} beta_ctx;
+
+#define SRC_NONE (-2)     /* no cached gaussian */
+#define SRC_ENTRY (-1)    /* the gaussian cached in the generator state on entry */
+
+typedef struct {
+    int64_t m;            /* next double of the stream */
+    int64_t src;          /* SRC_NONE, SRC_ENTRY, or the first double of the pair that cached it */
+    double cache;         /* the cached gaussian (valid when src != SRC_NONE) */
+} walk_state;
+
+/* numpy legacy_gauss */
+static inline int walk_gauss(const beta_ctx* C, walk_state* S, double* g) {
+    if (S->src != SRC_NONE) {
+        *g = S->cache;
+        S->src = SRC_NONE;
+        S->cache = 0.0;
+        return 0;
+    }
+    double f, x1, x2, r2;
+    int64_t q;
+    do {
+        if (S->m + 2 > C->cap) return -2;
+        q = S->m;
+        x1 = 2.0 * dbl_at(C->w, q) - 1.0;
+        x2 = 2.0 * dbl_at(C->w, q + 1) - 1.0;
+        r2 = x1 * x1 + x2 * x2;
+        S->m += 2;
+    } while (r2 >= 1.0 || r2 == 0.0);
+    f = sqrt(-2.0 * log(r2) / r2);
+    S->cache = f * x1;
+    S->src = q;
+    *g = f * x2;
+    return 0;
+}
+
+/* numpy legacy_beta for a < 1 < b: one sample from state S */
+static inline int walk_beta(const beta_ctx* C, walk_state* S, double* val) {
+    const double shape = C->a, b = C->bb, c = C->c;
+    double U, V, X, Y, Ga, Gb;
+    for (;;) {                                   /* legacy_standard_gamma, shape < 1 */
+        if (S->m + 2 > C->cap) return -2;
+        U = dbl_at(C->w, S->m);
+        V = -log(1.0 - dbl_at(C->w, S->m + 1));
+        S->m += 2;
+        if (U <= 1.0 - shape) {
+            X = pow(U, 1. / shape);
+            if (X <= V) break;
+        } else {
+            Y = -log((1 - U) / shape);
+            X = pow(1.0 - shape + shape * Y, 1. / shape);
+            if (X <= (V + Y)) break;
+        }
+    }
+    Ga = X;
+    for (;;) {                                   /* legacy_standard_gamma, shape > 1 */
+        do {
+            if (walk_gauss(C, S, &X)) return -2;
+            V = 1.0 + c * X;
+        } while (V <= 0.0);
+        V = V * V * V;
+        if (S->m + 1 > C->cap) return -2;
+        U = dbl_at(C->w, S->m);
+        S->m += 1;
+        if (U < 1.0 - 0.0331 * (X * X) * (X * X)) break;
+        if (log(U) < 0.5 * X * X + b * (1. - V + log(V))) break;
+    }
+    Gb = b * V;
+    *val = Ga / (Ga + Gb);
+    return 0;
+}
+
+typedef struct {
+    int64_t n;            /* samples recorded */
+    int64_t cap;
+    int64_t* m0;          /* state at the start of sample k */
+    int64_t* src0;
+    double* val;
+    walk_state end;       /* state after the last sample */
+    int rc;
+} chunk_rec;
+
+int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* gauss, double a,
+                     double b, double* out, int64_t n, int nthreads) {
+    if (!(a > 0.0 && a < 1.0 && b > 1.0) || n < 0) return -3;
+    if (n == 0) return 0;
+    if (nthreads < 1) nthreads = 1;
+    beta_ctx C;
+    C.a = a;
+    C.bb = b - 1. / 3.;
+    C.c = 1. / sqrt(9 * C.bb);
+    /* doubles per sample from a pilot walk over the first block(s) of the stream */
+    double per = 4.5;
+    {
+        uint32_t pilot[9 * MT_N];
+        memcpy(pilot, key, MT_N * sizeof(uint32_t));
+        mt_extend(pilot, 8);
+        C.w = pilot + *pos;
+        C.cap = (9 * MT_N - *pos) / 2;
+        walk_state S = {0, SRC_NONE, 0.0};
+        int64_t k = 0;
+        double v;
+        while (k < n && walk_beta(&C, &S, &v) == 0) k++;
+        if (k >= 64) per = (double)S.m / (double)k;
+    }
+    /* the stream: estimated need + 2 % + slack for the sequential tail */
+    const int64_t est = (int64_t)(per * (double)n * 1.02) + 4096;
+    const int64_t cap = est + 65536;
+    const int64_t need = 2 * cap;
+    const int64_t have = MT_N - *pos;
+    const int64_t nblocks = need > have ? (need - have + MT_N - 1) / MT_N : 0;
+    uint32_t* raw = (uint32_t*)malloc((size_t)(nblocks + 1) * MT_N * sizeof(uint32_t) + 64);
+    if (!raw) return -1;
+    memcpy(raw, key, MT_N * sizeof(uint32_t));
+    mt_extend(raw, nblocks);
+    C.w = raw + *pos;
+    C.cap = cap;
+
+    int nchunks = (int)(n / 16384);
+    if (nchunks > 8 * nthreads) nchunks = 8 * nthreads;
+    if (nchunks < 1) nchunks = 1;
+    chunk_rec* R = (chunk_rec*)calloc((size_t)nchunks, sizeof(chunk_rec));
+    if (!R) { free(raw); return -1; }
+    const walk_state entry = {0, *has_gauss ? SRC_ENTRY : SRC_NONE, *has_gauss ? *gauss : 0.0};
+    int rc = 0;
+
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int t = 0; t < nchunks; t++) {
+        chunk_rec* r = &R[t];
+        const int64_t p0 = (est * t) / nchunks, p1 = (est * (t + 1)) / nchunks;
+        r->cap = (int64_t)((double)(p1 - p0) / per * 1.25) + 1024;
+        r->m0 = (int64_t*)malloc((size_t)r->cap * sizeof(int64_t));
+        r->src0 = (int64_t*)malloc((size_t)r->cap * sizeof(int64_t));
+        r->val = (double*)malloc((size_t)r->cap * sizeof(double));
+        if (!r->m0 || !r->src0 || !r->val) { r->rc = -1; continue; }
+        walk_state S = entry;
+        if (t > 0) { S.m = p0; S.src = SRC_NONE; S.cache = 0.0; }   /* the guess */
+        while (S.m < p1 && r->n < r->cap && r->n < n) {
+            r->m0[r->n] = S.m;
+            r->src0[r->n] = S.src;
+            if (walk_beta(&C, &S, &r->val[r->n])) { r->rc = -2; break; }
+            r->n++;
+        }
+        r->end = S;
+    }
+
+    /* ---- stitch the chunks in order */
+    walk_state S = entry;
+    int64_t count = 0;
+    for (int t = 0; t < nchunks && count < n && rc == 0; t++) {
+        chunk_rec* r = &R[t];
+        if (r->rc == -1) { rc = -1; break; }
+        const int64_t p1 = (est * (t + 1)) / nchunks;
+        int64_t k = 0;
+        int merged = 0;
+        while (count < n) {
+            while (k < r->n && r->m0[k] < S.m) k++;
+            if (k < r->n && r->m0[k] == S.m && r->src0[k] == S.src) { merged = 1; break; }
+            if (S.m >= p1) break;                    /* no coincidence inside this chunk */
+            if (walk_beta(&C, &S, &out[count])) { rc = -2; break; }
+            count++;
+        }
+        if (rc || !merged) continue;
+        int64_t take = r->n - k;
+        /* a chunk whose walk stopped early (record full / stream end) is used up to there */
+        if (take > n - count) take = n - count;
+        memcpy(out + count, r->val + k, (size_t)take * sizeof(double));
+        count += take;
+        if (k + take < r->n) {                       /* stopped inside the chunk: n reached */
+            S.m = r->m0[k + take];
+            S.src = r->src0[k + take];
+            S.cache = 0.0;
+            if (S.src >= 0) {
+                const double x1 = 2.0 * dbl_at(C.w, S.src) - 1.0;
+                const double x2 = 2.0 * dbl_at(C.w, S.src + 1) - 1.0;
+                const double r2 = x1 * x1 + x2 * x2;
+                S.cache = sqrt(-2.0 * log(r2) / r2) * x1;
+            } else if (S.src == SRC_ENTRY) {
+                S.cache = entry.cache;
+            }
+        } else {
+            S = r->end;
+        }
+    }
+    while (rc == 0 && count < n) {                   /* the estimate fell short: finish in line */
+        if (walk_beta(&C, &S, &out[count])) { rc = -2; break; }
+        count++;
+    }
+    if (rc == 0) {
+        *has_gauss = S.src != SRC_NONE;
+        *gauss = S.src != SRC_NONE ? S.cache : 0.0;
+        int64_t cursor = *pos + 2 * S.m;
+        int64_t blk = cursor / MT_N, off = cursor % MT_N;
+        if (off == 0 && blk > 0) { blk -= 1; off = MT_N; }
+        memcpy(key, raw + blk * MT_N, MT_N * sizeof(uint32_t));
+        *pos = (int32_t)off;
+    }
+    for (int t = 0; t < nchunks; t++) { free(R[t].m0); free(R[t].src0); free(R[t].val); }
+    free(R);
+    free(raw);
+    return rc;
+}

@@ -85,18 +85,8 @@ def _draw_ecc(N, planet, P_mean):
     global generator -- Beta(0.867, 3.03) for planets, a power law for binaries."""
     _fastrng.skip(N)
     if planet:
-        return sample_ecc(_Len(N), planet=True, P_orb=P_mean)
+        return _fastrng.beta_rvs(0.867, 3.030, N)
     return _fastrng.powerlaw_rvs(0.2 if P_mean <= 10 else 0.6, N)
-
-
-class _Len:
-    """Stands for an array of which only the length is used."""
-
-    def __init__(self, n):
-        self.n = n
-
-    def __len__(self):
-        return self.n
 
 
 class _PlanetDraws:
