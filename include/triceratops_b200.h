@@ -78,16 +78,19 @@ typedef struct {
 
 /* Output of one scenario branch.  lnZ = m + ln(s) - ln(N) (-inf if no finite entry, +inf if any
  * entry is +inf: _numerics.py:12-51); (m, s) are exposed so that ranks holding disjoint slices
- * of the draws can be combined with one all-reduce. */
+ * of the draws can be combined with one collective.  (m, s) are accumulated per block of the
+ * persistent light-curve kernel in the order its warps pick up the draws: the last bits of lnZ
+ * may differ between two runs on the same input (|dlnZ| ~ 1e-15); per-draw lnL never does. */
 typedef struct {
     double lnZ;
     double m, s;          /* max of the finite ln-weights and sum of exp(lnw - m)            */
     int64_t n_finite;     /* finite ln-weights                                                */
     int64_t n_posinf;     /* +inf ln-weights                                                  */
     int64_t n_pass;       /* draws that survived the geometric mask of this branch           */
-    int64_t n_stamps;     /* time stamps whose sub-exposures were evaluated (diagnostic)     */
-    int64_t n_interior;   /* evaluated model points with the occultor inside the disc        */
-    int64_t n_limb;       /* evaluated model points with the occultor on the limb            */
+    int64_t n_stamps;     /* time stamps whose sub-exposures were evaluated  } work counters  */
+    int64_t n_interior;   /* evaluated model points, occultor inside the disc } of the roofline */
+    int64_t n_limb;       /* evaluated model points, occultor on the limb    } model: 0 unless */
+                          /*                                       tri_set_counting(1) is on  */
     double* lnL_out;      /* optional [N]: per-draw lnL (no prior), -inf where masked         */
     uint8_t* mask_out;    /* optional [N]: the geometric mask                                 */
     /* best draws, i.e. the head of (-lnL).argsort() (marginal_likelihoods.py:152-153), selected
@@ -95,7 +98,7 @@ typedef struct {
      * Leave top_cap = 0 to skip.  (Device-pointer calls return them unsorted.)                */
     int64_t top_cap;      /* in: capacity of top_idx / top_lnL                                */
     int64_t n_top;        /* out: entries written (= min(top_cap, n_evaluated))               */
-    int64_t n_evaluated;  /* out: draws with a finite lnL (valid when top_cap > 0)            */
+    int64_t n_evaluated;  /* out: draws with a finite lnL                                     */
     int64_t* top_idx;     /* out [top_cap]: draw indices                                      */
     double* top_lnL;      /* out [top_cap]: their lnL                                         */
 } tri_result;
@@ -109,6 +112,15 @@ const char* tri_last_error(void);
  * (time, flux, sigma, exptime, nsamples) -- triceratops.py:738-740, marginal_likelihoods.py:39-43. */
 int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, double sigma,
                        double exptime, int32_t nsamples);
+
+/* The same with one error per time stamp (an extension: the reference takes a scalar,
+ * triceratops.py:674, funcs.py:176).  chi^2 = sum_j (flux_j - model_j)^2 / flux_err_j^2; the
+ * scalar that the reference's formulas need -- the Gaussian constant -ln(sigma), applied once
+ * per light curve (marginal_likelihoods.py:130), and the secondary-depth cut 1.5 sigma
+ * (likelihoods.py:535) -- is sigma = mean(flux_err), what callers of the reference pass today.
+ * Constant errors give the scalar call's results (to rounding: the weights enter the sums). */
+int tri_set_lightcurve_err(const double* time, const double* flux, const double* flux_err,
+                           int64_t npts, double exptime, int32_t nsamples);
 
 /* L2 seam, host buffers: replaces the body of lnZ_* between the prior draws and _log_mean_exp. */
 int tri_eval_tp(const tri_tp_args* args, tri_result* out);
@@ -178,7 +190,9 @@ int tri_fetch_lnl(int32_t branch, double* out, int64_t N);
 int tri_log_mean_exp(const double* logw, int64_t n, tri_result* out);
 
 /* Device time [ms] of the kernels of the most recent eval/lnl call, from CUDA events on the
- * stream they ran on: geometry, light-curve/chi^2, log-mean-exp, and their launch count. */
+ * stream they ran on: geometry, light-curve/chi^2 (with the fused evidence epilogue), the
+ * finalize kernel (merge of the block records + best-draw selection), and their launch count
+ * (3 per evaluation). */
 int tri_last_timing(double* geometry_ms, double* lnl_ms, double* lse_ms, int32_t* launches);
 
 /* Device-side prior sampler support (opt-in mode, triceratops_b200.set_sampler("device")):

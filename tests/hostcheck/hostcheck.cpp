@@ -80,7 +80,7 @@ void hc_lnl(int eb, int64_t npts, const double* time_sorted, const double* flux_
         run += (long double)((double)d * (double)d);
         pre[j + 1] = (double)run;
     }
-    LightCurve lc{time_sorted, flux_sorted, pre.data(), (int)npts, nsamples, sigma, exptime,
+    LightCurve lc{time_sorted, flux_sorted, pre.data(), nullptr, (int)npts, nsamples, sigma, exptime,
                   time_sorted[0], time_sorted[npts - 1]};
     const double inv_ns = 1.0 / nsamples;
     for (int64_t i = 0; i < n; i++) {

@@ -59,7 +59,7 @@ EXPORTS = ("tri_init", "tri_shutdown", "tri_last_error", "tri_set_lightcurve", "
            "tri_simulate_tp", "tri_simulate_eb",
            "tri_fetch_lnl", "tri_log_mean_exp", "tri_last_timing", "tri_fp64_peak", "tri_sm_count",
            "tri_submit_tp", "tri_submit_eb", "tri_submit_tp_dev", "tri_submit_eb_dev", "tri_wait",
-           "tri_dev_splev", "tri_set_counting")
+           "tri_dev_splev", "tri_set_counting", "tri_set_lightcurve_err")
 
 _lib = None
 
@@ -86,6 +86,8 @@ def load():
     L.tri_init.argtypes = [ctypes.c_int]
     L.tri_set_lightcurve.argtypes = [c_double_p, c_double_p, ctypes.c_int64, ctypes.c_double,
                                      ctypes.c_double, ctypes.c_int32]
+    L.tri_set_lightcurve_err.argtypes = [c_double_p, c_double_p, c_double_p, ctypes.c_int64,
+                                         ctypes.c_double, ctypes.c_int32]
     L.tri_eval_tp.argtypes = [ctypes.POINTER(tri_tp_args), ctypes.POINTER(tri_result)]
     L.tri_eval_eb.argtypes = [ctypes.POINTER(tri_eb_args), ctypes.POINTER(tri_result)]
     L.tri_eval_tp_dev.argtypes = [ctypes.POINTER(tri_tp_args), ctypes.POINTER(tri_result),

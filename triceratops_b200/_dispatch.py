@@ -291,7 +291,9 @@ class CallGroup:
         with self.lock:
             seq = self.seq
             self.seq += 1
-            key = None if lc is None else (lc[0].tobytes(), lc[1].tobytes()) + tuple(lc[2:])
+            key = None if lc is None else (
+                np.asarray(lc[0]).tobytes(), np.asarray(lc[1]).tobytes(),
+                np.asarray(lc[2], dtype=np.float64).tobytes()) + tuple(lc[3:])
             send_lc = lc if key != self.lc_key else None
             self.lc_key = key
             hdr = dict(op="call", seq=seq, kind=kind, N=N, arrays=arrays, scalars=scalars,

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -20,10 +21,17 @@ namespace {
 
 using namespace tri;
 
+// Error text: per calling thread (the thread that got the error code reads its own message even
+// when other threads use the engine in between) with the engine's most recent error as the
+// answer for a thread that has none of its own.
 thread_local std::string g_err;
+std::mutex g_err_mutex;
+std::string g_err_engine;
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
+    std::lock_guard<std::mutex> lock(g_err_mutex);
+    g_err_engine = msg;
     return code;
 }
 
@@ -174,7 +182,7 @@ struct Ctx {
     OrbitTable tab{};
     // light curve
     bool have_lc = false;
-    double *d_time = nullptr, *d_flux = nullptr, *d_prefix = nullptr;
+    double *d_time = nullptr, *d_flux = nullptr, *d_prefix = nullptr, *d_weight = nullptr;
     int* d_perm = nullptr;   // sorted stamp -> caller's stamp
     size_t lc_cap = 0;
     LightCurve lc{};
@@ -482,6 +490,36 @@ Slot* free_slot() {
     return nullptr;
 }
 
+// Arenas only grow, and growing one means cudaFree (a device-wide synchronisation).  When a call
+// needs more than its slot holds, every free slot is grown to the new size in the same breath,
+// so that a run of equally large calls pays for it once and not once per slot of the ring.
+int grow_slots(Slot& S, size_t scratch, size_t staging, size_t pinned) {
+    if (scratch <= S.scratch.cap && staging <= S.staging.cap && pinned <= S.pinned.cap)
+        return TRI_OK;
+    for (int i = 0; i < kSlots; ++i) {
+        Slot& T = g.slots[i];
+        if (T.ticket != 0 && &T != &S) continue;
+        int rc = T.scratch.reserve(scratch);
+        if (!rc && staging) rc = T.staging.reserve(staging);
+        if (!rc && pinned) rc = T.pinned.reserve(pinned);
+        if (rc) return rc;
+    }
+    return TRI_OK;
+}
+
+// A submission that fails after its first asynchronous copy leaves work queued on the two
+// streams that refers to the slot's arenas: let it finish before the slot is handed out again.
+int abandon(Slot& S, int rc) {
+    cudaStreamSynchronize(g.copy_stream);
+    cudaStreamSynchronize(g.stream);
+    cudaGetLastError();
+    S.ticket = 0;
+    S.staging.reset();
+    S.pinned.reset();
+    S.scratch.reset();
+    return rc;
+}
+
 Slot* find_slot(int64_t ticket) {
     if (ticket <= 0) return nullptr;
     for (int i = 0; i < kSlots; ++i)
@@ -530,7 +568,13 @@ void commit(Slot& S, int branches, int64_t N, bool host, const tri_result* want,
 
 extern "C" {
 
-const char* tri_last_error(void) { return g_err.c_str(); }
+const char* tri_last_error(void) {
+    if (g_err.empty()) {
+        std::lock_guard<std::mutex> lock(g_err_mutex);
+        g_err = g_err_engine;
+    }
+    return g_err.c_str();
+}
 
 int tri_init(int device) {
     if (g.ready && g.device == device) return TRI_OK;
@@ -594,6 +638,7 @@ int tri_shutdown(void) {
     cudaFree(g.d_time);
     cudaFree(g.d_flux);
     cudaFree(g.d_prefix);
+    cudaFree(g.d_weight);
     cudaFree(g.d_perm);
     for (Slot& S : g.slots) {
         cudaFree(S.d_counters);
@@ -634,12 +679,21 @@ int tri_sm_count(int32_t* n) {
     return TRI_OK;
 }
 
-int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, double sigma,
-                       double exptime, int32_t nsamples) {
+static int set_lightcurve(const double* time, const double* flux, const double* err,
+                          int64_t npts, double sigma, double exptime, int32_t nsamples) {
     int rc = need_ready(false);
     if (rc) return rc;
     if (!time || !flux || npts <= 0) return fail(TRI_EINVAL, "empty light curve");
     if (npts > (int64_t)1 << 28) return fail(TRI_EINVAL, "light curve too long");
+    if (err) {   // per-point errors: the reference scalar is their mean
+        long double acc = 0.0L;
+        for (int64_t j = 0; j < npts; j++) {
+            if (!(err[j] > 0.0) || !std::isfinite(err[j]))
+                return fail(TRI_EINVAL, "per-point errors must be finite and > 0");
+            acc += err[j];
+        }
+        sigma = (double)(acc / (long double)npts);
+    }
     if (!(sigma > 0.0) || nsamples < 1 || !(exptime >= 0.0))
         return fail(TRI_EINVAL, "sigma must be > 0, nsamples >= 1, exptime >= 0");
     for (int64_t j = 0; j < npts; j++)
@@ -650,14 +704,19 @@ int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, dou
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(),
                      [&](int64_t x, int64_t y) { return time[x] < time[y]; });
-    std::vector<double> t(npts), f(npts), pre(npts + 1);
+    std::vector<double> t(npts), f(npts), pre(npts + 1), wgt(err ? npts : 0);
     long double run = 0.0L;
     pre[0] = 0.0;
     for (int64_t j = 0; j < npts; j++) {
         t[j] = time[order[j]];
         f[j] = flux[order[j]];
         long double d = (long double)f[j] - 1.0L;
-        run += (long double)((double)d * (double)d);
+        double term = (double)d * (double)d;
+        if (err) {
+            wgt[j] = 1.0 / (err[order[j]] * err[order[j]]);
+            term = ((double)d * wgt[j]) * (double)d;     // as the kernel forms w r^2
+        }
+        run += (long double)term;
         pre[j + 1] = (double)run;
     }
     CU(cudaSetDevice(g.device));
@@ -667,24 +726,28 @@ int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, dou
     CU(cudaStreamSynchronize(g.stream));
     if ((size_t)npts > g.lc_cap) {
         cudaFree(g.d_time); cudaFree(g.d_flux); cudaFree(g.d_prefix); cudaFree(g.d_perm);
-        g.d_time = g.d_flux = g.d_prefix = nullptr;
+        cudaFree(g.d_weight);
+        g.d_time = g.d_flux = g.d_prefix = g.d_weight = nullptr;
         g.d_perm = nullptr;
         g.lc_cap = 0;
         CU(cudaMalloc(&g.d_perm, npts * sizeof(int)));
         CU(cudaMalloc(&g.d_time, npts * sizeof(double)));
         CU(cudaMalloc(&g.d_flux, npts * sizeof(double)));
         CU(cudaMalloc(&g.d_prefix, (npts + 1) * sizeof(double)));
+        CU(cudaMalloc(&g.d_weight, npts * sizeof(double)));
         g.lc_cap = (size_t)npts;
     }
     CU(cudaMemcpy(g.d_time, t.data(), npts * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g.d_flux, f.data(), npts * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(g.d_prefix, pre.data(), (npts + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    if (err) CU(cudaMemcpy(g.d_weight, wgt.data(), npts * sizeof(double), cudaMemcpyHostToDevice));
     {
         std::vector<int> perm(npts);
         for (int64_t j = 0; j < npts; j++) perm[j] = (int)order[j];
         CU(cudaMemcpy(g.d_perm, perm.data(), npts * sizeof(int), cudaMemcpyHostToDevice));
     }
     g.lc.time = g.d_time; g.lc.flux = g.d_flux; g.lc.prefix = g.d_prefix;
+    g.lc.weight = err ? g.d_weight : nullptr;
     g.lc.npts = (int)npts; g.lc.nsamples = nsamples; g.lc.sigma = sigma; g.lc.exptime = exptime;
     g.lc.tmin = t.front(); g.lc.tmax = t.back();
     // stage the light curve in shared memory only when that costs no occupancy
@@ -703,6 +766,17 @@ int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, dou
     return TRI_OK;
 }
 
+int tri_set_lightcurve(const double* time, const double* flux, int64_t npts, double sigma,
+                       double exptime, int32_t nsamples) {
+    return set_lightcurve(time, flux, nullptr, npts, sigma, exptime, nsamples);
+}
+
+int tri_set_lightcurve_err(const double* time, const double* flux, const double* flux_err,
+                           int64_t npts, double exptime, int32_t nsamples) {
+    if (!flux_err) return fail(TRI_EINVAL, "flux_err is NULL");
+    return set_lightcurve(time, flux, flux_err, npts, 0.0, exptime, nsamples);
+}
+
 // ---- submit / wait --------------------------------------------------------------------------
 int tri_submit_tp_dev(const tri_tp_args* a, const tri_result* want, void* stream,
                       int64_t* ticket) {
@@ -716,8 +790,9 @@ int tri_submit_tp_dev(const tri_tp_args* a, const tri_result* want, void* stream
     CU(cudaSetDevice(g.device));
     cudaStream_t s = (cudaStream_t)stream;   // NULL is the CUDA default stream, as everywhere
     if (a->N > 0) {
-        rc = enqueue_tp(*S, *a, *want, s);
-        if (rc) return rc;
+        rc = grow_slots(*S, scratch_bytes(a->N, true), 0, 0);
+        if (!rc) rc = enqueue_tp(*S, *a, *want, s);
+        if (rc) { cudaStreamSynchronize(s); return abandon(*S, rc); }
     }
     CU(cudaEventRecord(S->done, s));
     commit(*S, 1, a->N, false, want, ticket);
@@ -736,8 +811,9 @@ int tri_submit_eb_dev(const tri_eb_args* a, const tri_result want[2], void* stre
     CU(cudaSetDevice(g.device));
     cudaStream_t s = (cudaStream_t)stream;   // NULL is the CUDA default stream, as everywhere
     if (a->N > 0) {
-        rc = enqueue_eb(*S, *a, want, s);
-        if (rc) return rc;
+        rc = grow_slots(*S, scratch_bytes(a->N, true), 0, 0);
+        if (!rc) rc = enqueue_eb(*S, *a, want, s);
+        if (rc) { cudaStreamSynchronize(s); return abandon(*S, rc); }
     }
     CU(cudaEventRecord(S->done, s));
     commit(*S, 2, a->N, false, want, ticket);
@@ -789,28 +865,22 @@ static int reserve_top(Slot& S, int64_t cap) {
     return TRI_OK;
 }
 
-int tri_submit_tp(const tri_tp_args* a, const tri_result* want, int64_t* ticket) {
-    int rc = need_ready(true);
-    if (rc) return rc;
-    if (!ticket) return fail(TRI_EINVAL, "NULL argument");
-    rc = check_tp(a, want);
-    if (rc) return rc;
-    Slot* S = free_slot();
-    if (!S) return no_slot();
-    CU(cudaSetDevice(g.device));
+static int submit_tp_body(Slot* S, const tri_tp_args* a, const tri_result* want,
+                          int64_t* ticket) {
+    int rc;
     const int64_t N = a->N;
     if (N > 0) {
         cudaStream_t cs = g.copy_stream;
-        S->staging.reset();
-        rc = S->staging.reserve((size_t)N * 8 * 16 + (size_t)N * 3 + 8192
-                                + (size_t)std::max<int64_t>(want->top_cap, 0) * 32);
+        // pageable caller columns go through the pinned arena (sized for the EB-type column
+        // set too: a slot serves both kinds in turn)
+        rc = grow_slots(*S, scratch_bytes(N, true),
+                        (size_t)N * 8 * 16 + (size_t)N * 3 + 8192
+                            + (size_t)std::max<int64_t>(want->top_cap, 0) * 32,
+                        is_pinned(a->inc.ptr)
+                            ? 0 : std::min(kPinnedLimit, (size_t)N * 8 * 14 + (size_t)N + 8192));
         if (rc) return rc;
+        S->staging.reset();
         S->pinned.reset();
-        if (!is_pinned(a->inc.ptr)) {   // pageable caller columns go through the pinned arena
-            // (sized for the EB-type column set too: a slot serves both kinds in turn)
-            rc = S->pinned.reserve(std::min(kPinnedLimit, (size_t)N * 8 * 14 + (size_t)N + 8192));
-            if (rc) return rc;
-        }
         tri_tp_args d = *a;
         Col c;
 #define STAGE(field)                                   \
@@ -846,28 +916,34 @@ int tri_submit_tp(const tri_tp_args* a, const tri_result* want, int64_t* ticket)
     return TRI_OK;
 }
 
-int tri_submit_eb(const tri_eb_args* a, const tri_result want[2], int64_t* ticket) {
+int tri_submit_tp(const tri_tp_args* a, const tri_result* want, int64_t* ticket) {
     int rc = need_ready(true);
     if (rc) return rc;
     if (!ticket) return fail(TRI_EINVAL, "NULL argument");
-    rc = check_eb(a, want);
+    rc = check_tp(a, want);
     if (rc) return rc;
     Slot* S = free_slot();
     if (!S) return no_slot();
     CU(cudaSetDevice(g.device));
+    rc = submit_tp_body(S, a, want, ticket);
+    return rc ? abandon(*S, rc) : TRI_OK;
+}
+
+static int submit_eb_body(Slot* S, const tri_eb_args* a, const tri_result want[2],
+                          int64_t* ticket) {
+    int rc;
     const int64_t N = a->N;
     if (N > 0) {
         cudaStream_t cs = g.copy_stream;
-        S->staging.reset();
-        rc = S->staging.reserve((size_t)N * 8 * 16 + (size_t)N * 3 + 8192
-                                + (size_t)std::max<int64_t>(want[0].top_cap, 0) * 16
-                                + (size_t)std::max<int64_t>(want[1].top_cap, 0) * 16);
+        rc = grow_slots(*S, scratch_bytes(N, true),
+                        (size_t)N * 8 * 16 + (size_t)N * 3 + 8192
+                            + (size_t)std::max<int64_t>(want[0].top_cap, 0) * 16
+                            + (size_t)std::max<int64_t>(want[1].top_cap, 0) * 16,
+                        is_pinned(a->inc.ptr)
+                            ? 0 : std::min(kPinnedLimit, (size_t)N * 8 * 14 + (size_t)N + 8192));
         if (rc) return rc;
+        S->staging.reset();
         S->pinned.reset();
-        if (!is_pinned(a->inc.ptr)) {
-            rc = S->pinned.reserve(std::min(kPinnedLimit, (size_t)N * 8 * 14 + (size_t)N + 8192));
-            if (rc) return rc;
-        }
         tri_eb_args d = *a;
         Col c;
         STAGE(reb) STAGE(ebfr) STAGE(q) STAGE(P_orb) STAGE(inc) STAGE(ecc) STAGE(argp)
@@ -901,6 +977,19 @@ int tri_submit_eb(const tri_eb_args* a, const tri_result want[2], int64_t* ticke
     CU(cudaEventRecord(S->done, g.stream));
     commit(*S, 2, N, true, want, ticket);
     return TRI_OK;
+}
+
+int tri_submit_eb(const tri_eb_args* a, const tri_result want[2], int64_t* ticket) {
+    int rc = need_ready(true);
+    if (rc) return rc;
+    if (!ticket) return fail(TRI_EINVAL, "NULL argument");
+    rc = check_eb(a, want);
+    if (rc) return rc;
+    Slot* S = free_slot();
+    if (!S) return no_slot();
+    CU(cudaSetDevice(g.device));
+    rc = submit_eb_body(S, a, want, ticket);
+    return rc ? abandon(*S, rc) : TRI_OK;
 }
 
 int tri_wait(int64_t ticket, tri_result* out) {

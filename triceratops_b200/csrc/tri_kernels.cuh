@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
                         if (A.model_out) A.model_out[(size_t)w * npts + A.perm[j]] = md;
                         const double* fp = VS.flux;
                         const double rr = fp[j] - md;
-                        red = fma(rr, rr, red);
+                        red = fma(A.lc.weight ? rr * __ldg(A.lc.weight + j) : rr, rr, red);
                     } else {
                         red = fmin(red, m);
                     }
@@ -608,7 +608,8 @@ __global__ void __launch_bounds__(kLnlThreads, kLnlMinBlocks) lnl_kernel(LnlArgs
             const double* pre = VS.prefix;
             chi += (pre[jlo] - pre[0]) + (pre[npts] - pre[jhi]);
             const double sigma = A.lc.sigma;
-            const double half_chi2 = 0.5 * (chi / (sigma * sigma));       // likelihoods.py:486
+            const double half_chi2 = A.lc.weight ? 0.5 * chi              // weights carry 1/sigma_j^2
+                                                 : 0.5 * (chi / (sigma * sigma));   // likelihoods.py:486
             val = A.raw ? half_chi2 : S.lnorm - half_chi2;
         }
         if (kCount && A.counters) {

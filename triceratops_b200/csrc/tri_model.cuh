@@ -172,6 +172,42 @@ TRI_TABLE(kEll, 18,
           0.44325141463, 0.0626060122, 0.04757383546, 0.01736506451,
           0.2499836831, 0.09200180037, 0.04069697526, 0.00526449639)
 
+// acos: fdlibm's rational approximation R(z) = z P(z) / Q(z) of (asin(x) - x) / x
+TRI_TABLE(kAcos, 12,
+          1.66666666666666657415e-01,   /* 0 pS0 */
+          -3.25565818622400915405e-01,  /* 1 pS1 */
+          2.01212532134862925881e-01,   /* 2 pS2 */
+          -4.00555345006794114027e-02,  /* 3 pS3 */
+          7.91534994289814532176e-04,   /* 4 pS4 */
+          3.47933107596021167570e-05,   /* 5 pS5 */
+          -2.40339491173441421878e+00,  /* 6 qS1 */
+          2.02094576023350569471e+00,   /* 7 qS2 */
+          -6.88283971605453293030e-01,  /* 8 qS3 */
+          7.70381505559019352791e-02,   /* 9 qS4 */
+          1.57079632679489655800e+00,   /* 10 pi/2 high */
+          6.12323399573676603587e-17)   /* 11 pi/2 low  */
+
+// acos(x) for |x| <= 1 (the limb-crossing angles of occult_quad; NaN -> NaN), ~1 ulp: one
+// reciprocal and one square root from the hardware seeds instead of the CUDA library routine's
+// 138 instructions with 26 embedded literals.
+TRI_HD double acos_unit(double x) {
+#if defined(__CUDA_ARCH__)
+    const double* T = TRI_T(kAcos);
+    const double ax = fabs(x);
+    const bool big = ax >= 0.5;
+    const double z = big ? (1.0 - ax) * 0.5 : x * x;
+    const double pz = z * (T[0] + z * (T[1] + z * (T[2] + z * (T[3] + z * (T[4] + z * T[5])))));
+    const double qz = 1.0 + z * (T[6] + z * (T[7] + z * (T[8] + z * T[9])));
+    const double r = pz * fast_rcp(qz);
+    if (!big) return T[10] - (x - (T[11] - x * r));
+    const double sq = fast_sqrt(z);      // (|x| > 1 -> NaN, as acos)
+    const double t = 2.0 * fma(sq, r, sq);
+    return x > 0.0 ? t : 2.0 * T[10] - t + 2.0 * T[11];
+#else
+    return acos(x);
+#endif
+}
+
 // sin and cos of an angle of a few radians at most (true anomalies): quadrant reduction with a
 // two-term pi/2, then the two polynomials; ~1 ulp, no huge-argument path (|x| < 1e5 assumed).
 TRI_HD void sincos_small(double x, double& s, double& c) {
@@ -247,7 +283,10 @@ struct OrbitTable {
 struct LightCurve {
     const double* time;    // [npts] ascending
     const double* flux;    // [npts]
-    const double* prefix;  // [npts+1] running sum of (flux-1)^2, prefix[0]=0
+    const double* prefix;  // [npts+1] running sum of w (flux-1)^2, prefix[0]=0
+    const double* weight;  // [npts] 1/sigma_j^2 for per-point errors (tri_set_lightcurve_err),
+                           // nullptr for the reference's scalar sigma (w == 1 in the sums, the
+                           // division by sigma^2 is applied once at the end, likelihoods.py:486)
     int npts;
     int nsamples;
     double sigma;
@@ -562,8 +601,8 @@ TRI_HD double occult_quad(double z, double k, const LimbT& L, int& cls) {
     cls = partial ? 2 : 1;
     if (partial) {
         double iz = fast_rcp(z);
-        kap1 = acos(fmin((1.0 - k2 + z2) * 0.5 * iz, 1.0));
-        kap0 = acos(fmin((k2 + z2 - 1.0) * 0.5 * iz * L.inv_k, 1.0));
+        kap1 = acos_unit(fmin((1.0 - k2 + z2) * 0.5 * iz, 1.0));
+        kap0 = acos_unit(fmin((k2 + z2 - 1.0) * 0.5 * iz * L.inv_k, 1.0));
         double t = 1.0 + z2 - k2;
         le = (k2 * kap0 + kap1 - 0.5 * sqrt(fmax(4.0 * z2 - t * t, 0.0))) * kInvPi;
     }

@@ -81,8 +81,14 @@ class Pending:
     def _result(self):
         if self._out is None:
             eng = self._engine
-            _cabi.check(eng.lib.tri_wait(ctypes.c_int64(self._ticket), self._rr))
-            eng._inflight.remove(self)
+            try:
+                _cabi.check(eng.lib.tri_wait(ctypes.c_int64(self._ticket), self._rr))
+            finally:
+                # the library has released the slot whether or not the wait succeeded: a failed
+                # evaluation must not stay at the head of the queue (every later submit would
+                # wait for its dead ticket again)
+                if self in eng._inflight:
+                    eng._inflight.remove(self)
             out = self._build(self._rr)
             # fewer finite draws than the table has rows: the caller pads the table from the
             # full lnL array, which is only reachable until the next evaluation completes
@@ -144,11 +150,23 @@ class Engine:
         flux = _cabi.f64(flux)
         if time.shape != flux.shape or time.ndim != 1:
             raise ValueError("time and flux must be 1-D arrays of equal length")
-        key = (time.tobytes(), flux.tobytes(), float(sigma), float(exptime), int(nsamples))
-        if key == self._lc_key:
-            return
-        _cabi.check(self.lib.tri_set_lightcurve(_cabi.dptr(time), _cabi.dptr(flux), time.size,
-                                                float(sigma), float(exptime), int(nsamples)))
+        if np.ndim(sigma) == 0:
+            key = (time.tobytes(), flux.tobytes(), float(sigma), float(exptime), int(nsamples))
+            if key == self._lc_key:
+                return
+            _cabi.check(self.lib.tri_set_lightcurve(_cabi.dptr(time), _cabi.dptr(flux),
+                                                    time.size, float(sigma), float(exptime),
+                                                    int(nsamples)))
+        else:   # one error per stamp (tri_set_lightcurve_err)
+            err = _cabi.f64(sigma)
+            if err.shape != time.shape:
+                raise ValueError("per-point errors must have the shape of time")
+            key = (time.tobytes(), flux.tobytes(), err.tobytes(), float(exptime), int(nsamples))
+            if key == self._lc_key:
+                return
+            _cabi.check(self.lib.tri_set_lightcurve_err(_cabi.dptr(time), _cabi.dptr(flux),
+                                                        _cabi.dptr(err), time.size,
+                                                        float(exptime), int(nsamples)))
         self._lc_key = key
 
     # ------------------------------------------------------------------ helpers

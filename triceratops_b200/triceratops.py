@@ -143,6 +143,10 @@ class target:
         keep = ~np.isnan(time) & ~np.isnan(flux_0)
         time = time[keep]
         flux_0 = flux_0[keep]
+        if np.ndim(flux_err_0) != 0:
+            # an error per time stamp (an extension of the reference's scalar flux_err_0, see
+            # tri_set_lightcurve_err): chi^2 is weighted per point, the scalar formulas use the mean
+            flux_err_0 = np.asarray(flux_err_0, dtype=float)[keep]
         filtered = self.stars[self.stars["tdepth"] > 0]
         n_rows = 3 * len(filtered) + 12
         targets = np.zeros(n_rows, dtype=np.dtype("i8"))
