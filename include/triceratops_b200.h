@@ -203,6 +203,74 @@ int tri_last_timing(double* geometry_ms, double* lnl_ms, double* lse_ms, int32_t
 int tri_dev_splev(const double* t, const double* c, int32_t n, int32_t k, const double* x,
                   double* y, int64_t N, void* stream);
 
+/* ---- device sampler (opt-in): one fused kernel per scenario draws the prior samples in HBM and
+ * applies the transforms of priors.py:16-383 / :580-1005, funcs.py:54-140 and the limb-darkening
+ * look-ups of marginal_likelihoods.py, writing the columns tri_submit_*_dev takes.  Every pointer
+ * below is a DEVICE pointer; the small tables are uploaded once by the Python layer. */
+typedef struct {           /* broken power law, inverse CDF (priors.py:54-111) */
+    int32_t nseg;          /* 0: not a draw, `constant` is returned */
+    double constant;
+    double powers[3], amps[3], integrals[3], cum[3], epow[3];   /* epow[k] = edges[k]^(p_k + 1) */
+    double norm;
+} tri_powerlaw;
+
+typedef struct {           /* FITPACK spline (t, c, k) as scipy stores it */
+    const double* t;
+    const double* c;
+    int32_t n, k;
+} tri_spline;
+
+typedef struct {           /* constants of lnprior_bound_TP / lnprior_bound_EB (priors.py:580-1005) */
+    double d_pc;           /* 1000 / plx */
+    double M_eff, M_act;   /* max(M_s, 1) and M_s */
+    double f1, f2, f3, alpha, dlogP, slope, slope2, t2, t3, t4, t5;
+    int32_t first_decade;  /* 1: lnprior_bound_EB, 0: lnprior_bound_TP */
+} tri_bound_prior;
+
+typedef struct {
+    int64_t n;             /* draws to make (this rank's share) */
+    int64_t index0;        /* global index of the first one: the random stream of a draw depends
+                            * on (seed, stream, global index) only, whatever the sharding */
+    uint64_t seed, stream;
+    int32_t kind;          /* 0 TP-type, 1 EB-type */
+    int32_t host;          /* event on: 0 the target, 1 its bound companion (S*), 2 a background
+                            * star (B*) */
+    int32_t diluter;       /* other star in the aperture: 0 none, 1 bound companion (P*, S*),
+                            * 2 background star (D*, B*) */
+    int32_t flatpriors;
+    double P_lo, P_hi;     /* period range [d]; equal: fixed period */
+    double ecc_expo;       /* binaries: eccentricity power-law exponent (priors.py:150-154) */
+    double M_s, R_s, Teff, u1, u2;                  /* the target star */
+    tri_powerlaw rp_hi, rp_lo, q_pl, qc_pl;         /* sample_rp (two mass regimes), sample_q,
+                                                     * sample_q_companion */
+    tri_spline hot_R, cool_R, hot_T, cool_T;        /* stellar_relations (funcs.py:54-79) */
+    tri_spline flux_tess, flux_cc;                  /* flux_relation in the TESS band and in the
+                                                     * contrast-curve band (funcs.py:121-140) */
+    double f_target_tess, f_target_cc;              /* flux_relation(M_s) in those bands */
+    const double *ldc_u1, *ldc_u2;                  /* [27][4] limb darkening at the target's Z
+                                                     * over (Teff, logg) nodes (:945-972) */
+    double Teff_cap;
+    int32_t prior_mode;    /* 0 none, 1 bound companion, 2 background star */
+    int32_t use_cc;        /* a contrast curve was given */
+    int32_t beb_cc_band;   /* BEB with a contrast curve in J/H/K: flux_cc is that band */
+    int32_t cc_n;
+    const double *cc_sep, *cc_con;                  /* contrast curve (or the 2.2" / 1.0 default) */
+    tri_bound_prior bound;
+    double bg_const_prior;                          /* background prior without a contrast curve */
+    const double* molusc_q;                         /* optional [n]: companion mass ratios */
+    int64_t n_comp, idx_hi;                         /* TRILEGAL stars; randint upper bound */
+    const double *bg_mass, *bg_radius, *bg_logg, *bg_teff, *bg_u1, *bg_u2;
+    const double *bg_fr_tess, *bg_dmag_cc, *bg_fr_cc;
+    /* outputs [n] (NULL: not wanted) */
+    double *o_body, *o_ebfr, *o_q, *o_P, *o_inc, *o_ecc, *o_argp, *o_mtot, *o_rhost, *o_u1, *o_u2,
+           *o_cfr, *o_lnprior, *o_mhost, *o_meb;
+    uint8_t* o_mask;
+    int32_t* err_flag;     /* set to 1 if a limb-darkening node lies beyond the grid */
+} tri_sampler_args;
+
+/* Queue the sampler kernel on `stream` (NULL = the CUDA default stream); does not wait. */
+int tri_dev_sample(const tri_sampler_args* args, void* stream);
+
 /* Measured FP64 FMA issue rate of this GPU [DFMA/s] (roofline denominator). */
 int tri_fp64_peak(double* dfma_per_s);
 
@@ -210,6 +278,11 @@ int tri_fp64_peak(double* dfma_per_s);
  * roofline model -- n_stamps, n_interior, n_limb of tri_result -- in the hot loop (about 1.5 %
  * slower); when off those three fields are 0.  bench.py turns it on for one untimed pass. */
 int tri_set_counting(int32_t on);
+
+/* sizeof() of the ABI structs, in the order tri_col, tri_tp_args, tri_eb_args, tri_result,
+ * tri_powerlaw, tri_spline, tri_bound_prior, tri_sampler_args (the first n of them), so that a
+ * binding can verify its own layouts.  Needs no device. */
+int tri_struct_sizes(int64_t* out, int32_t n);
 
 /* SM count of the bound device. */
 int tri_sm_count(int32_t* n);

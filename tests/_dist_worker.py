@@ -37,19 +37,9 @@ def main(out_path):
     cp = dict(prob=tgt.probs.prob.values.copy(), R_p=tgt.probs.R_p.values.copy(),
               inc=tgt.probs.inc.values.copy(), FPP=float(tgt.FPP), u1=np.array(tgt.u1),
               collectives=tgt.collectives)
-    # device-sampler mode: every rank draws its own samples (torch CPU tensors here), the rows
-    # of all scenario branches travel in the call's one exchange
-    import triceratops_b200
-    triceratops_b200.set_sampler("device", seed=5)
-    try:
-        dtgt = calc_probs_small(t, f, s, N=4000, full=True)
-    finally:
-        triceratops_b200.set_sampler("host")
-    dev = dict(lnZ=dtgt.lnZ.copy(), prob=dtgt.probs.prob.values.copy(),
-               R_p=dtgt.probs.R_p.values.copy(), collectives=dtgt.collectives)
     with open(out_path + ".%d" % rank, "wb") as fh:
         pickle.dump(dict(rank=rank, world=world, shard=(lo, hi), tp=tp, eb=eb, ptp=ptp,
-                         lnZ_cp=lnZ_cp, cp=cp, dev=dev), fh)
+                         lnZ_cp=lnZ_cp, cp=cp), fh)
     dist.barrier()
     dist.destroy_process_group()
 

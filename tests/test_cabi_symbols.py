@@ -35,6 +35,13 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_cabi.tri_tp_args) == 8 + 11 * 16 + 8 + 8
     assert ctypes.sizeof(_cabi.tri_eb_args) == 8 + 13 * 16 + 8 + 8
     assert ctypes.sizeof(_cabi.tri_result) == 16 * 8
+    # every struct of the binding against the compiler's own sizeof
+    sizes = (ctypes.c_int64 * 8)()
+    assert _cabi.load().tri_struct_sizes(sizes, 8) == 0
+    mine = [ctypes.sizeof(t) for t in (_cabi.tri_col, _cabi.tri_tp_args, _cabi.tri_eb_args,
+                                       _cabi.tri_result, _cabi.tri_powerlaw, _cabi.tri_spline,
+                                       _cabi.tri_bound_prior, _cabi.tri_sampler_args)]
+    assert list(sizes) == mine
 
 
 def test_calls_before_init_fail_with_state_error():

@@ -1,10 +1,15 @@
-"""Opt-in device sampler (device_priors.py / device_sampler.py): the draws come from a different
-random stream than numpy's, so equivalence with the host mode is statistical.
+"""Opt-in device sampler (csrc/tri_sampler.cuh through device_sampler.py): one fused kernel
+per scenario draws the priors in HBM from Philox streams, so equivalence with the host mode
+(numpy's stream) is statistical.  All tests need the GPU.
 
-CPU part: every column each scenario hands to the engine is captured in both modes and compared
-with a two-sample Kolmogorov-Smirnov test (fixed seeds; all ten scenarios, with and without a
-contrast curve), and the deterministic transforms are checked against the host ones on the same
-deviates.  GPU part: evidences of the two modes agree within their Monte-Carlo scatter."""
+  * every column each scenario hands to the engine is captured in both modes and compared with
+    a two-sample Kolmogorov-Smirnov test (fixed seeds; all ten scenarios, with and without a
+    contrast curve);
+  * the deterministic transforms inside the kernel (stellar / flux relations, limb-darkening
+    look-up, flux-ratio wiring, priors) are recomputed on the host from the kernel's own primary
+    draws with the package's host formulas;
+  * a draw's stream depends on its global index only: two half-size shards equal one call;
+  * evidences of the two modes agree within their Monte-Carlo scatter."""
 import numpy as np
 import pytest
 import torch
@@ -13,16 +18,16 @@ from scipy import stats
 import triceratops_b200
 import triceratops_b200.marginal_likelihoods as ml
 from conftest import TOI465, lnz_calls
-from triceratops_b200 import _dispatch, device_priors as dp, funcs, priors
-from triceratops_b200._ldc import grid_for
+from triceratops_b200 import _dispatch, funcs
+
+pytestmark = pytest.mark.gpu
 
 
 class _Capture:
-    """Stands where the engine stands and keeps the columns of every call."""
-    device = -1
-    torch_device = torch.device("cpu")
+    """Wraps the CUDA engine: keeps the columns of every call, evaluates nothing."""
 
-    def __init__(self):
+    def __init__(self, real):
+        self.real, self.device, self.lib = real, real.device, real.lib
         self.calls = []
 
     def set_lightcurve(self, *a):
@@ -62,15 +67,16 @@ class _Capture:
                                extra_mask=self._np(extra_mask), is_host=companion_is_host))
         return self._res(N)
 
-    def eval_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100):
+    def eval_eb_tensors(self, N, cols, extra_mask=None, companion_is_host=False, n_best=100,
+                        **kw):
         self.calls.append(dict({k: self._np(v) for k, v in cols.items()},
                                extra_mask=self._np(extra_mask), is_host=companion_is_host))
         return self._res(N), self._res(N)
 
 
 @pytest.fixture()
-def capture():
-    cap = _Capture()
+def capture(gpu_engine):
+    cap = _Capture(gpu_engine)
     saved = _dispatch.get_engine
     _dispatch.get_engine = lambda: cap
     yield cap
@@ -78,22 +84,27 @@ def capture():
     triceratops_b200.set_sampler("host")
 
 
-NAMES = ["TTP", "TEB", "PTP", "PTPcc", "PEB", "STP", "STPcc", "SEB", "SEBcc", "DTP", "DTPcc",
-         "DEB", "BTP", "BTPcc", "BEB", "BEBcc"]
+NAMES = ["TTP", "TEB", "PTP", "PTPcc", "PEB", "PEBcc", "STP", "STPcc", "SEB", "SEBcc", "DTP",
+         "DTPcc", "DEB", "DEBcc", "BTP", "BTPcc", "BEB", "BEBcc"]
+
+
+def _both_modes(name, capture, lc, tri, cc, N, seed):
+    calls = lnz_calls(TOI465, N, tri, cc, lc)
+    triceratops_b200.set_sampler("host")
+    np.random.seed(seed)
+    calls[name](ml)
+    host = capture.calls.pop()
+    triceratops_b200.set_sampler("device", seed=seed + 101)
+    calls[name](ml)
+    dev = capture.calls.pop()
+    return host, dev
 
 
 @pytest.mark.parametrize("name", NAMES)
 def test_columns_have_the_same_distributions_in_both_modes(name, capture, toi465_lc,
                                                            trilegal_file, contrast_file):
     N = 60_000
-    calls = lnz_calls(TOI465, N, trilegal_file, contrast_file, toi465_lc)
-    triceratops_b200.set_sampler("host")
-    np.random.seed(101)
-    calls[name](ml)
-    host = capture.calls.pop()
-    triceratops_b200.set_sampler("device", seed=202)
-    calls[name](ml)
-    dev = capture.calls.pop()
+    host, dev = _both_modes(name, capture, toi465_lc, trilegal_file, contrast_file, N, 101)
     assert host["is_host"] == dev["is_host"]
     assert set(host) == set(dev)
     for key in host:
@@ -103,12 +114,17 @@ def test_columns_have_the_same_distributions_in_both_modes(name, capture, toi465
         if h is None or d is None:
             if key == "extra_mask":       # "all true" may be passed as None
                 assert (h is None or np.all(h)) and (d is None or np.all(d)), (name, key)
+            elif key == "lnprior":        # an all-zero prior may be passed as None
+                assert (h is None or not np.any(h)) and (d is None or not np.any(d)), (name, key)
             else:
                 assert h is None and d is None, (name, key)
             continue
         h, d = np.asarray(h, float).ravel(), np.asarray(d, float).ravel()
         if h.size == 1 or d.size == 1:
-            assert h.size == d.size == 1 and np.isclose(h[0], d[0], rtol=1e-12), (name, key)
+            assert np.allclose(np.unique(h), np.unique(d), rtol=1e-12), (name, key)
+            continue
+        if key == "extra_mask":
+            assert abs(h.mean() - d.mean()) < 5 * np.sqrt(0.25 / N) + 1e-3, (name, key)
             continue
         # same share of -inf / excluded entries (binomial tolerance), same body
         for bad in (np.isneginf, lambda v: ~np.isfinite(v)):
@@ -119,69 +135,88 @@ def test_columns_have_the_same_distributions_in_both_modes(name, capture, toi465
         assert p > 1e-4, (name, key, p)
 
 
-def test_transforms_agree_with_host_on_the_same_deviates(contrast_file):
-    rng = np.random.default_rng(0)
-    n = 50_000
-    x = rng.random(n)
-    xt = torch.from_numpy(x.copy())
-    Ms = rng.uniform(0.1, 1.5, n)
-    close = lambda a, b: np.testing.assert_allclose(np.asarray(b), a, rtol=1e-11)  # noqa: E731
-    close(priors.sample_rp(x.copy(), Ms, False), dp.sample_rp(xt, torch.from_numpy(Ms), False))
-    close(priors.sample_inc(x.copy()), dp.sample_inc(xt))
-    for M in (1.3, 0.811, 0.25, 0.08):
-        close(priors.sample_q(x.copy(), M), dp.sample_q(xt, M))
-        close(priors.sample_q_companion(x.copy(), M), dp.sample_q_companion(xt, M))
-    m = rng.uniform(0.05, 3, n)
-    mt = torch.from_numpy(m)
-    a = funcs.stellar_relations(m, np.full(n, 0.9), np.full(n, 5000.))
-    b = dp.stellar_relations(mt, 0.9, 5000.)
-    close(a[0], b[0])
-    close(a[1], b[1])
-    for filt in ("TESS", "J", "H", "K"):
-        close(funcs.flux_relation(m, filt), dp.flux_relation(mt, filt))
-    sep, con = funcs.file_to_contrast_curve(contrast_file)
-    con = np.maximum.accumulate(con) + np.arange(con.size) * 1e-9     # a monotonic curve
-    dm = rng.uniform(0, 12, n)
-    with np.errstate(divide="ignore"):
-        for M in (1.3, 0.811):
-            for host_fn, dev_fn in ((priors.lnprior_bound_TP, dp.lnprior_bound_TP),
-                                    (priors.lnprior_bound_EB, dp.lnprior_bound_EB)):
-                want = host_fn(M, 8.16, dm, sep, con)
-                got = dev_fn(M, 8.16, torch.from_numpy(dm), torch.from_numpy(sep),
-                             torch.from_numpy(con)).numpy()
-                assert np.array_equal(np.isfinite(want), np.isfinite(got))
-                fin = np.isfinite(want)
-                np.testing.assert_allclose(got[fin], want[fin], rtol=1e-10)
-    T, lg = rng.uniform(2800, 9900, n), rng.uniform(3, 5.6, n)
-    a = grid_for("TESS").at_Z_rounded(0.0, T, lg, 10000)
-    b = dp.ldc_at_Z_rounded(grid_for("TESS"), 0.0, torch.from_numpy(T), torch.from_numpy(lg),
-                            10000)
-    assert np.array_equal(a[0], b[0].numpy()) and np.array_equal(a[1], b[1].numpy())
-
-
-def test_eccentricity_samplers_follow_their_laws():
-    torch.manual_seed(3)
-    n = 200_000
-    assert stats.kstest(dp.sample_ecc(n, True, 3.0, "cpu").numpy(), "beta",
-                        args=(0.867, 3.03)).pvalue > 1e-3
-    assert stats.kstest(dp.sample_ecc(n, False, 3.0, "cpu").numpy(), "powerlaw",
-                        args=(0.2,)).pvalue > 1e-3
-    assert stats.kstest(dp.sample_ecc(n, False, 20.0, "cpu").numpy(), "powerlaw",
-                        args=(0.6,)).pvalue > 1e-3
-
-
-def test_result_tables_keep_the_reference_layout(oracle_engine, toi465_lc):
-    t, f, s = toi465_lc
+def test_derived_columns_follow_the_host_formulas(capture, toi465_lc, trilegal_file,
+                                                  contrast_file):
+    """The kernel's transforms against the package's host code, on the kernel's own primary
+    draws: EB radius and flux ratio from the drawn mass ratio (stellar_relations,
+    flux_relation), the companion's flux ratio, radius and limb darkening from its mass ratio
+    (SEB), the bound-companion prior from the flux ratio (PTP, contrast curve in K)."""
+    from triceratops_b200._ldc import grid_for
+    from triceratops_b200.priors import lnprior_bound_TP
+    N = 40_000
+    M, R, T = TOI465["M"], TOI465["R"], TOI465["Teff"]
+    calls = lnz_calls(TOI465, N, trilegal_file, contrast_file, toi465_lc)
     triceratops_b200.set_sampler("device", seed=5)
+    calls["TEB"](ml)
+    c = capture.calls.pop()
+    masses = c["q"] * M
+    radii, _ = funcs.stellar_relations(masses, np.full(N, R), np.full(N, T))
+    np.testing.assert_allclose(c["reb"], radii, rtol=1e-12)
+    f = funcs.flux_relation(masses)
+    np.testing.assert_allclose(c["ebfr"], f / (f + funcs.flux_relation(np.array([M]))),
+                               rtol=1e-11)
+    np.testing.assert_allclose(c["mtot"], M + masses, rtol=1e-14)
+    assert 0 <= c["inc"].min() and c["inc"].max() <= 90 and c["argp"].max() < 360
+
+    calls["SEB"](ml)
+    c = capture.calls.pop()
+    m_comp = c["mtot"] - c["q"] * (c["mtot"] / (1 + c["q"]))     # host mass = mtot / (1 + q)
+    np.testing.assert_allclose(m_comp, c["mtot"] / (1 + c["q"]), rtol=1e-12)
+    r_comp, t_comp = funcs.stellar_relations(m_comp, np.full(N, R), np.full(N, T))
+    np.testing.assert_allclose(c["rhost"], r_comp, rtol=1e-11)
+    fc = funcs.flux_relation(m_comp)
+    np.testing.assert_allclose(c["cfr"], fc / (fc + funcs.flux_relation(np.array([M]))),
+                               rtol=1e-10)
+    logg = np.log10(6.6743e-08 * (m_comp * 1.988409870698051e+33) / (r_comp * 69570000000.0) ** 2)
+    u1, u2 = grid_for("TESS").at_Z_rounded(0.0, t_comp, logg, 13000)
+    np.testing.assert_allclose(c["u1"], u1, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(c["u2"], u2, rtol=0, atol=1e-12)
+
+    calls["PTP"](ml)                      # no contrast curve: the 2.2 arcsec default
+    c = capture.calls.pop()
+    dm = 2.5 * np.log10(c["cfr"] / (1 - c["cfr"]))
+    want = lnprior_bound_TP(M, TOI465["plx"], np.abs(dm), np.array([2.2]), np.array([1.0]))
+    want[want > 0] = 0.0
+    want[dm > 0] = -np.inf
+    np.testing.assert_allclose(c["lnprior"], want, rtol=1e-10, atol=1e-12)
+
+
+def test_streams_depend_on_the_global_draw_index_only(capture, toi465_lc):
+    """Sharding invariance of the sample itself: draws [lo, hi) of a call are the same numbers
+    whether they are made by one rank or by the rank that owns that slice."""
+    from triceratops_b200 import device_sampler as ds
+    t, f, s = toi465_lc
+    args = (t, f, s, 0.00139, 20, 10_000, 1, 0, 0, TOI465["P"], TOI465["M"], TOI465["R"],
+            TOI465["Teff"], (0.4, 0.2), False, "TESS")
+    ds.seed(9)
+    whole = ds._sample(*args)[3]
+    saved = _dispatch.shard_bounds
     try:
-        res, twin = ml.lnZ_TEB(t, f, s, 3.836169, 0.811, 0.84738, 4936.0, 0.0, 1500, True)
+        parts = []
+        for lo, hi in ((0, 4000), (4000, 10_000)):
+            _dispatch.shard_bounds = lambda N, lo=lo, hi=hi: (lo, hi)
+            ds.seed(9)
+            parts.append(ds._sample(*args)[3])
     finally:
-        triceratops_b200.set_sampler("host")
-    for r in (res, twin):
-        assert set(r) == {"M_s", "R_s", "u1", "u2", "P_orb", "inc", "b", "R_p", "ecc", "argp",
-                          "M_EB", "R_EB", "fluxratio_EB", "fluxratio_comp", "lnZ"}
-        assert all(len(r[k]) == 100 for k in r if k != "lnZ")
-    assert np.all(twin["P_orb"] == 2 * 3.836169)
+        _dispatch.shard_bounds = saved
+    for k in ("body", "q", "inc", "ecc", "argp", "ebfr"):
+        joined = torch.cat([p[k] for p in parts])
+        assert torch.equal(joined, whole[k]), k
+
+
+def test_eccentricity_samplers_follow_their_laws(capture, toi465_lc):
+    from triceratops_b200 import device_sampler as ds
+    t, f, s = toi465_lc
+    base = (t, f, s, 0.00139, 20, 200_000)
+    star = (TOI465["P"], TOI465["M"], TOI465["R"], TOI465["Teff"], (0.4, 0.2), False, "TESS")
+    ds.seed(3)
+    ecc = ds._sample(*base, 0, 0, 0, *star)[3]["ecc"].cpu().numpy()
+    assert stats.kstest(ecc, stats.beta(0.867, 3.03).cdf).pvalue > 1e-4
+    ecc = ds._sample(*base, 1, 0, 0, *star)[3]["ecc"].cpu().numpy()
+    assert stats.kstest(ecc, stats.powerlaw(0.2).cdf).pvalue > 1e-4
+    long_P = (20.0,) + star[1:]
+    ecc = ds._sample(*base, 1, 0, 0, *long_P)[3]["ecc"].cpu().numpy()
+    assert stats.kstest(ecc, stats.powerlaw(0.6).cdf).pvalue > 1e-4
 
 
 @pytest.mark.gpu
@@ -238,13 +273,12 @@ def test_device_mode_calc_probs_runs_and_is_reproducible(gpu_engine, toi465_lc, 
     assert np.array_equal(out[0], out[1])      # same seed, same streams, same answer
 
 
-@pytest.mark.gpu
 def test_splev_kernel_matches_scipy(gpu_engine):
-    """tri_dev_splev (one launch per spline evaluation in device mode) against scipy's FITPACK,
-    inside the knot range and extrapolating beyond both ends."""
-    import torch
+    """tri_dev_splev against scipy's FITPACK, inside the knot range and extrapolating beyond
+    both ends (the same de Boor recurrence serves the sampler kernel)."""
+    import ctypes
     from scipy.interpolate import InterpolatedUnivariateSpline, splev as sp_splev
-    from triceratops_b200 import device_priors as dp, funcs
+    from triceratops_b200 import _cabi
     rng = np.random.default_rng(5)
     x = np.concatenate([rng.uniform(0.05, 2.6, 200_000), [0.0, 0.1, 0.63, 2.0, 3.5, -1.0]])
     xd = torch.as_tensor(x, device="cuda")
@@ -255,5 +289,12 @@ def test_splev_kernel_matches_scipy(gpu_engine):
         splines.append(InterpolatedUnivariateSpline(xs, np.sin(xs) + xs ** 2, k=k))
     for spl in splines:
         want = sp_splev(x, spl._eval_args, ext=0)
-        got = dp.splev(spl, xd).cpu().numpy()
+        t, c, k = spl._eval_args
+        td, cd = torch.as_tensor(t, device="cuda"), torch.as_tensor(c, device="cuda")
+        y = torch.empty_like(xd)
+        _cabi.check(gpu_engine.lib.tri_dev_splev(td.data_ptr(), cd.data_ptr(), td.numel(),
+                                                 int(k), xd.data_ptr(), y.data_ptr(),
+                                                 xd.numel(), ctypes.c_void_p(0)))
+        torch.cuda.synchronize()
+        got = y.cpu().numpy()
         np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-13 * np.abs(want).max())

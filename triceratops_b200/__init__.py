@@ -65,9 +65,10 @@ def set_sampler(mode="host", seed=None):
 
     "host" (default): numpy's global RNG in the reference's call order -- a given np.random.seed
         reproduces the reference's draws bit for bit (the parity mode).
-    "device": draws are generated in HBM (torch Philox) and never visit the host; statistically
-        equivalent results, ~10x less wall time per calc_probs (device_sampler.py).  `seed`
-        makes the device streams reproducible.
+    "device": draws are generated in HBM by one fused kernel per scenario (Philox streams,
+        csrc/tri_sampler.cuh) and never visit the host; statistically equivalent results, a
+        calc_probs at N = 1e6 in the time of its GPU work (device_sampler.py).  `seed` makes the
+        device streams reproducible.
     """
     from . import marginal_likelihoods
     if mode not in ("host", "device"):

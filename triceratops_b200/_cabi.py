@@ -53,13 +53,58 @@ class tri_result(ctypes.Structure):
                 ("top_idx", ctypes.c_void_p), ("top_lnL", ctypes.c_void_p)]
 
 
+class tri_powerlaw(ctypes.Structure):
+    _fields_ = [("nseg", ctypes.c_int32), ("constant", ctypes.c_double),
+                ("powers", ctypes.c_double * 3), ("amps", ctypes.c_double * 3),
+                ("integrals", ctypes.c_double * 3), ("cum", ctypes.c_double * 3),
+                ("epow", ctypes.c_double * 3), ("norm", ctypes.c_double)]
+
+
+class tri_spline(ctypes.Structure):
+    _fields_ = [("t", ctypes.c_void_p), ("c", ctypes.c_void_p), ("n", ctypes.c_int32),
+                ("k", ctypes.c_int32)]
+
+
+class tri_bound_prior(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_double) for n in ("d_pc", "M_eff", "M_act", "f1", "f2", "f3",
+                                                "alpha", "dlogP", "slope", "slope2", "t2", "t3",
+                                                "t4", "t5")]
+                + [("first_decade", ctypes.c_int32)])
+
+
+class tri_sampler_args(ctypes.Structure):
+    _fields_ = (
+        [("n", ctypes.c_int64), ("index0", ctypes.c_int64), ("seed", ctypes.c_uint64),
+         ("stream", ctypes.c_uint64), ("kind", ctypes.c_int32), ("host", ctypes.c_int32),
+         ("diluter", ctypes.c_int32), ("flatpriors", ctypes.c_int32)]
+        + [(n, ctypes.c_double) for n in ("P_lo", "P_hi", "ecc_expo", "M_s", "R_s", "Teff", "u1",
+                                          "u2")]
+        + [(n, tri_powerlaw) for n in ("rp_hi", "rp_lo", "q_pl", "qc_pl")]
+        + [(n, tri_spline) for n in ("hot_R", "cool_R", "hot_T", "cool_T", "flux_tess",
+                                     "flux_cc")]
+        + [("f_target_tess", ctypes.c_double), ("f_target_cc", ctypes.c_double),
+           ("ldc_u1", ctypes.c_void_p), ("ldc_u2", ctypes.c_void_p), ("Teff_cap", ctypes.c_double),
+           ("prior_mode", ctypes.c_int32), ("use_cc", ctypes.c_int32),
+           ("beb_cc_band", ctypes.c_int32), ("cc_n", ctypes.c_int32),
+           ("cc_sep", ctypes.c_void_p), ("cc_con", ctypes.c_void_p), ("bound", tri_bound_prior),
+           ("bg_const_prior", ctypes.c_double), ("molusc_q", ctypes.c_void_p),
+           ("n_comp", ctypes.c_int64), ("idx_hi", ctypes.c_int64)]
+        + [(n, ctypes.c_void_p) for n in ("bg_mass", "bg_radius", "bg_logg", "bg_teff", "bg_u1",
+                                          "bg_u2", "bg_fr_tess", "bg_dmag_cc", "bg_fr_cc")]
+        + [("o_" + n, ctypes.c_void_p) for n in ("body", "ebfr", "q", "P", "inc", "ecc", "argp",
+                                                 "mtot", "rhost", "u1", "u2", "cfr", "lnprior",
+                                                 "mhost", "meb")]
+        + [("o_mask", ctypes.c_void_p), ("err_flag", ctypes.c_void_p)])
+
+
 # every symbol include/triceratops_b200.h declares
 EXPORTS = ("tri_init", "tri_shutdown", "tri_last_error", "tri_set_lightcurve", "tri_eval_tp",
            "tri_eval_eb", "tri_eval_tp_dev", "tri_eval_eb_dev", "tri_lnl_tp", "tri_lnl_eb",
            "tri_simulate_tp", "tri_simulate_eb",
            "tri_fetch_lnl", "tri_log_mean_exp", "tri_last_timing", "tri_fp64_peak", "tri_sm_count",
            "tri_submit_tp", "tri_submit_eb", "tri_submit_tp_dev", "tri_submit_eb_dev", "tri_wait",
-           "tri_dev_splev", "tri_set_counting", "tri_set_lightcurve_err")
+           "tri_dev_splev", "tri_set_counting", "tri_set_lightcurve_err", "tri_dev_sample",
+           "tri_struct_sizes")
 
 _lib = None
 
@@ -117,6 +162,8 @@ def load():
                                   ctypes.POINTER(ctypes.c_int32)]
     L.tri_fp64_peak.argtypes = [c_double_p]
     L.tri_set_counting.argtypes = [ctypes.c_int32]
+    L.tri_dev_sample.argtypes = [ctypes.POINTER(tri_sampler_args), ctypes.c_void_p]
+    L.tri_struct_sizes.argtypes = [ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]
     L.tri_sm_count.argtypes = [ctypes.POINTER(ctypes.c_int32)]
     _lib = L
     return L

@@ -16,6 +16,7 @@
 
 #include "../../include/triceratops_b200.h"
 #include "tri_kernels.cuh"
+#include "tri_sampler.cuh"
 
 namespace {
 
@@ -665,6 +666,15 @@ int tri_shutdown(void) {
     return TRI_OK;
 }
 
+int tri_struct_sizes(int64_t* out, int32_t n) {
+    const int64_t sizes[8] = {sizeof(tri_col), sizeof(tri_tp_args), sizeof(tri_eb_args),
+                              sizeof(tri_result), sizeof(tri_powerlaw), sizeof(tri_spline),
+                              sizeof(tri_bound_prior), sizeof(tri_sampler_args)};
+    if (!out || n < 0 || n > 8) return fail(TRI_EINVAL, "bad argument");
+    for (int i = 0; i < n; ++i) out[i] = sizes[i];
+    return TRI_OK;
+}
+
 int tri_set_counting(int32_t on) {
     int rc = need_ready(false);
     if (rc) return rc;
@@ -1216,6 +1226,25 @@ int tri_dev_splev(const double* t, const double* c, int32_t n, int32_t k, const 
         case 4: splev_kernel<4><<<blocks, 256, 0, s>>>(t, c, n, x, y, N); break;
         default: splev_kernel<5><<<blocks, 256, 0, s>>>(t, c, n, x, y, N); break;
     }
+    CU(cudaGetLastError());
+    return TRI_OK;
+}
+
+int tri_dev_sample(const tri_sampler_args* a, void* stream) {
+    int rc = need_ready(false);
+    if (rc) return rc;
+    if (!a || a->n < 0) return fail(TRI_EINVAL, "bad argument");
+    if (a->n == 0) return TRI_OK;
+    if (!a->o_body || !a->o_P || !a->o_inc || !a->o_ecc || !a->o_argp || !a->o_mtot)
+        return fail(TRI_EINVAL, "a required output column is NULL");
+    if ((a->diluter == 2 && (!a->bg_fr_tess || a->idx_hi <= 0)) ||
+        (a->host == 1 && (!a->ldc_u1 || !a->ldc_u2 || !a->err_flag)) ||
+        (a->prior_mode != 0 && (!a->cc_sep || !a->cc_con || a->cc_n < 1)))
+        return fail(TRI_EINVAL, "a table the scenario needs is NULL");
+    CU(cudaSetDevice(g.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int blocks = (int)std::min<int64_t>((a->n + 255) / 256, (int64_t)g.sm_count * 8);
+    sampler_kernel<<<blocks, 256, 0, s>>>(*a);
     CU(cudaGetLastError());
     return TRI_OK;
 }
