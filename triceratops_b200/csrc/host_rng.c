@@ -131,6 +131,14 @@ int trih_mt_randint(uint32_t* key, int32_t* pos, int64_t low, uint32_t rng, int6
  * _fastrng.py compare them.
  * ------------------------------------------------------------------------------------------- */
 #include <math.h>
+#include <stdio.h>
+#include <time.h>
+
+static double now_s(void) {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return t.tv_sec + 1e-9 * t.tv_nsec;
+}
 
 static inline double dbl_at(const uint32_t* w, int64_t m) {
     uint32_t a = temper(w[2 * m]) >> 5, b = temper(w[2 * m + 1]) >> 6;
@@ -228,6 +236,9 @@ int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ga
     if (!(a > 0.0 && a < 1.0 && b > 1.0) || n < 0) return -3;
     if (n == 0) return 0;
     if (nthreads < 1) nthreads = 1;
+    const int trace = getenv("TRI_B200_RNG_TRACE") != NULL;
+    const double t_start = now_s();
+    double t_pilot = 0, t_extend = 0, t_walk = 0;
     beta_ctx C;
     C.a = a;
     C.bb = b - 1. / 3.;
@@ -246,6 +257,7 @@ int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ga
         while (k < n && walk_beta(&C, &S, &v) == 0) k++;
         if (k >= 64) per = (double)S.m / (double)k;
     }
+    t_pilot = now_s();
     /* the stream: estimated need + 2 % + slack for the sequential tail */
     const int64_t est = (int64_t)(per * (double)n * 1.02) + 4096;
     const int64_t cap = est + 65536;
@@ -258,6 +270,7 @@ int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ga
     mt_extend(raw, nblocks);
     C.w = raw + *pos;
     C.cap = cap;
+    t_extend = now_s();
 
     int nchunks = (int)(n / 16384);
     if (nchunks > 8 * nthreads) nchunks = 8 * nthreads;
@@ -267,30 +280,51 @@ int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ga
     const walk_state entry = {0, *has_gauss ? SRC_ENTRY : SRC_NONE, *has_gauss ? *gauss : 0.0};
     int rc = 0;
 
+    /* (position + [a gaussian is cached]) mod 2 never changes along a walk: a sample consumes
+     * 2 doubles per gamma(a) attempt, 2 per polar attempt and 1 per Marsaglia-Tsang attempt,
+     * and every Marsaglia-Tsang attempt also toggles the cache.  A guess of the other class
+     * could never meet the true walk, so the chunks start on the true walk's class.  (The one
+     * exception -- a gaussian below -1/c = -4.9 is redrawn without a uniform, 4e-7 per sample --
+     * flips the class: the stitcher notices and the remaining chunks are walked again.) */
+    int cls = (int)((entry.m + (entry.src != SRC_NONE)) & 1);
+    int first = 0, t = 0;
+    walk_state S = entry;             /* the true walk (stitcher) */
+    int64_t count = 0;
+walk_again:
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-    for (int t = 0; t < nchunks; t++) {
+    for (int tc = first; tc < nchunks; tc++) {
+        const int t = tc;
         chunk_rec* r = &R[t];
         const int64_t p0 = (est * t) / nchunks, p1 = (est * (t + 1)) / nchunks;
-        r->cap = (int64_t)((double)(p1 - p0) / per * 1.25) + 1024;
-        r->m0 = (int64_t*)malloc((size_t)r->cap * sizeof(int64_t));
-        r->src0 = (int64_t*)malloc((size_t)r->cap * sizeof(int64_t));
-        r->val = (double*)malloc((size_t)r->cap * sizeof(double));
+        if (!r->m0) {
+            r->cap = (int64_t)((double)(p1 - p0) / per * 1.25) + 1024;
+            r->m0 = (int64_t*)malloc((size_t)r->cap * sizeof(int64_t));
+            r->src0 = (int64_t*)malloc((size_t)r->cap * sizeof(int64_t));
+            r->val = (double*)malloc((size_t)r->cap * sizeof(double));
+        }
+        r->n = 0;
+        r->rc = 0;
         if (!r->m0 || !r->src0 || !r->val) { r->rc = -1; continue; }
-        walk_state S = entry;
-        if (t > 0) { S.m = p0; S.src = SRC_NONE; S.cache = 0.0; }   /* the guess */
-        while (S.m < p1 && r->n < r->cap && r->n < n) {
-            r->m0[r->n] = S.m;
-            r->src0[r->n] = S.src;
-            if (walk_beta(&C, &S, &r->val[r->n])) { r->rc = -2; break; }
+        walk_state W = entry;
+        if (t > 0) {                                   /* the guess: a sample starts here */
+            W.m = p0 + (((p0 & 1) != cls) ? 1 : 0);
+            W.src = SRC_NONE;
+            W.cache = 0.0;
+        }
+        while (W.m < p1 && r->n < r->cap && r->n < n) {
+            r->m0[r->n] = W.m;
+            r->src0[r->n] = W.src;
+            if (walk_beta(&C, &W, &r->val[r->n])) { r->rc = -2; break; }
             r->n++;
         }
-        r->end = S;
+        r->end = W;
     }
+    if (first > 0) goto stitch_resume;
 
+    t_walk = now_s();
     /* ---- stitch the chunks in order */
-    walk_state S = entry;
-    int64_t count = 0;
-    for (int t = 0; t < nchunks && count < n && rc == 0; t++) {
+stitch_resume:
+    for (; t < nchunks && count < n && rc == 0; t++) {
         chunk_rec* r = &R[t];
         if (r->rc == -1) { rc = -1; break; }
         const int64_t p1 = (est * (t + 1)) / nchunks;
@@ -303,7 +337,16 @@ int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ga
             if (walk_beta(&C, &S, &out[count])) { rc = -2; break; }
             count++;
         }
-        if (rc || !merged) continue;
+        if (rc) continue;
+        if (!merged) {
+            const int now = (int)((S.m + (S.src != SRC_NONE)) & 1);
+            if (now != cls && t + 1 < nchunks && count < n) {   /* the class flipped (see above) */
+                cls = now;
+                first = ++t;
+                goto walk_again;
+            }
+            continue;
+        }
         int64_t take = r->n - k;
         /* a chunk whose walk stopped early (record full / stream end) is used up to there */
         if (take > n - count) take = n - count;
@@ -338,6 +381,11 @@ int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ga
         memcpy(key, raw + blk * MT_N, MT_N * sizeof(uint32_t));
         *pos = (int32_t)off;
     }
+    if (trace)
+        fprintf(stderr, "beta n=%lld threads=%d chunks=%d: pilot %.2f extend %.2f walk %.2f "
+                "stitch %.2f ms (%.2f doubles/sample)\n", (long long)n, nthreads, nchunks,
+                (t_pilot - t_start) * 1e3, (t_extend - t_pilot) * 1e3, (t_walk - t_extend) * 1e3,
+                (now_s() - t_walk) * 1e3, per);
     for (int t = 0; t < nchunks; t++) { free(R[t].m0); free(R[t].src0); free(R[t].val); }
     free(R);
     free(raw);

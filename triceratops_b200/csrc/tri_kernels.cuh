@@ -809,22 +809,38 @@ __global__ void __launch_bounds__(kFinThreads) finalize_kernel(FinalizeArgs F) {
     const int64_t top_cap = F.top_cap[br];
     const bool two = gridDim.x > 1;
     // one pass over the work items: above the bucket -> output; in the bucket -> candidates
-    for (int64_t e = tid; e < n_items; e += kFinThreads) {
-        const int64_t slot = e < n_front ? e : F.cap - 1 - (e - n_front);
-        const int64_t item = F.items[slot];
-        if (two && (int)(item & 1) != br) continue;
-        const double v = F.cval[slot];
-        if (!isfinite(v)) continue;
-        const unsigned bin = (unsigned)(topk_key(v) >> 48);
-        if (bin > bucket) {
-            unsigned pos = atomicAdd(&sh_nout, 1u);
-            if ((int64_t)pos < top_cap) { out_idx[pos] = item >> 1; out_val[pos] = v; }
-        } else if (bin == bucket) {
-            unsigned pos = atomicAdd(&sh_ncand, 1u);
-            if (pos < (unsigned)kFinCand) {
-                Composite c = make_comp(v, item >> 1);
-                cand_hi[pos] = c.hi;
-                cand_lo[pos] = c.lo;
+    // (four independent loads in flight per thread: the pass is L2-latency bound)
+    for (int64_t base = tid; base < n_items; base += 4 * kFinThreads) {
+        int64_t item[4];
+        double val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t e = base + (int64_t)u * kFinThreads;
+            item[u] = -1;
+            val[u] = 0.0;
+            if (e < n_items) {
+                const int64_t slot = e < n_front ? e : F.cap - 1 - (e - n_front);
+                item[u] = F.items[slot];
+                val[u] = F.cval[slot];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (item[u] < 0) continue;
+            if (two && (int)(item[u] & 1) != br) continue;
+            const double v = val[u];
+            if (!isfinite(v)) continue;
+            const unsigned bin = (unsigned)(topk_key(v) >> 48);
+            if (bin > bucket) {
+                unsigned pos = atomicAdd(&sh_nout, 1u);
+                if ((int64_t)pos < top_cap) { out_idx[pos] = item[u] >> 1; out_val[pos] = v; }
+            } else if (bin == bucket) {
+                unsigned pos = atomicAdd(&sh_ncand, 1u);
+                if (pos < (unsigned)kFinCand) {
+                    Composite c = make_comp(v, item[u] >> 1);
+                    cand_hi[pos] = c.hi;
+                    cand_lo[pos] = c.lo;
+                }
             }
         }
     }
