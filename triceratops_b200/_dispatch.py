@@ -593,6 +593,16 @@ def scenario_threads():
         return 4
 
 
+def gil_switch_interval():
+    """Interpreter switch interval [s] while calc_probs runs its scenario threads
+    (TRI_B200_SWITCH_INTERVAL, default 0.2 ms; Python's own default is 5 ms)."""
+    import os
+    try:
+        return max(1e-5, float(os.environ.get("TRI_B200_SWITCH_INTERVAL", "0.0002")))
+    except ValueError:
+        return 0.0002
+
+
 # ---- device-sampler mode: every rank owns its own draws --------------------------------------
 class LocalBranch:
     """This rank's share of a branch: evidence record and its best LOCAL draws."""

@@ -34,6 +34,23 @@ def _n_threads():
     return max(1, min(cores // ranks, 32))
 
 
+def _tune_malloc():
+    """TRI_B200_MALLOC_TUNE=1: keep large host arrays in glibc's heap instead of fresh mmap
+    regions, so that the 8 MB draw columns of consecutive scenarios reuse already-faulted pages
+    (a first-touch page fault per 4 KB is ~40 % of a bulk `rand(1e6)`).  Off by default: it is a
+    process-wide allocator setting and keeps freed memory in the process."""
+    if os.environ.get("TRI_B200_MALLOC_TUNE") != "1":
+        return False
+    try:
+        libc = ctypes.CDLL("libc.so.6")
+        M_TRIM_THRESHOLD, M_MMAP_THRESHOLD = -1, -3
+        return bool(libc.mallopt(M_MMAP_THRESHOLD, 1 << 30)
+                    and libc.mallopt(M_TRIM_THRESHOLD, (1 << 31) - 1))
+    except OSError:
+        return False
+
+
+MALLOC_TUNED = _tune_malloc()
 N_THREADS = _n_threads()
 _pool = ThreadPoolExecutor(N_THREADS) if N_THREADS > 1 else None
 _lib = None

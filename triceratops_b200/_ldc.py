@@ -27,6 +27,7 @@ class LdcGrid:
         self.loggs = np.array(df.logg, dtype=float)
         self.u1s = np.array(df[col_u1], dtype=float)
         self.u2s = np.array(df[col_u2], dtype=float)
+        self._nearest_cache = {}
         self._uZ = _first_occurrence_unique(self.Zs)
         self._uT = _first_occurrence_unique(self.Teffs)
         self._ug = _first_occurrence_unique(self.loggs)
@@ -40,6 +41,12 @@ class LdcGrid:
 
     # ---- target star: nearest node in (Z, Teff, logg)         marginal_likelihoods.py:90-98
     def nearest(self, Z, Teff, logg):
+        key = (float(Z), float(Teff), float(logg))
+        if key not in self._nearest_cache:      # (asked for by every scenario of a target)
+            self._nearest_cache[key] = self._nearest(Z, Teff, logg)
+        return self._nearest_cache[key]
+
+    def _nearest(self, Z, Teff, logg):
         this_Z = self.Zs[np.argmin(np.abs(self.Zs - Z))]
         this_Teff = self.Teffs[np.argmin(np.abs(self.Teffs - Teff))]
         this_logg = self.loggs[np.argmin(np.abs(self.loggs - logg))]

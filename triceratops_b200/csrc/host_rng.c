@@ -44,6 +44,21 @@ CLONES static void mt_extend(uint32_t* raw, int64_t nblocks) {
     }
 }
 
+/* Grow-only scratch for the raw state words, one per calling thread: a fresh 8-40 MB block per
+ * call would be page-faulted in again every time (a third of a bulk rand(1e6)). */
+static __thread uint32_t* t_raw = NULL;
+static __thread size_t t_raw_cap = 0;
+
+static uint32_t* raw_scratch(size_t words) {
+    if (words > t_raw_cap) {
+        free(t_raw);
+        t_raw_cap = words + words / 8;
+        t_raw = (uint32_t*)malloc(t_raw_cap * sizeof(uint32_t));
+        if (!t_raw) t_raw_cap = 0;
+    }
+    return t_raw;
+}
+
 static inline uint32_t temper(uint32_t y) {
     y ^= (y >> 11);
     y ^= (y << 7) & 0x9d2c5680u;
@@ -66,7 +81,7 @@ int trih_mt_rand(uint32_t* key, int32_t* pos, double* out, int64_t n) {
     const int64_t need = 2 * n;
     const int64_t have = MT_N - *pos;                       /* words left in the current key */
     const int64_t nblocks = need > have ? (need - have + MT_N - 1) / MT_N : 0;
-    uint32_t* raw = (uint32_t*)malloc((size_t)(nblocks + 1) * MT_N * sizeof(uint32_t) + 64);
+    uint32_t* raw = raw_scratch((size_t)(nblocks + 1) * MT_N + 16);
     if (!raw) return -1;
     memcpy(raw, key, MT_N * sizeof(uint32_t));
     mt_extend(raw, nblocks);
@@ -76,7 +91,6 @@ int trih_mt_rand(uint32_t* key, int32_t* pos, double* out, int64_t n) {
     if (off == 0 && blk > 0) { blk -= 1; off = MT_N; }      /* numpy regenerates lazily */
     memcpy(key, raw + blk * MT_N, MT_N * sizeof(uint32_t));
     *pos = (int32_t)off;
-    free(raw);
     return 0;
 }
 
@@ -264,7 +278,7 @@ int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ga
     const int64_t need = 2 * cap;
     const int64_t have = MT_N - *pos;
     const int64_t nblocks = need > have ? (need - have + MT_N - 1) / MT_N : 0;
-    uint32_t* raw = (uint32_t*)malloc((size_t)(nblocks + 1) * MT_N * sizeof(uint32_t) + 64);
+    uint32_t* raw = raw_scratch((size_t)(nblocks + 1) * MT_N + 16);
     if (!raw) return -1;
     memcpy(raw, key, MT_N * sizeof(uint32_t));
     mt_extend(raw, nblocks);
@@ -276,7 +290,7 @@ int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ga
     if (nchunks > 8 * nthreads) nchunks = 8 * nthreads;
     if (nchunks < 1) nchunks = 1;
     chunk_rec* R = (chunk_rec*)calloc((size_t)nchunks, sizeof(chunk_rec));
-    if (!R) { free(raw); return -1; }
+    if (!R) return -1;
     const walk_state entry = {0, *has_gauss ? SRC_ENTRY : SRC_NONE, *has_gauss ? *gauss : 0.0};
     int rc = 0;
 
@@ -388,6 +402,5 @@ stitch_resume:
                 (now_s() - t_walk) * 1e3, per);
     for (int t = 0; t < nchunks; t++) { free(R[t].m0); free(R[t].src0); free(R[t].val); }
     free(R);
-    free(raw);
     return rc;
 }

@@ -54,8 +54,11 @@ def _periods(P_orb, N):
         P = _fastrng.uniform(P_orb[0], P_orb[-1], N)
         return P, np.mean(P)
     # np.mean(np.full(N, P)) is what the reference hands to sample_ecc; it can differ from P in
-    # the last bits, which only matters at the P <= 10 switch, so take the same route
-    return float(P_orb), np.mean(np.full(N, P_orb))
+    # the last bits, which only matters at the P <= 10 switch: take the same route there, and
+    # spare the generator-holding thread two 8 MB passes everywhere else
+    if abs(float(P_orb) - 10.0) < 1e-6:
+        return float(P_orb), np.mean(np.full(N, P_orb))
+    return float(P_orb), float(P_orb)
 
 
 def _take(x, idx):

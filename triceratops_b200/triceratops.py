@@ -14,6 +14,7 @@ from an online session), optionally its `pix_coords`, and a saved TRILEGAL file.
 """
 import collections
 import functools
+import sys
 import warnings
 
 import numpy as np
@@ -215,6 +216,11 @@ class target:
 
         follower = group is not None and group.scatter and not group.is_root
         ok = False
+        # the thread that holds numpy's generator hands the GIL back and forth with the
+        # scenario threads ~150 times per call: a short switch interval keeps those hand-overs
+        # from costing 5 ms each
+        switch_interval = sys.getswitchinterval()
+        sys.setswitchinterval(_dispatch.gil_switch_interval())
         try:
             with _dispatch.deferring():
                 for i, ID in enumerate(filtered["ID"].values if not follower else ()):
@@ -281,6 +287,7 @@ class target:
                 ok = True
         finally:
             chain.close()
+            sys.setswitchinterval(switch_interval)
             try:
                 if group is not None and group.scatter and group.is_root:
                     group.finish_root(error=not ok)
