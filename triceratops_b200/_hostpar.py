@@ -29,8 +29,11 @@ def _n_threads():
         cores = len(os.sched_getaffinity(0))
     except AttributeError:  # pragma: no cover
         cores = os.cpu_count() or 1
-    # one process per GPU: the ranks of a node share its cores
+    # one process per GPU: the ranks of a node share its cores.  With numpy's draws rank 0 makes
+    # them for every rank (the others wait in the scatter), so it takes what the others leave
     ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    if ranks > 1 and os.environ.get("LOCAL_RANK", "0") == "0":
+        return max(1, min(cores - (ranks - 1), 32))
     return max(1, min(cores // ranks, 32))
 
 
