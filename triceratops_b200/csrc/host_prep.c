@@ -61,3 +61,22 @@ int trih_splev(const double* t, int n, const double* c, int k, const double* x, 
     }
     return 0;
 }
+
+/* out[i] = tab[idx[i]]: the gather behind `property_of_background_star[idxs]` (reference
+ * marginal_likelihoods.py:1463-1480 and alike, ~30 of them per calc_probs).  numpy's fancy
+ * indexing does this single-threaded while holding the GIL, which stalls the thread that is
+ * drawing the next scenario's priors; here it runs without the GIL over the caller's threads.
+ * Returns -1 (nothing written past the first bad element's chunk) if an index is out of range. */
+int trih_take_f64(const double* tab, int64_t ntab, const int64_t* idx, double* out, int64_t n,
+                  int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    int bad = 0;
+#pragma omp parallel for schedule(static) num_threads(nthreads) reduction(| : bad)
+    for (int64_t i = 0; i < n; i++) {
+        int64_t j = idx[i];
+        if (j < 0) j += ntab;                  /* numpy's negative indices */
+        if (j < 0 || j >= ntab) { bad |= 1; continue; }
+        out[i] = tab[j];
+    }
+    return bad ? -1 : 0;
+}

@@ -75,10 +75,19 @@ def renorm_flux(flux, flux_err, star_fluxratio: float):
     return (flux - (1 - star_fluxratio)) / star_fluxratio, flux_err / star_fluxratio
 
 
+_contrast_cache = {}
+
+
 def file_to_contrast_curve(contrast_curve_file: str):
     """(separations [arcsec], |contrasts| [mag]) from a two-column CSV (funcs.py:203-219)."""
-    data = np.loadtxt(contrast_curve_file, delimiter=',')
-    return data.T[0], np.abs(data.T[1])
+    st = os.stat(contrast_curve_file)
+    key = (os.path.abspath(contrast_curve_file), st.st_mtime_ns, st.st_size)
+    if key not in _contrast_cache:      # (every chunk of every P*/S*/D*/B* scenario asks)
+        if len(_contrast_cache) > 8:
+            _contrast_cache.clear()
+        data = np.loadtxt(contrast_curve_file, delimiter=',')
+        _contrast_cache[key] = (data.T[0].copy(), np.abs(data.T[1]))
+    return _contrast_cache[key]
 
 
 def separation_at_contrast(delta_mags, separations, contrasts):

@@ -25,6 +25,7 @@ import numpy as np
 from pandas import read_csv
 
 from . import _dispatch, _fastrng
+from . import _hostpar
 from ._constants import G, Msun, Rsun, pi
 from ._ldc import grid_for
 from .funcs import (file_to_contrast_curve, flux_relation, stellar_relations, trilegal_results)
@@ -65,7 +66,7 @@ def _take(x, idx):
     """x[idx] for per-draw arrays, np.full for broadcast scalars."""
     if np.ndim(x) == 0:
         return np.full(len(idx), x)
-    return x[idx]
+    return _hostpar.take(x, idx)       # (large float64 gathers run without the GIL)
 
 
 def _logg(M, R):
@@ -104,9 +105,18 @@ class _PlanetDraws:
         self.eccs = _draw_ecc(N, True, P_mean)
         self.x_w = _fastrng.rand(N)
 
+    @staticmethod
+    def transform(x_rp, x_inc, x_w, host_masses, flatpriors):
+        """(rps, incs, argps) of a chunk of deviates; host_masses per draw or one value."""
+        if np.ndim(host_masses) == 0:
+            host_masses = np.full(len(x_rp), host_masses)
+        return sample_rp(x_rp, host_masses, flatpriors), sample_inc(x_inc), sample_w(x_w)
+
     def finish(self, host_masses, flatpriors):
-        return (sample_rp(self.x_rp, host_masses, flatpriors), sample_inc(self.x_inc), self.eccs,
-                sample_w(self.x_w))
+        rps, incs, argps = _hostpar.pmap_block(
+            lambda x_rp, x_inc, x_w, m: self.transform(x_rp, x_inc, x_w, m, flatpriors),
+            len(self.x_rp), self.x_rp, self.x_inc, self.x_w, host_masses)
+        return rps, incs, self.eccs, argps
 
 
 def _draw_planet(N, host_masses, flatpriors, P_mean):
@@ -123,7 +133,10 @@ class _BinaryDraws:
         self.x_w = _fastrng.rand(N)
 
     def finish(self, M_s):
-        return sample_inc(self.x_inc), sample_q(self.x_q, M_s), self.eccs, sample_w(self.x_w)
+        incs, qs, argps = _hostpar.pmap_block(
+            lambda x_inc, x_q, x_w: (sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)),
+            len(self.x_inc), self.x_inc, self.x_q, self.x_w)
+        return incs, qs, self.eccs, argps
 
 
 class _CompanionDraw:
@@ -297,7 +310,7 @@ def lnZ_TTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     draws = _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
-    rps, incs, eccs, argps = draws.finish(np.full(N, M_s), flatpriors)
+    rps, incs, eccs, argps = draws.finish(M_s, flatpriors)
     return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, 0.0, None, None, False)
 
 
@@ -321,11 +334,16 @@ def lnZ_TEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     draws = _BinaryDraws(N, P_mean)
     _dispatch.rng_done()
-    incs, qs, eccs, argps = draws.finish(M_s)
-    masses = qs * M_s
-    radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
-    fluxratios = _fluxratio(masses, M_s)
-    return _run_eb(N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses, radii,
+
+    def block(x_inc, x_q, x_w):
+        incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
+        masses = qs * M_s
+        radii, _ = stellar_relations(masses, np.full(len(qs), R_s), np.full(len(qs), Teff))
+        return incs, qs, argps, masses, radii, _fluxratio(masses, M_s), M_s + masses
+
+    incs, qs, argps, masses, radii, fluxratios, mtot = _hostpar.pmap_block(
+        block, N, draws.x_inc, draws.x_q, draws.x_w)
+    return _run_eb(N, M_s, R_s, u1, u2, P, mtot, incs, qs, draws.eccs, argps, masses, radii,
                    fluxratios, 0.0, None, None, False, scalar_loop=not parallel)
 
 
@@ -350,19 +368,25 @@ def lnZ_PTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     # deterministic and may overlap the next scenario's draws
     comp, draws = _CompanionDraw(N, molusc_file), _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
-    qs_comp = comp.finish(M_s)
-    rps, incs, eccs, argps = draws.finish(np.full(N, M_s), flatpriors)
-    masses_comp = qs_comp * M_s
-    fluxratios_comp = _fluxratio(masses_comp, M_s)
 
-    def cc_term():
-        fr = _fluxratio(masses_comp, M_s, filt)
-        return fr / (1 - fr)
+    def block(qs_comp, x_rp, x_inc, x_w):
+        rps, incs, argps = draws.transform(x_rp, x_inc, x_w, M_s, flatpriors)
+        masses_comp = qs_comp * M_s
+        fluxratios_comp = _fluxratio(masses_comp, M_s)
 
-    lnprior = _bound_prior(lnprior_bound_TP, M_s, plx, N, molusc_file, contrast_curve_file,
-                           fluxratios_comp / (1 - fluxratios_comp), cc_term)
-    return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, fluxratios_comp,
-                   lnprior, qs_comp != 0.0, False)
+        def cc_term():
+            fr = _fluxratio(masses_comp, M_s, filt)
+            return fr / (1 - fr)
+
+        lnprior = _bound_prior(lnprior_bound_TP, M_s, plx, len(qs_comp), molusc_file,
+                               contrast_curve_file, fluxratios_comp / (1 - fluxratios_comp),
+                               cc_term)
+        return rps, incs, argps, fluxratios_comp, lnprior, qs_comp != 0.0
+
+    rps, incs, argps, fluxratios_comp, lnprior, extra = _hostpar.pmap_block(
+        block, N, comp.finish(M_s), draws.x_rp, draws.x_inc, draws.x_w)
+    return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, draws.eccs, argps, fluxratios_comp,
+                   lnprior, extra, False)
 
 
 def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
@@ -383,28 +407,37 @@ def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     u1, u2 = grid_for(mission).nearest(Z, Teff, _logg(M_s, R_s))
     draws, comp = _BinaryDraws(N, P_mean), _CompanionDraw(N, molusc_file)
     _dispatch.rng_done()
-    incs, qs, eccs, argps = draws.finish(M_s)
-    qs_comp = comp.finish(M_s)
-    masses = qs * M_s
-    radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
-    fluxratios = _fluxratio(masses, M_s)
-    masses_comp = qs_comp * M_s
-    fluxratios_comp = _fluxratio(masses_comp, M_s)
 
-    def cc_term():
-        fr = _fluxratio(masses_comp, M_s, filt)
-        return fr / (1 - fr)
+    def block(qs_comp, x_inc, x_q, x_w):
+        incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
+        masses = qs * M_s
+        radii, _ = stellar_relations(masses, np.full(len(qs), R_s), np.full(len(qs), Teff))
+        fluxratios = _fluxratio(masses, M_s)
+        masses_comp = qs_comp * M_s
+        fluxratios_comp = _fluxratio(masses_comp, M_s)
 
-    lnprior = _bound_prior(lnprior_bound_EB, M_s, plx, N, molusc_file, contrast_curve_file,
-                           fluxratios_comp / (1 - fluxratios_comp), cc_term)
-    return _run_eb(N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses, radii,
-                   fluxratios, fluxratios_comp, lnprior, qs_comp != 0.0, False, scalar_loop=not parallel)
+        def cc_term():
+            fr = _fluxratio(masses_comp, M_s, filt)
+            return fr / (1 - fr)
+
+        lnprior = _bound_prior(lnprior_bound_EB, M_s, plx, len(qs), molusc_file,
+                               contrast_curve_file, fluxratios_comp / (1 - fluxratios_comp),
+                               cc_term)
+        return (incs, qs, argps, masses, radii, fluxratios, M_s + masses, fluxratios_comp,
+                lnprior, qs_comp != 0.0)
+
+    (incs, qs, argps, masses, radii, fluxratios, mtot, fluxratios_comp, lnprior,
+     extra) = _hostpar.pmap_block(block, N, comp.finish(M_s), draws.x_inc, draws.x_q, draws.x_w)
+    return _run_eb(N, M_s, R_s, u1, u2, P, mtot, incs, qs, draws.eccs, argps, masses, radii,
+                   fluxratios, fluxratios_comp, lnprior, extra, False,
+                   scalar_loop=not parallel)
 
 
 def _companion_stars(N, M_s, R_s, Teff, Z, mission, qs_comp, Teff_cap):
     """Properties of the drawn bound companions when THEY host the event (:927-972)."""
     masses_comp = qs_comp * M_s
-    radii_comp, Teffs_comp = stellar_relations(masses_comp, np.full(N, R_s), np.full(N, Teff))
+    radii_comp, Teffs_comp = stellar_relations(masses_comp, np.full(len(qs_comp), R_s),
+                                               np.full(len(qs_comp), Teff))
     loggs_comp = np.log10(G * (masses_comp * Msun) / (radii_comp * Rsun) ** 2)
     fluxratios_comp = _fluxratio(masses_comp, M_s)
     u1s, u2s = grid_for(mission).at_Z_rounded(Z, Teffs_comp, loggs_comp, Teff_cap)
@@ -429,19 +462,26 @@ def lnZ_STP(time: np.ndarray, flux: np.ndarray, sigma: float,
     # draws first (q_comp, then the planet around a host of mass q_comp M_s), see lnZ_PTP
     comp, draws = _CompanionDraw(N, molusc_file), _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
-    qs_comp = comp.finish(M_s)
-    rps, incs, eccs, argps = draws.finish(qs_comp * M_s, flatpriors)
-    (masses_comp, radii_comp, _, fluxratios_comp, u1s, u2s) = _companion_stars(
-        N, M_s, R_s, Teff, Z, mission, qs_comp, 10000)
 
-    def cc_term():
-        fr = _fluxratio(masses_comp, M_s, filt)
-        return fr / (1 - fr)
+    def block(qs_comp, x_rp, x_inc, x_w):
+        rps, incs, argps = draws.transform(x_rp, x_inc, x_w, qs_comp * M_s, flatpriors)
+        (masses_comp, radii_comp, _, fluxratios_comp, u1s, u2s) = _companion_stars(
+            len(qs_comp), M_s, R_s, Teff, Z, mission, qs_comp, 10000)
 
-    lnprior = _bound_prior(lnprior_bound_TP, M_s, plx, N, molusc_file, contrast_curve_file,
-                           fluxratios_comp / (1 - fluxratios_comp), cc_term)
-    return _run_tp(N, masses_comp, radii_comp, u1s, u2s, P, masses_comp, rps, incs, eccs, argps,
-                   fluxratios_comp, lnprior, qs_comp != 0.0, True)
+        def cc_term():
+            fr = _fluxratio(masses_comp, M_s, filt)
+            return fr / (1 - fr)
+
+        lnprior = _bound_prior(lnprior_bound_TP, M_s, plx, len(qs_comp), molusc_file,
+                               contrast_curve_file, fluxratios_comp / (1 - fluxratios_comp),
+                               cc_term)
+        return (rps, incs, argps, masses_comp, radii_comp, fluxratios_comp, u1s, u2s, lnprior,
+                qs_comp != 0.0)
+
+    (rps, incs, argps, masses_comp, radii_comp, fluxratios_comp, u1s, u2s, lnprior,
+     extra) = _hostpar.pmap_block(block, N, comp.finish(M_s), draws.x_rp, draws.x_inc, draws.x_w)
+    return _run_tp(N, masses_comp, radii_comp, u1s, u2s, P, masses_comp, rps, incs, draws.eccs,
+                   argps, fluxratios_comp, lnprior, extra, True)
 
 
 def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
@@ -461,25 +501,33 @@ def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     P, P_mean = _periods(P_orb, N)
     draws, comp = _BinaryDraws(N, P_mean), _CompanionDraw(N, molusc_file)
     _dispatch.rng_done()
-    incs, qs, eccs, argps = draws.finish(M_s)
-    qs_comp = comp.finish(M_s)
-    # Teff clamp of 13000 K (grid stops at 10000 K) as in the reference, :1181
-    (masses_comp, radii_comp, Teffs_comp, fluxratios_comp, u1s, u2s) = _companion_stars(
-        N, M_s, R_s, Teff, Z, mission, qs_comp, 13000)
-    masses = qs * masses_comp
-    radii, _ = stellar_relations(masses, radii_comp, Teffs_comp)
-    fluxratios = _fluxratio(masses, M_s)
 
-    def cc_term():
-        fr = _fluxratio(masses, M_s, filt)
-        fr_comp = _fluxratio(masses_comp, M_s, filt)
-        return (fr_comp / (1 - fr_comp)) + (fr / (1 - fr))
+    def block(qs_comp, x_inc, x_q, x_w):
+        incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
+        # Teff clamp of 13000 K (grid stops at 10000 K) as in the reference, :1181
+        (masses_comp, radii_comp, Teffs_comp, fluxratios_comp, u1s, u2s) = _companion_stars(
+            len(qs), M_s, R_s, Teff, Z, mission, qs_comp, 13000)
+        masses = qs * masses_comp
+        radii, _ = stellar_relations(masses, radii_comp, Teffs_comp)
+        fluxratios = _fluxratio(masses, M_s)
 
-    lnprior = _bound_prior(lnprior_bound_EB, M_s, plx, N, molusc_file, contrast_curve_file,
-                           (fluxratios_comp / (1 - fluxratios_comp))
-                           + (fluxratios / (1 - fluxratios)), cc_term)
-    return _run_eb(N, masses_comp, radii_comp, u1s, u2s, P, masses_comp + masses, incs, qs, eccs,
-                   argps, masses, radii, fluxratios, fluxratios_comp, lnprior, qs_comp != 0.0,
+        def cc_term():
+            fr = _fluxratio(masses, M_s, filt)
+            fr_comp = _fluxratio(masses_comp, M_s, filt)
+            return (fr_comp / (1 - fr_comp)) + (fr / (1 - fr))
+
+        lnprior = _bound_prior(lnprior_bound_EB, M_s, plx, len(qs), molusc_file,
+                               contrast_curve_file,
+                               (fluxratios_comp / (1 - fluxratios_comp))
+                               + (fluxratios / (1 - fluxratios)), cc_term)
+        return (incs, qs, argps, masses_comp, radii_comp, u1s, u2s, masses_comp + masses, masses,
+                radii, fluxratios, fluxratios_comp, lnprior, qs_comp != 0.0)
+
+    (incs, qs, argps, masses_comp, radii_comp, u1s, u2s, mtot, masses, radii, fluxratios,
+     fluxratios_comp, lnprior, extra) = _hostpar.pmap_block(
+        block, N, comp.finish(M_s), draws.x_inc, draws.x_q, draws.x_w)
+    return _run_eb(N, masses_comp, radii_comp, u1s, u2s, P, mtot, incs, qs, draws.eccs,
+                   argps, masses, radii, fluxratios, fluxratios_comp, lnprior, extra,
                    True, scalar_loop=not parallel)
 
 
@@ -504,12 +552,19 @@ def lnZ_DTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     idxs = _fastrng.randint(0, bg.N_comp - 1, N)     # upper bound N_comp-1, as :1463
     draws = _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
-    rps, incs, eccs, argps = draws.finish(np.full(N, M_s), flatpriors)
-    cfr = bg.fluxratios[idxs]
-    lnprior = _background_prior(bg, N, contrast_curve_file,
-                                2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
-    return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, eccs, argps, cfr, lnprior, None,
-                   False)
+    band = bg.band(filt)
+
+    def block(idxs, x_rp, x_inc, x_w):
+        rps, incs, argps = draws.transform(x_rp, x_inc, x_w, M_s, flatpriors)
+        cfr = _take(bg.fluxratios, idxs)
+        lnprior = _background_prior(bg, len(idxs), contrast_curve_file,
+                                    2.5 * np.log10(cfr / (1 - cfr)), _take(band, idxs))
+        return rps, incs, argps, cfr, lnprior
+
+    rps, incs, argps, cfr, lnprior = _hostpar.pmap_block(block, N, idxs, draws.x_rp,
+                                                         draws.x_inc, draws.x_w)
+    return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, draws.eccs, argps, cfr, lnprior,
+                   None, False)
 
 
 def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
@@ -532,14 +587,21 @@ def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
     idxs = _fastrng.randint(0, bg.N_comp - 1, N)     # :1672
     _dispatch.rng_done()
-    incs, qs, eccs, argps = draws.finish(M_s)
-    masses = qs * M_s
-    radii, _ = stellar_relations(masses, np.full(N, R_s), np.full(N, Teff))
-    fluxratios = _fluxratio(masses, M_s)
-    cfr = bg.fluxratios[idxs]
-    lnprior = _background_prior(bg, N, contrast_curve_file,
-                                2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
-    return _run_eb(N, M_s, R_s, u1, u2, P, M_s + masses, incs, qs, eccs, argps, masses, radii,
+    band = bg.band(filt)
+
+    def block(idxs, x_inc, x_q, x_w):
+        incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
+        masses = qs * M_s
+        radii, _ = stellar_relations(masses, np.full(len(qs), R_s), np.full(len(qs), Teff))
+        fluxratios = _fluxratio(masses, M_s)
+        cfr = _take(bg.fluxratios, idxs)
+        lnprior = _background_prior(bg, len(idxs), contrast_curve_file,
+                                    2.5 * np.log10(cfr / (1 - cfr)), _take(band, idxs))
+        return incs, qs, argps, masses, radii, fluxratios, M_s + masses, cfr, lnprior
+
+    incs, qs, argps, masses, radii, fluxratios, mtot, cfr, lnprior = _hostpar.pmap_block(
+        block, N, idxs, draws.x_inc, draws.x_q, draws.x_w)
+    return _run_eb(N, M_s, R_s, u1, u2, P, mtot, incs, qs, draws.eccs, argps, masses, radii,
                    fluxratios, cfr, lnprior, None, False, scalar_loop=not parallel)
 
 
@@ -562,16 +624,24 @@ def lnZ_BTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     idxs = _fastrng.randint(0, bg.N_comp, N)         # :1926
     draws = _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
-    host_masses = bg.masses[idxs]
-    rps, incs, eccs, argps = draws.finish(host_masses, flatpriors)
     radii_comp = bg.radii()
     u1s_comp, u2s_comp = grid_for(mission).nearest_each(bg.Teffs, bg.loggs, bg.Zs)
-    cfr = bg.fluxratios[idxs]
-    lnprior = _background_prior(bg, N, contrast_curve_file,
-                                2.5 * np.log10(cfr / (1 - cfr)), bg.band(filt)[idxs])
-    extra = (bg.loggs[idxs] >= 3.5) & (bg.Teffs[idxs] <= 10000)
-    return _run_tp(N, host_masses, radii_comp[idxs], u1s_comp[idxs], u2s_comp[idxs], P,
-                   host_masses, rps, incs, eccs, argps, cfr, lnprior, extra, True)
+    band = bg.band(filt)
+
+    def block(idxs, x_rp, x_inc, x_w):
+        host_masses = _take(bg.masses, idxs)
+        rps, incs, argps = draws.transform(x_rp, x_inc, x_w, host_masses, flatpriors)
+        cfr = _take(bg.fluxratios, idxs)
+        lnprior = _background_prior(bg, len(idxs), contrast_curve_file,
+                                    2.5 * np.log10(cfr / (1 - cfr)), _take(band, idxs))
+        extra = (_take(bg.loggs, idxs) >= 3.5) & (_take(bg.Teffs, idxs) <= 10000)
+        return (host_masses, rps, incs, argps, cfr, lnprior, extra, _take(radii_comp, idxs),
+                _take(u1s_comp, idxs), _take(u2s_comp, idxs))
+
+    (host_masses, rps, incs, argps, cfr, lnprior, extra, host_radii, u1s,
+     u2s) = _hostpar.pmap_block(block, N, idxs, draws.x_rp, draws.x_inc, draws.x_w)
+    return _run_tp(N, host_masses, host_radii, u1s, u2s, P, host_masses, rps, incs, draws.eccs,
+                   argps, cfr, lnprior, extra, True)
 
 
 def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
@@ -596,35 +666,44 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     bg = _Background(trilegal_fname, Tmag, Jmag, Hmag, Kmag)
     idxs = _fastrng.randint(0, bg.N_comp, N)         # :2139
     _dispatch.rng_done()
-    incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
     radii_comp = bg.radii()
     u1s_comp, u2s_comp = grid_for(mission).nearest_each(bg.Teffs, bg.loggs, bg.Zs)
-    host_masses = bg.masses[idxs]
-    host_radii = radii_comp[idxs]
-    cfr = bg.fluxratios[idxs]
-    masses = qs * host_masses
-    radii, _ = stellar_relations(masses, host_radii, bg.Teffs[idxs])
+    # "TESS" and "Vis" share one flux relation and use the TESS-band magnitudes
+    cc_band = filt if filt in ("J", "H", "K") else "TESS"
+    band_fluxratios = {b: bg.fluxratios_in(b) for b in ("TESS", cc_band)}
 
-    def distance_corrected(band):
-        # EB flux ratio scaled from "bound at the target's distance" to the background star's
-        # actual brightness (:2147-2182)
-        cfr_band = bg.fluxratios_in(band)[idxs]
-        bound = _fluxratio(host_masses, M_s, band)
-        return _fluxratio(masses, M_s, band) * (cfr_band / bound), cfr_band
+    def block(idxs, x_inc, x_q, x_w):
+        incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
+        host_masses = _take(bg.masses, idxs)
+        host_radii = _take(radii_comp, idxs)
+        cfr = _take(bg.fluxratios, idxs)
+        masses = qs * host_masses
+        radii, _ = stellar_relations(masses, host_radii, _take(bg.Teffs, idxs))
 
-    fluxratios, _ = distance_corrected("TESS")
-    if contrast_curve_file is None:
-        dmag = 2.5 * np.log10((cfr / (1 - cfr)) + (fluxratios / (1 - fluxratios)))
-        lnprior = _background_prior(bg, N, None, dmag, None)
-    else:
-        # "TESS" and "Vis" share one flux relation and use the TESS-band magnitudes
-        fr_cc, cfr_cc = distance_corrected(filt if filt in ("J", "H", "K") else "TESS")
-        dmag = 2.5 * np.log10((cfr_cc / (1 - cfr_cc)) + (fr_cc / (1 - fr_cc)))
-        lnprior = _background_prior(bg, N, contrast_curve_file, None, dmag)
-    extra = (bg.loggs[idxs] >= 3.5) & (bg.Teffs[idxs] <= 10000)
-    return _run_eb(N, host_masses, host_radii, u1s_comp[idxs], u2s_comp[idxs], P,
-                   host_masses + masses, incs, qs, eccs, argps, masses, radii, fluxratios, cfr,
-                   lnprior, extra, True, scalar_loop=not parallel)
+        def distance_corrected(band):
+            # EB flux ratio scaled from "bound at the target's distance" to the background
+            # star's actual brightness (:2147-2182)
+            cfr_band = _take(band_fluxratios[band], idxs)
+            bound = _fluxratio(host_masses, M_s, band)
+            return _fluxratio(masses, M_s, band) * (cfr_band / bound), cfr_band
+
+        fluxratios, _ = distance_corrected("TESS")
+        if contrast_curve_file is None:
+            dmag = 2.5 * np.log10((cfr / (1 - cfr)) + (fluxratios / (1 - fluxratios)))
+            lnprior = _background_prior(bg, len(idxs), None, dmag, None)
+        else:
+            fr_cc, cfr_cc = distance_corrected(cc_band)
+            dmag = 2.5 * np.log10((cfr_cc / (1 - cfr_cc)) + (fr_cc / (1 - fr_cc)))
+            lnprior = _background_prior(bg, len(idxs), contrast_curve_file, None, dmag)
+        extra = (_take(bg.loggs, idxs) >= 3.5) & (_take(bg.Teffs, idxs) <= 10000)
+        return (incs, qs, argps, host_masses, host_radii, _take(u1s_comp, idxs),
+                _take(u2s_comp, idxs), host_masses + masses, masses, radii, fluxratios, cfr,
+                lnprior, extra)
+
+    (incs, qs, argps, host_masses, host_radii, u1s, u2s, mtot, masses, radii, fluxratios, cfr,
+     lnprior, extra) = _hostpar.pmap_block(block, N, idxs, x_inc, x_q, x_w)
+    return _run_eb(N, host_masses, host_radii, u1s, u2s, P, mtot, incs, qs, eccs, argps, masses,
+                   radii, fluxratios, cfr, lnprior, extra, True, scalar_loop=not parallel)
 
 
 # ------------------------------------------------- nearby stars of unknown / evolved nature
@@ -670,10 +749,10 @@ def lnZ_NTP_unknown(time: np.ndarray, flux: np.ndarray, sigma: float,
     if hosts.n == 0:
         return _no_hosts(with_b=False)
     idxs = _fastrng.randint(0, hosts.n, N)
-    host_masses = hosts.masses[idxs]
+    host_masses = _take(hosts.masses, idxs)
     rps, incs, eccs, argps = _draw_planet(N, host_masses, flatpriors, P_mean)
-    extra = (hosts.loggs[idxs] >= 3.5) & (hosts.Teffs[idxs] <= 10000)
-    return _run_tp(N, host_masses, hosts.radii[idxs], hosts.u1s[idxs], hosts.u2s[idxs], P,
+    extra = (_take(hosts.loggs, idxs) >= 3.5) & (_take(hosts.Teffs, idxs) <= 10000)
+    return _run_tp(N, host_masses, _take(hosts.radii, idxs), _take(hosts.u1s, idxs), _take(hosts.u2s, idxs), P,
                    host_masses, rps, incs, eccs, argps, 0.0, None, extra, False)
 
 
@@ -691,13 +770,13 @@ def lnZ_NEB_unknown(time: np.ndarray, flux: np.ndarray, sigma: float,
     if hosts.n == 0:
         return _no_hosts(with_b=True)                           # a single dict, as :2665
     idxs = _fastrng.randint(0, hosts.n, N)
-    host_masses, host_radii = hosts.masses[idxs], hosts.radii[idxs]
+    host_masses, host_radii = _take(hosts.masses, idxs), _take(hosts.radii, idxs)
     masses = qs * host_masses
-    radii, _ = stellar_relations(masses, host_radii, hosts.Teffs[idxs])
+    radii, _ = stellar_relations(masses, host_radii, _take(hosts.Teffs, idxs))
     f = flux_relation(masses)
     fluxratios = f / (f + flux_relation(host_masses))
-    extra = (hosts.loggs[idxs] >= 3.5) & (hosts.Teffs[idxs] <= 10000)
-    return _run_eb(N, host_masses, host_radii, hosts.u1s[idxs], hosts.u2s[idxs], P,
+    extra = (_take(hosts.loggs, idxs) >= 3.5) & (_take(hosts.Teffs, idxs) <= 10000)
+    return _run_eb(N, host_masses, host_radii, _take(hosts.u1s, idxs), _take(hosts.u2s, idxs), P,
                    host_masses + masses, incs, qs, eccs, argps, masses, radii, fluxratios, 0.0,
                    None, extra, False, scalar_loop=not parallel)
 
