@@ -76,6 +76,27 @@ wrap(engine_mod.Engine, "submit_tp", "eng:submit_tp")
 wrap(engine_mod.Engine, "submit_eb", "eng:submit_eb")
 wrap(engine_mod.Pending, "result", "eng:result")
 
+orig_block = _hostpar.pmap_block
+
+
+def traced_block(fn, n, *arrays):
+    t0 = time.perf_counter()
+
+    def chunk(*a):
+        c0 = time.perf_counter()
+        try:
+            return fn(*a)
+        finally:
+            span("chunk", c0, time.perf_counter())
+    try:
+        return orig_block(chunk, n, *arrays)
+    finally:
+        span("block", t0, time.perf_counter())
+
+
+_hostpar.pmap_block = traced_block
+ml._hostpar.pmap_block = traced_block
+
 orig_run = _dispatch.ScenarioChain.run
 orig_done = _dispatch.rng_done
 
@@ -143,7 +164,15 @@ for th, ev in by_thread.items():
                      "held_other_ms": {k: round(v * 1e3, 1) for k, v in other.items()},
                      "after_ms": {k: round(v * 1e3, 1) for k, v in after.items()}})
 rows.sort(key=lambda r: r["got_generator"])
-out = {"wall_s": round(wall, 4), "draws": args.draws, "config": args.config,
+chunks = [(a - t_begin, b - t_begin) for th, lab, a, b in spans if lab == "chunk"]
+blocks = [(a - t_begin, b - t_begin) for th, lab, a, b in spans if lab == "block"]
+block_stats = {"blocks": len(blocks), "chunks": len(chunks),
+               "chunk_thread_s": round(sum(b - a for a, b in chunks), 4),
+               "block_wall_s": round(sum(b - a for a, b in blocks), 4),
+               "chunk_ms_median": round(1e3 * float(np.median([b - a for a, b in chunks])), 2)
+               if chunks else None,
+               "chunk_ms_max": round(1e3 * max(b - a for a, b in chunks), 2) if chunks else None}
+out = {"blocks": block_stats, "wall_s": round(wall, 4), "draws": args.draws, "config": args.config,
        "host_threads": _hostpar.N_THREADS,
        "chain_end_s": max(r["released"] for r in rows) if rows else None,
        "rng_total_s": round(sum(r["in_rng_ms"] for r in rows) / 1e3, 4),

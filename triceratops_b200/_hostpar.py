@@ -162,7 +162,9 @@ def block_chunks(n):
     if _pool is None or n < 2 * MIN_CHUNK:
         return [slice(0, n)]
     want = os.environ.get("TRI_B200_BLOCK_CHUNKS")
-    parts = int(want) if want else N_THREADS
+    # one chunk per thread, and more of them when that would push a chunk's temporaries
+    # (8 bytes x ~10 live arrays per element) out of a core's cache
+    parts = int(want) if want else max(N_THREADS, -(-n // (2 * MIN_CHUNK)))
     parts = max(1, min(parts, n // (MIN_CHUNK // 2)))
     edges = [(i * n) // parts for i in range(parts + 1)]
     return [slice(edges[i], edges[i + 1]) for i in range(parts)]

@@ -152,6 +152,14 @@ class _CompanionDraw:
             return sample_q_companion(self.x, M_s)
         return _companion_q(self.N, M_s, self.molusc_file)
 
+    def column(self, M_s):
+        """What a scenario's block gets per draw: the deviates (the block applies `transform`)
+        or, with a MOLUSC table, the mass ratios themselves."""
+        return self.x if self.molusc_file is None else self.finish(M_s)
+
+    def transform(self, col, M_s):
+        return sample_q_companion(col, M_s) if self.molusc_file is None else col
+
 
 def _companion_q(N, M_s, molusc_file):
     """Mass ratios of bound companions: prior draws or a MOLUSC table (e.g. :455-464)."""
@@ -369,7 +377,8 @@ def lnZ_PTP(time: np.ndarray, flux: np.ndarray, sigma: float,
     comp, draws = _CompanionDraw(N, molusc_file), _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
 
-    def block(qs_comp, x_rp, x_inc, x_w):
+    def block(c_comp, x_rp, x_inc, x_w):
+        qs_comp = comp.transform(c_comp, M_s)
         rps, incs, argps = draws.transform(x_rp, x_inc, x_w, M_s, flatpriors)
         masses_comp = qs_comp * M_s
         fluxratios_comp = _fluxratio(masses_comp, M_s)
@@ -384,7 +393,7 @@ def lnZ_PTP(time: np.ndarray, flux: np.ndarray, sigma: float,
         return rps, incs, argps, fluxratios_comp, lnprior, qs_comp != 0.0
 
     rps, incs, argps, fluxratios_comp, lnprior, extra = _hostpar.pmap_block(
-        block, N, comp.finish(M_s), draws.x_rp, draws.x_inc, draws.x_w)
+        block, N, comp.column(M_s), draws.x_rp, draws.x_inc, draws.x_w)
     return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, draws.eccs, argps, fluxratios_comp,
                    lnprior, extra, False)
 
@@ -408,7 +417,8 @@ def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     draws, comp = _BinaryDraws(N, P_mean), _CompanionDraw(N, molusc_file)
     _dispatch.rng_done()
 
-    def block(qs_comp, x_inc, x_q, x_w):
+    def block(c_comp, x_inc, x_q, x_w):
+        qs_comp = comp.transform(c_comp, M_s)
         incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
         masses = qs * M_s
         radii, _ = stellar_relations(masses, np.full(len(qs), R_s), np.full(len(qs), Teff))
@@ -427,7 +437,7 @@ def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
                 lnprior, qs_comp != 0.0)
 
     (incs, qs, argps, masses, radii, fluxratios, mtot, fluxratios_comp, lnprior,
-     extra) = _hostpar.pmap_block(block, N, comp.finish(M_s), draws.x_inc, draws.x_q, draws.x_w)
+     extra) = _hostpar.pmap_block(block, N, comp.column(M_s), draws.x_inc, draws.x_q, draws.x_w)
     return _run_eb(N, M_s, R_s, u1, u2, P, mtot, incs, qs, draws.eccs, argps, masses, radii,
                    fluxratios, fluxratios_comp, lnprior, extra, False,
                    scalar_loop=not parallel)
@@ -463,7 +473,8 @@ def lnZ_STP(time: np.ndarray, flux: np.ndarray, sigma: float,
     comp, draws = _CompanionDraw(N, molusc_file), _PlanetDraws(N, P_mean)
     _dispatch.rng_done()
 
-    def block(qs_comp, x_rp, x_inc, x_w):
+    def block(c_comp, x_rp, x_inc, x_w):
+        qs_comp = comp.transform(c_comp, M_s)
         rps, incs, argps = draws.transform(x_rp, x_inc, x_w, qs_comp * M_s, flatpriors)
         (masses_comp, radii_comp, _, fluxratios_comp, u1s, u2s) = _companion_stars(
             len(qs_comp), M_s, R_s, Teff, Z, mission, qs_comp, 10000)
@@ -479,7 +490,7 @@ def lnZ_STP(time: np.ndarray, flux: np.ndarray, sigma: float,
                 qs_comp != 0.0)
 
     (rps, incs, argps, masses_comp, radii_comp, fluxratios_comp, u1s, u2s, lnprior,
-     extra) = _hostpar.pmap_block(block, N, comp.finish(M_s), draws.x_rp, draws.x_inc, draws.x_w)
+     extra) = _hostpar.pmap_block(block, N, comp.column(M_s), draws.x_rp, draws.x_inc, draws.x_w)
     return _run_tp(N, masses_comp, radii_comp, u1s, u2s, P, masses_comp, rps, incs, draws.eccs,
                    argps, fluxratios_comp, lnprior, extra, True)
 
@@ -502,7 +513,8 @@ def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     draws, comp = _BinaryDraws(N, P_mean), _CompanionDraw(N, molusc_file)
     _dispatch.rng_done()
 
-    def block(qs_comp, x_inc, x_q, x_w):
+    def block(c_comp, x_inc, x_q, x_w):
+        qs_comp = comp.transform(c_comp, M_s)
         incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
         # Teff clamp of 13000 K (grid stops at 10000 K) as in the reference, :1181
         (masses_comp, radii_comp, Teffs_comp, fluxratios_comp, u1s, u2s) = _companion_stars(
@@ -525,7 +537,7 @@ def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
 
     (incs, qs, argps, masses_comp, radii_comp, u1s, u2s, mtot, masses, radii, fluxratios,
      fluxratios_comp, lnprior, extra) = _hostpar.pmap_block(
-        block, N, comp.finish(M_s), draws.x_inc, draws.x_q, draws.x_w)
+        block, N, comp.column(M_s), draws.x_inc, draws.x_q, draws.x_w)
     return _run_eb(N, masses_comp, radii_comp, u1s, u2s, P, mtot, incs, qs, draws.eccs,
                    argps, masses, radii, fluxratios, fluxratios_comp, lnprior, extra,
                    True, scalar_loop=not parallel)
