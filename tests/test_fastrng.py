@@ -95,3 +95,25 @@ def test_engine_calls_are_identical_with_and_without_the_helper(monkeypatch):
         assert (a["extra_mask"] is None) == (b["extra_mask"] is None)
         if a["extra_mask"] is not None:
             assert np.array_equal(a["extra_mask"], b["extra_mask"])
+
+
+@pytest.mark.parametrize("margin", [64, -3000, -10_000_000])
+@pytest.mark.parametrize("hi", [2, 3, 1000, 2499, 65536, 2 ** 31 + 5])
+def test_randint_bulk_matches_numpy_also_when_the_word_estimate_falls_short(margin, hi):
+    """randint produces its words in bulk from an estimate of the rejection rate; a short
+    estimate (forced here) must refill and land on the same values and stream position."""
+    L = _fastrng._load()
+    n = 50_001
+    np.random.seed(5)
+    np.random.rand(7)
+    want, after = np.random.randint(0, hi, n), np.random.rand(5)
+    np.random.seed(5)
+    np.random.rand(7)
+    L.trih_debug_randint_margin.argtypes = [__import__("ctypes").c_int64]
+    L.trih_debug_randint_margin(margin)
+    try:
+        got = _fastrng.randint(0, hi, n)
+    finally:
+        L.trih_debug_randint_margin(64)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    assert np.array_equal(np.random.rand(5), after)

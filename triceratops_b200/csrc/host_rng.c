@@ -14,6 +14,8 @@
  * Build: gcc -O3 (libtriceratops_host.so).  Not a compute fallback: nothing of the light-curve
  * path lives here.
  */
+#include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -25,8 +27,10 @@
 
 #if defined(__GNUC__) && defined(__x86_64__)
 #define CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#define CPU_RELAX() __builtin_ia32_pause()
 #else
 #define CLONES
+#define CPU_RELAX() ((void)0)
 #endif
 
 /* raw[0..624) holds the current key; fills raw[624 .. 624 + 624 * nblocks) with the state words
@@ -95,31 +99,56 @@ int trih_mt_rand(uint32_t* key, int32_t* pos, double* out, int64_t n) {
 }
 
 /* out[n] = np.random.randint(low, low + rng + 1, n) for 0 < rng < 2^32 - 1 (legacy masked
- * rejection on single 32-bit words: numpy _bounded_integers, use_masked = True) */
+ * rejection on single 32-bit words: numpy _bounded_integers, use_masked = True).  Every word of
+ * the stream is either accepted or rejected on its own, so the words are produced in bulk and
+ * compacted branch-free: the output is written for every word and the cursor only advances past
+ * the accepted ones (numpy's own loop costs ~10 ns per word in the block-boundary test). */
+static int64_t g_randint_margin = 64;
+void trih_debug_randint_margin(int64_t words) { g_randint_margin = words; }   /* (tests) */
+
+static int64_t compact_accepted(const uint32_t* raw, int64_t* cursor, int64_t end, uint32_t mask,
+                                uint32_t rng, int64_t low, int64_t* out, int64_t k, int64_t n) {
+    int64_t i = *cursor;
+    /* out[n - 1] is the last slot that may be written: stop as soon as k reaches n */
+    for (; i < end && k < n; i++) {
+        const uint32_t v = temper(raw[i]) & mask;
+        out[k] = low + (int64_t)v;
+        k += (v <= rng);
+    }
+    *cursor = i;
+    return k;
+}
+
 int trih_mt_randint(uint32_t* key, int32_t* pos, int64_t low, uint32_t rng, int64_t* out,
                     int64_t n) {
     if (n <= 0) return 0;
     uint32_t mask = rng;
     mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-    uint32_t* raw = (uint32_t*)malloc((size_t)2 * MT_N * sizeof(uint32_t));
+    const double p = ((double)rng + 1.0) / ((double)mask + 1.0);       /* acceptance, >= 1/2 */
+    int64_t est = (int64_t)((double)n / p + 8.0 * sqrt((double)n * (1.0 - p)) / p)
+                  + g_randint_margin;
+    if (est < 1) est = 1;
+    const int64_t have = MT_N - *pos;
+    int64_t nblocks = est > have ? (est - have + MT_N - 1) / MT_N : 0;
+    const int64_t more = 8;                                  /* blocks per refill */
+    uint32_t* raw = raw_scratch((size_t)((nblocks > more ? nblocks : more) + 2) * MT_N + 16);
     if (!raw) return -1;
     memcpy(raw, key, MT_N * sizeof(uint32_t));
-    int64_t p = *pos;
-    for (int64_t i = 0; i < n; i++) {
-        uint32_t v;
-        do {
-            if (p == MT_N) {           /* next block, in place */
-                mt_extend(raw, 1);
-                memcpy(raw, raw + MT_N, MT_N * sizeof(uint32_t));
-                p = 0;
-            }
-            v = temper(raw[p++]) & mask;
-        } while (v > rng);
-        out[i] = low + (int64_t)v;
+    mt_extend(raw, nblocks);
+    int64_t cursor = *pos, end = (nblocks + 1) * MT_N, k = 0;
+    for (;;) {
+        k = compact_accepted(raw, &cursor, end, mask, rng, low, out, k, n);
+        if (k == n) break;
+        /* the estimate fell short: the last block becomes the key, a few more follow */
+        memmove(raw, raw + end - MT_N, MT_N * sizeof(uint32_t));
+        mt_extend(raw, more);
+        cursor = MT_N;
+        end = (more + 1) * MT_N;
     }
-    memcpy(key, raw, MT_N * sizeof(uint32_t));
-    *pos = (int32_t)p;
-    free(raw);
+    int64_t blk = cursor / MT_N, off = cursor % MT_N;
+    if (off == 0 && blk > 0) { blk -= 1; off = MT_N; }      /* numpy regenerates lazily */
+    memcpy(key, raw + blk * MT_N, MT_N * sizeof(uint32_t));
+    *pos = (int32_t)off;
     return 0;
 }
 
@@ -281,7 +310,11 @@ int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ga
     uint32_t* raw = raw_scratch((size_t)(nblocks + 1) * MT_N + 16);
     if (!raw) return -1;
     memcpy(raw, key, MT_N * sizeof(uint32_t));
-    mt_extend(raw, nblocks);
+    /* only the head of the stream is produced up front; thread 0 produces the rest while the
+     * other threads already walk the first chunks (see the parallel region) */
+    const int64_t piece = 1024;                              /* blocks per publication */
+    int64_t ext_blocks = nblocks < 2 * piece || nthreads < 2 ? nblocks : 2 * piece;
+    mt_extend(raw, ext_blocks);
     C.w = raw + *pos;
     C.cap = cap;
     t_extend = now_s();
@@ -304,12 +337,34 @@ int trih_legacy_beta(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* ga
     int first = 0, t = 0;
     walk_state S = entry;             /* the true walk (stitcher) */
     int64_t count = 0;
+    int next_chunk;
 walk_again:
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-    for (int tc = first; tc < nchunks; tc++) {
-        const int t = tc;
+    next_chunk = first;
+#pragma omp parallel num_threads(nthreads)
+    {
+    if (omp_get_thread_num() == 0) {
+        /* the producer: the rest of the stream, published piece by piece */
+        for (int64_t b = __atomic_load_n(&ext_blocks, __ATOMIC_RELAXED); b < nblocks;) {
+            const int64_t k = nblocks - b < piece ? nblocks - b : piece;
+            mt_extend(raw + b * MT_N, k);
+            b += k;
+            __atomic_store_n(&ext_blocks, b, __ATOMIC_RELEASE);
+        }
+    }
+    for (;;) {
+        const int t = __atomic_fetch_add(&next_chunk, 1, __ATOMIC_RELAXED);
+        if (t >= nchunks) break;
         chunk_rec* r = &R[t];
         const int64_t p0 = (est * t) / nchunks, p1 = (est * (t + 1)) / nchunks;
+        /* the words this chunk may read: its range of the stream and a sample's worth beyond */
+        int64_t want = (*pos + 2 * (p1 + 4096)) / MT_N + 1;
+        if (want > nblocks) want = nblocks;
+        int64_t got;
+        while ((got = __atomic_load_n(&ext_blocks, __ATOMIC_ACQUIRE)) < want)
+            CPU_RELAX();
+        beta_ctx L = C;                                /* never reads past what is published */
+        const int64_t avail = ((got + 1) * MT_N - *pos) / 2;
+        if (avail < L.cap) L.cap = avail;
         if (!r->m0) {
             r->cap = (int64_t)((double)(p1 - p0) / per * 1.25) + 1024;
             r->m0 = (int64_t*)malloc((size_t)r->cap * sizeof(int64_t));
@@ -328,10 +383,11 @@ walk_again:
         while (W.m < p1 && r->n < r->cap && r->n < n) {
             r->m0[r->n] = W.m;
             r->src0[r->n] = W.src;
-            if (walk_beta(&C, &W, &r->val[r->n])) { r->rc = -2; break; }
+            if (walk_beta(&L, &W, &r->val[r->n])) { r->rc = -2; break; }
             r->n++;
         }
         r->end = W;
+    }
     }
     if (first > 0) goto stitch_resume;
 
