@@ -44,7 +44,8 @@ def _load():
         return None
     try:
         L = ctypes.CDLL(_build.HOST_SO_PATH)
-        L.trih_mt_rand.argtypes = [_U32, ctypes.POINTER(ctypes.c_int32), _D, ctypes.c_int64]
+        L.trih_mt_rand.argtypes = [_U32, ctypes.POINTER(ctypes.c_int32), _D, ctypes.c_int64,
+                                   ctypes.c_int]
         L.trih_mt_randint.argtypes = [_U32, ctypes.POINTER(ctypes.c_int32), ctypes.c_int64,
                                       ctypes.c_uint32, _I64, ctypes.c_int64]
         L.trih_legacy_beta.argtypes = [_U32, ctypes.POINTER(ctypes.c_int32),
@@ -70,6 +71,11 @@ def _commit(st, key, pos):
     np.random.set_state((st[0], key, int(pos.value), st[3], st[4]))
 
 
+def _convert_threads():
+    from ._hostpar import N_THREADS
+    return max(1, min(int(N_THREADS), 4))
+
+
 def _advance(n, out):
     """Draw n doubles into `out` (None: only advance the state); False if not possible."""
     s = _state()
@@ -77,7 +83,8 @@ def _advance(n, out):
         return False
     st, key, pos = s
     if _lib.trih_mt_rand(key.ctypes.data_as(_U32), ctypes.byref(pos),
-                         out.ctypes.data_as(_D) if out is not None else None, n) != 0:
+                         out.ctypes.data_as(_D) if out is not None else None, n,
+                         _convert_threads()) != 0:
         return False
     _commit(st, key, pos)
     return True
@@ -165,7 +172,8 @@ def powerlaw_rvs(a, n):
     if n < MIN_N or _load() is None:
         from scipy.stats import powerlaw
         return powerlaw.rvs(a, size=n)
-    return pow(rand(n), 1.0 / a) * 1 + 0
+    x = rand(n)
+    return np.power(x, 1.0 / a, out=x)        # (* scale + loc with 1, 0: the same bits)
 
 
 def beta_rvs(a, b, n, _force=False):
@@ -190,4 +198,6 @@ def beta_rvs(a, b, n, _force=False):
         from scipy.stats import beta
         return beta.rvs(a, b, size=n)
     np.random.set_state((st[0], key, int(pos.value), int(has_gauss.value), float(gauss.value)))
-    return out * 1 + 0       # rv_continuous.rvs: vals * scale + loc
+    # (rv_continuous.rvs returns vals * scale + loc with scale 1, loc 0: the same bits for
+    # these values in (0, 1))
+    return out

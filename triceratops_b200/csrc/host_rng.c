@@ -79,8 +79,10 @@ CLONES static void words_to_doubles(const uint32_t* w, double* out, int64_t n) {
     }
 }
 
-/* key[624], *pos (0..624): numpy's state, updated in place.  out[n] = np.random.rand(n). */
-int trih_mt_rand(uint32_t* key, int32_t* pos, double* out, int64_t n) {
+/* key[624], *pos (0..624): numpy's state, updated in place.  out[n] = np.random.rand(n).
+ * The state recurrence is sequential; the tempering + conversion of the words is spread over
+ * `nthreads` (the caller's choice per call; large n only). */
+int trih_mt_rand(uint32_t* key, int32_t* pos, double* out, int64_t n, int nthreads) {
     if (n <= 0) return 0;
     const int64_t need = 2 * n;
     const int64_t have = MT_N - *pos;                       /* words left in the current key */
@@ -89,7 +91,19 @@ int trih_mt_rand(uint32_t* key, int32_t* pos, double* out, int64_t n) {
     if (!raw) return -1;
     memcpy(raw, key, MT_N * sizeof(uint32_t));
     mt_extend(raw, nblocks);
-    if (out) words_to_doubles(raw + *pos, out, n);    /* (NULL: skip the draws) */
+    if (out) {                                        /* (NULL: skip the draws) */
+        const uint32_t* w = raw + *pos;
+        if (nthreads > 1 && n >= (1 << 18)) {
+            const int64_t per = (n + nthreads - 1) / nthreads;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (int t = 0; t < nthreads; t++) {
+                const int64_t lo = t * per, hi = lo + per < n ? lo + per : n;
+                if (lo < hi) words_to_doubles(w + 2 * lo, out + lo, hi - lo);
+            }
+        } else {
+            words_to_doubles(w, out, n);
+        }
+    }
     int64_t cursor = *pos + need;                           /* in words from raw[0] */
     int64_t blk = cursor / MT_N, off = cursor % MT_N;
     if (off == 0 && blk > 0) { blk -= 1; off = MT_N; }      /* numpy regenerates lazily */

@@ -90,7 +90,14 @@ def _draw_ecc(N, planet, P_mean):
     _fastrng.skip(N)
     if planet:
         return _fastrng.beta_rvs(0.867, 3.030, N)
-    return _fastrng.powerlaw_rvs(0.2 if P_mean <= 10 else 0.6, N)
+    # scipy.stats.powerlaw.rvs(a, size=N) is pow(uniform deviates, 1/a): only the deviates are
+    # taken here, while the generator is held; _ecc_binary() maps them later, chunk by chunk
+    return _fastrng.rand(N)
+
+
+def _ecc_binary(x, P_mean):
+    """In place: the binaries' eccentricities from the deviates _draw_ecc(N, False, .) drew."""
+    np.power(x, 1.0 / (0.2 if P_mean <= 10 else 0.6), out=x)
 
 
 class _PlanetDraws:
@@ -127,15 +134,22 @@ class _BinaryDraws:
     """Same for a stellar companion: inc, q, ecc, argp."""
 
     def __init__(self, N, P_mean):
+        self.P_mean = P_mean
         self.x_inc = _fastrng.rand(N)
         self.x_q = _fastrng.rand(N)
-        self.eccs = _draw_ecc(N, False, P_mean)
+        self.eccs = _draw_ecc(N, False, P_mean)      # deviates until transform() has run
         self.x_w = _fastrng.rand(N)
+
+    def transform(self, x_inc, x_q, x_e, x_w, M_s):
+        """(incs, qs, argps) of a chunk of deviates; the chunk of self.eccs becomes
+        eccentricities in place."""
+        _ecc_binary(x_e, self.P_mean)
+        return sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
 
     def finish(self, M_s):
         incs, qs, argps = _hostpar.pmap_block(
-            lambda x_inc, x_q, x_w: (sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)),
-            len(self.x_inc), self.x_inc, self.x_q, self.x_w)
+            lambda x_inc, x_q, x_e, x_w: self.transform(x_inc, x_q, x_e, x_w, M_s),
+            len(self.x_inc), self.x_inc, self.x_q, self.eccs, self.x_w)
         return incs, qs, self.eccs, argps
 
 
@@ -343,14 +357,14 @@ def lnZ_TEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     draws = _BinaryDraws(N, P_mean)
     _dispatch.rng_done()
 
-    def block(x_inc, x_q, x_w):
-        incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
+    def block(x_inc, x_q, x_e, x_w):
+        incs, qs, argps = draws.transform(x_inc, x_q, x_e, x_w, M_s)
         masses = qs * M_s
         radii, _ = stellar_relations(masses, np.full(len(qs), R_s), np.full(len(qs), Teff))
         return incs, qs, argps, masses, radii, _fluxratio(masses, M_s), M_s + masses
 
     incs, qs, argps, masses, radii, fluxratios, mtot = _hostpar.pmap_block(
-        block, N, draws.x_inc, draws.x_q, draws.x_w)
+        block, N, draws.x_inc, draws.x_q, draws.eccs, draws.x_w)
     return _run_eb(N, M_s, R_s, u1, u2, P, mtot, incs, qs, draws.eccs, argps, masses, radii,
                    fluxratios, 0.0, None, None, False, scalar_loop=not parallel)
 
@@ -417,9 +431,9 @@ def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     draws, comp = _BinaryDraws(N, P_mean), _CompanionDraw(N, molusc_file)
     _dispatch.rng_done()
 
-    def block(c_comp, x_inc, x_q, x_w):
+    def block(c_comp, x_inc, x_q, x_e, x_w):
         qs_comp = comp.transform(c_comp, M_s)
-        incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
+        incs, qs, argps = draws.transform(x_inc, x_q, x_e, x_w, M_s)
         masses = qs * M_s
         radii, _ = stellar_relations(masses, np.full(len(qs), R_s), np.full(len(qs), Teff))
         fluxratios = _fluxratio(masses, M_s)
@@ -437,7 +451,7 @@ def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
                 lnprior, qs_comp != 0.0)
 
     (incs, qs, argps, masses, radii, fluxratios, mtot, fluxratios_comp, lnprior,
-     extra) = _hostpar.pmap_block(block, N, comp.column(M_s), draws.x_inc, draws.x_q, draws.x_w)
+     extra) = _hostpar.pmap_block(block, N, comp.column(M_s), draws.x_inc, draws.x_q, draws.eccs, draws.x_w)
     return _run_eb(N, M_s, R_s, u1, u2, P, mtot, incs, qs, draws.eccs, argps, masses, radii,
                    fluxratios, fluxratios_comp, lnprior, extra, False,
                    scalar_loop=not parallel)
@@ -513,9 +527,9 @@ def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     draws, comp = _BinaryDraws(N, P_mean), _CompanionDraw(N, molusc_file)
     _dispatch.rng_done()
 
-    def block(c_comp, x_inc, x_q, x_w):
+    def block(c_comp, x_inc, x_q, x_e, x_w):
         qs_comp = comp.transform(c_comp, M_s)
-        incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
+        incs, qs, argps = draws.transform(x_inc, x_q, x_e, x_w, M_s)
         # Teff clamp of 13000 K (grid stops at 10000 K) as in the reference, :1181
         (masses_comp, radii_comp, Teffs_comp, fluxratios_comp, u1s, u2s) = _companion_stars(
             len(qs), M_s, R_s, Teff, Z, mission, qs_comp, 13000)
@@ -537,7 +551,7 @@ def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
 
     (incs, qs, argps, masses_comp, radii_comp, u1s, u2s, mtot, masses, radii, fluxratios,
      fluxratios_comp, lnprior, extra) = _hostpar.pmap_block(
-        block, N, comp.column(M_s), draws.x_inc, draws.x_q, draws.x_w)
+        block, N, comp.column(M_s), draws.x_inc, draws.x_q, draws.eccs, draws.x_w)
     return _run_eb(N, masses_comp, radii_comp, u1s, u2s, P, mtot, incs, qs, draws.eccs,
                    argps, masses, radii, fluxratios, fluxratios_comp, lnprior, extra,
                    True, scalar_loop=not parallel)
@@ -601,8 +615,8 @@ def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     _dispatch.rng_done()
     band = bg.band(filt)
 
-    def block(idxs, x_inc, x_q, x_w):
-        incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
+    def block(idxs, x_inc, x_q, x_e, x_w):
+        incs, qs, argps = draws.transform(x_inc, x_q, x_e, x_w, M_s)
         masses = qs * M_s
         radii, _ = stellar_relations(masses, np.full(len(qs), R_s), np.full(len(qs), Teff))
         fluxratios = _fluxratio(masses, M_s)
@@ -612,7 +626,7 @@ def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
         return incs, qs, argps, masses, radii, fluxratios, M_s + masses, cfr, lnprior
 
     incs, qs, argps, masses, radii, fluxratios, mtot, cfr, lnprior = _hostpar.pmap_block(
-        block, N, idxs, draws.x_inc, draws.x_q, draws.x_w)
+        block, N, idxs, draws.x_inc, draws.x_q, draws.eccs, draws.x_w)
     return _run_eb(N, M_s, R_s, u1, u2, P, mtot, incs, qs, draws.eccs, argps, masses, radii,
                    fluxratios, cfr, lnprior, None, False, scalar_loop=not parallel)
 
@@ -684,7 +698,8 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
     cc_band = filt if filt in ("J", "H", "K") else "TESS"
     band_fluxratios = {b: bg.fluxratios_in(b) for b in ("TESS", cc_band)}
 
-    def block(idxs, x_inc, x_q, x_w):
+    def block(idxs, x_inc, x_q, x_e, x_w):
+        _ecc_binary(x_e, P_mean)
         incs, qs, argps = sample_inc(x_inc), sample_q(x_q, M_s), sample_w(x_w)
         host_masses = _take(bg.masses, idxs)
         host_radii = _take(radii_comp, idxs)
@@ -713,7 +728,7 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
                 lnprior, extra)
 
     (incs, qs, argps, host_masses, host_radii, u1s, u2s, mtot, masses, radii, fluxratios, cfr,
-     lnprior, extra) = _hostpar.pmap_block(block, N, idxs, x_inc, x_q, x_w)
+     lnprior, extra) = _hostpar.pmap_block(block, N, idxs, x_inc, x_q, eccs, x_w)
     return _run_eb(N, host_masses, host_radii, u1s, u2s, P, mtot, incs, qs, eccs, argps, masses,
                    radii, fluxratios, cfr, lnprior, extra, True, scalar_loop=not parallel)
 
