@@ -35,7 +35,8 @@ def needs_build():
 
 def build_host(force=False):
     """gcc build of csrc/host_prep.c (OpenMP spline evaluation for the prior-draw preparation)."""
-    srcs = [os.path.join(CSRC, "host_prep.c"), os.path.join(CSRC, "host_rng.c")]
+    srcs = [os.path.join(CSRC, "host_prep.c"), os.path.join(CSRC, "host_rng.c"),
+            os.path.join(CSRC, "host_blocks.c")]
     if (not force and os.path.exists(HOST_SO_PATH)
             and os.path.getmtime(HOST_SO_PATH) >= max(os.path.getmtime(s) for s in srcs)):
         return HOST_SO_PATH

@@ -28,6 +28,7 @@ class LdcGrid:
         self.u1s = np.array(df[col_u1], dtype=float)
         self.u2s = np.array(df[col_u2], dtype=float)
         self._nearest_cache = {}
+        self._node_tables = {}
         self._uZ = _first_occurrence_unique(self.Zs)
         self._uT = _first_occurrence_unique(self.Teffs)
         self._ug = _first_occurrence_unique(self.loggs)
@@ -53,6 +54,23 @@ class LdcGrid:
         r = self._unique_row((self.Zs == this_Z) & (self.Teffs == this_Teff)
                              & (self.loggs == this_logg))
         return self.u1s[r].item(), self.u2s[r].item()
+
+    def node_table(self, Z):
+        """(sorted node codes Teff * 100 + round(logg * 10), u1, u2 in that order) of the grid
+        slice at the target's Z -- at_Z_rounded()'s look-up table, for csrc/host_blocks.c."""
+        key = float(Z)
+        if key not in self._node_tables:
+            at_Z = self.Zs == self.Zs[np.abs(self.Zs - Z).argmin()]
+            T_at, g_at = self.Teffs[at_Z], self.loggs[at_Z]
+            code_tab = T_at.astype(np.int64) * 100 + np.round(g_at * 10).astype(np.int64)
+            order = np.argsort(code_tab, kind="stable")
+            code_sorted = np.ascontiguousarray(code_tab[order])
+            if np.any(np.diff(code_sorted) == 0):
+                raise ValueError("can only convert an array of size 1 to a Python scalar")
+            self._node_tables[key] = (code_sorted,
+                                      np.ascontiguousarray(self.u1s[at_Z][order]),
+                                      np.ascontiguousarray(self.u2s[at_Z][order]))
+        return self._node_tables[key]
 
     # ---- bound companions: round onto the grid at the target's Z    :945-972 / :1160-1187
     def at_Z_rounded(self, Z, Teffs, loggs, Teff_cap):

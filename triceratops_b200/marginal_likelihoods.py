@@ -24,7 +24,7 @@ TP-type scenarios give the same numbers either way.
 import numpy as np
 from pandas import read_csv
 
-from . import _dispatch, _fastrng
+from . import _blocks, _dispatch, _fastrng
 from . import _hostpar
 from ._constants import G, Msun, Rsun, pi
 from ._ldc import grid_for
@@ -95,6 +95,20 @@ def _draw_ecc(N, planet, P_mean):
     return _fastrng.rand(N)
 
 
+def _prepare(kind, block, N, arrays, **ckw):
+    """Outputs of a scenario's element-wise preparation: csrc/host_blocks.c (one GIL-free call,
+    the same values bit for bit) when usable, else `block` chunk by chunk in Python threads."""
+    res = _blocks.run(kind, N, **ckw)
+    if res is None:
+        cc = ckw.get("contrast_curve_file")
+        if cc is not None and not _blocks.order_free(file_to_contrast_curve(cc)[1]):
+            # numpy.interp on this table depends on the order of the queries: all N in one
+            # call, as the reference makes it
+            return block(*arrays)
+        res = _hostpar.pmap_block(block, N, *arrays)
+    return res
+
+
 def _ecc_binary(x, P_mean):
     """In place: the binaries' eccentricities from the deviates _draw_ecc(N, False, .) drew."""
     np.power(x, 1.0 / (0.2 if P_mean <= 10 else 0.6), out=x)
@@ -120,9 +134,16 @@ class _PlanetDraws:
         return sample_rp(x_rp, host_masses, flatpriors), sample_inc(x_inc), sample_w(x_w)
 
     def finish(self, host_masses, flatpriors):
-        rps, incs, argps = _hostpar.pmap_block(
-            lambda x_rp, x_inc, x_w, m: self.transform(x_rp, x_inc, x_w, m, flatpriors),
-            len(self.x_rp), self.x_rp, self.x_inc, self.x_w, host_masses)
+        def block(x_rp, x_inc, x_w, m):
+            return self.transform(x_rp, x_inc, x_w, m, flatpriors)
+        N = len(self.x_rp)
+        arrays = (self.x_rp, self.x_inc, self.x_w, host_masses)
+        if np.ndim(host_masses) == 0:
+            rps, incs, argps = _prepare("TTP", block, N, arrays, M_s=host_masses, R_s=0.0,
+                                        Teff=0.0, x_rp=self.x_rp, x_inc=self.x_inc,
+                                        x_w=self.x_w, flatpriors=flatpriors)
+        else:
+            rps, incs, argps = _hostpar.pmap_block(block, N, *arrays)
         return rps, incs, self.eccs, argps
 
 
@@ -363,8 +384,10 @@ def lnZ_TEB(time: np.ndarray, flux: np.ndarray, sigma: float,
         radii, _ = stellar_relations(masses, np.full(len(qs), R_s), np.full(len(qs), Teff))
         return incs, qs, argps, masses, radii, _fluxratio(masses, M_s), M_s + masses
 
-    incs, qs, argps, masses, radii, fluxratios, mtot = _hostpar.pmap_block(
-        block, N, draws.x_inc, draws.x_q, draws.eccs, draws.x_w)
+    incs, qs, argps, masses, radii, fluxratios, mtot = _prepare(
+        "TEB", block, N, (draws.x_inc, draws.x_q, draws.eccs, draws.x_w), M_s=M_s, R_s=R_s,
+        Teff=Teff, x_inc=draws.x_inc, x_q=draws.x_q, x_e=draws.eccs, x_w=draws.x_w,
+        P_mean=P_mean)
     return _run_eb(N, M_s, R_s, u1, u2, P, mtot, incs, qs, draws.eccs, argps, masses, radii,
                    fluxratios, 0.0, None, None, False, scalar_loop=not parallel)
 
@@ -406,8 +429,12 @@ def lnZ_PTP(time: np.ndarray, flux: np.ndarray, sigma: float,
                                cc_term)
         return rps, incs, argps, fluxratios_comp, lnprior, qs_comp != 0.0
 
-    rps, incs, argps, fluxratios_comp, lnprior, extra = _hostpar.pmap_block(
-        block, N, comp.column(M_s), draws.x_rp, draws.x_inc, draws.x_w)
+    c_comp = comp.column(M_s)
+    rps, incs, argps, fluxratios_comp, lnprior, extra = _prepare(
+        "PTP", block, N, (c_comp, draws.x_rp, draws.x_inc, draws.x_w), M_s=M_s, R_s=R_s,
+        Teff=Teff, c_comp=c_comp, x_rp=draws.x_rp, x_inc=draws.x_inc, x_w=draws.x_w,
+        flatpriors=flatpriors, molusc=molusc_file is not None, filt=filt,
+        contrast_curve_file=contrast_curve_file, plx=plx, bound_kind="TP")
     return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, draws.eccs, argps, fluxratios_comp,
                    lnprior, extra, False)
 
@@ -450,8 +477,13 @@ def lnZ_PEB(time: np.ndarray, flux: np.ndarray, sigma: float,
         return (incs, qs, argps, masses, radii, fluxratios, M_s + masses, fluxratios_comp,
                 lnprior, qs_comp != 0.0)
 
+    c_comp = comp.column(M_s)
     (incs, qs, argps, masses, radii, fluxratios, mtot, fluxratios_comp, lnprior,
-     extra) = _hostpar.pmap_block(block, N, comp.column(M_s), draws.x_inc, draws.x_q, draws.eccs, draws.x_w)
+     extra) = _prepare(
+        "PEB", block, N, (c_comp, draws.x_inc, draws.x_q, draws.eccs, draws.x_w), M_s=M_s,
+        R_s=R_s, Teff=Teff, c_comp=c_comp, x_inc=draws.x_inc, x_q=draws.x_q, x_e=draws.eccs,
+        x_w=draws.x_w, P_mean=P_mean, molusc=molusc_file is not None, filt=filt,
+        contrast_curve_file=contrast_curve_file, plx=plx, bound_kind="EB")
     return _run_eb(N, M_s, R_s, u1, u2, P, mtot, incs, qs, draws.eccs, argps, masses, radii,
                    fluxratios, fluxratios_comp, lnprior, extra, False,
                    scalar_loop=not parallel)
@@ -503,8 +535,14 @@ def lnZ_STP(time: np.ndarray, flux: np.ndarray, sigma: float,
         return (rps, incs, argps, masses_comp, radii_comp, fluxratios_comp, u1s, u2s, lnprior,
                 qs_comp != 0.0)
 
+    c_comp = comp.column(M_s)
     (rps, incs, argps, masses_comp, radii_comp, fluxratios_comp, u1s, u2s, lnprior,
-     extra) = _hostpar.pmap_block(block, N, comp.column(M_s), draws.x_rp, draws.x_inc, draws.x_w)
+     extra) = _prepare(
+        "STP", block, N, (c_comp, draws.x_rp, draws.x_inc, draws.x_w), M_s=M_s, R_s=R_s,
+        Teff=Teff, c_comp=c_comp, x_rp=draws.x_rp, x_inc=draws.x_inc, x_w=draws.x_w,
+        flatpriors=flatpriors, molusc=molusc_file is not None, filt=filt,
+        contrast_curve_file=contrast_curve_file, plx=plx, bound_kind="TP",
+        ldc_grid=grid_for(mission), Z=Z, ldc_cap=10000)
     return _run_tp(N, masses_comp, radii_comp, u1s, u2s, P, masses_comp, rps, incs, draws.eccs,
                    argps, fluxratios_comp, lnprior, extra, True)
 
@@ -549,9 +587,14 @@ def lnZ_SEB(time: np.ndarray, flux: np.ndarray, sigma: float,
         return (incs, qs, argps, masses_comp, radii_comp, u1s, u2s, masses_comp + masses, masses,
                 radii, fluxratios, fluxratios_comp, lnprior, qs_comp != 0.0)
 
+    c_comp = comp.column(M_s)
     (incs, qs, argps, masses_comp, radii_comp, u1s, u2s, mtot, masses, radii, fluxratios,
-     fluxratios_comp, lnprior, extra) = _hostpar.pmap_block(
-        block, N, comp.column(M_s), draws.x_inc, draws.x_q, draws.eccs, draws.x_w)
+     fluxratios_comp, lnprior, extra) = _prepare(
+        "SEB", block, N, (c_comp, draws.x_inc, draws.x_q, draws.eccs, draws.x_w), M_s=M_s,
+        R_s=R_s, Teff=Teff, c_comp=c_comp, x_inc=draws.x_inc, x_q=draws.x_q, x_e=draws.eccs,
+        x_w=draws.x_w, P_mean=P_mean, molusc=molusc_file is not None, filt=filt,
+        contrast_curve_file=contrast_curve_file, plx=plx, bound_kind="EB",
+        ldc_grid=grid_for(mission), Z=Z, ldc_cap=13000)
     return _run_eb(N, masses_comp, radii_comp, u1s, u2s, P, mtot, incs, qs, draws.eccs,
                    argps, masses, radii, fluxratios, fluxratios_comp, lnprior, extra,
                    True, scalar_loop=not parallel)
@@ -587,8 +630,12 @@ def lnZ_DTP(time: np.ndarray, flux: np.ndarray, sigma: float,
                                     2.5 * np.log10(cfr / (1 - cfr)), _take(band, idxs))
         return rps, incs, argps, cfr, lnprior
 
-    rps, incs, argps, cfr, lnprior = _hostpar.pmap_block(block, N, idxs, draws.x_rp,
-                                                         draws.x_inc, draws.x_w)
+    rps, incs, argps, cfr, lnprior = _prepare(
+        "DTP", block, N, (idxs, draws.x_rp, draws.x_inc, draws.x_w), M_s=M_s, R_s=R_s,
+        Teff=Teff, idxs=idxs, x_rp=draws.x_rp, x_inc=draws.x_inc, x_w=draws.x_w,
+        flatpriors=flatpriors, contrast_curve_file=contrast_curve_file, N_comp=bg.N_comp,
+        population=_blocks.Population(None, None, None, None, bg.fluxratios, band, None, None,
+                                      None, None))
     return _run_tp(N, M_s, R_s, u1, u2, P, M_s, rps, incs, draws.eccs, argps, cfr, lnprior,
                    None, False)
 
@@ -625,8 +672,13 @@ def lnZ_DEB(time: np.ndarray, flux: np.ndarray, sigma: float,
                                     2.5 * np.log10(cfr / (1 - cfr)), _take(band, idxs))
         return incs, qs, argps, masses, radii, fluxratios, M_s + masses, cfr, lnprior
 
-    incs, qs, argps, masses, radii, fluxratios, mtot, cfr, lnprior = _hostpar.pmap_block(
-        block, N, idxs, draws.x_inc, draws.x_q, draws.eccs, draws.x_w)
+    incs, qs, argps, masses, radii, fluxratios, mtot, cfr, lnprior = _prepare(
+        "DEB", block, N, (idxs, draws.x_inc, draws.x_q, draws.eccs, draws.x_w), M_s=M_s,
+        R_s=R_s, Teff=Teff, idxs=idxs, x_inc=draws.x_inc, x_q=draws.x_q, x_e=draws.eccs,
+        x_w=draws.x_w, P_mean=P_mean, contrast_curve_file=contrast_curve_file,
+        N_comp=bg.N_comp,
+        population=_blocks.Population(None, None, None, None, bg.fluxratios, band, None, None,
+                                      None, None))
     return _run_eb(N, M_s, R_s, u1, u2, P, mtot, incs, qs, draws.eccs, argps, masses, radii,
                    fluxratios, cfr, lnprior, None, False, scalar_loop=not parallel)
 
@@ -661,11 +713,15 @@ def lnZ_BTP(time: np.ndarray, flux: np.ndarray, sigma: float,
         lnprior = _background_prior(bg, len(idxs), contrast_curve_file,
                                     2.5 * np.log10(cfr / (1 - cfr)), _take(band, idxs))
         extra = (_take(bg.loggs, idxs) >= 3.5) & (_take(bg.Teffs, idxs) <= 10000)
-        return (host_masses, rps, incs, argps, cfr, lnprior, extra, _take(radii_comp, idxs),
-                _take(u1s_comp, idxs), _take(u2s_comp, idxs))
+        return (host_masses, rps, incs, argps, cfr, lnprior, _take(radii_comp, idxs),
+                _take(u1s_comp, idxs), _take(u2s_comp, idxs), extra)
 
-    (host_masses, rps, incs, argps, cfr, lnprior, extra, host_radii, u1s,
-     u2s) = _hostpar.pmap_block(block, N, idxs, draws.x_rp, draws.x_inc, draws.x_w)
+    (host_masses, rps, incs, argps, cfr, lnprior, host_radii, u1s, u2s, extra) = _prepare(
+        "BTP", block, N, (idxs, draws.x_rp, draws.x_inc, draws.x_w), M_s=M_s, R_s=R_s,
+        Teff=Teff, idxs=idxs, x_rp=draws.x_rp, x_inc=draws.x_inc, x_w=draws.x_w,
+        flatpriors=flatpriors, contrast_curve_file=contrast_curve_file, N_comp=bg.N_comp,
+        population=_blocks.Population(bg.masses, radii_comp, bg.Teffs, bg.loggs, bg.fluxratios,
+                                      band, None, None, u1s_comp, u2s_comp))
     return _run_tp(N, host_masses, host_radii, u1s, u2s, P, host_masses, rps, incs, draws.eccs,
                    argps, cfr, lnprior, extra, True)
 
@@ -728,7 +784,13 @@ def lnZ_BEB(time: np.ndarray, flux: np.ndarray, sigma: float,
                 lnprior, extra)
 
     (incs, qs, argps, host_masses, host_radii, u1s, u2s, mtot, masses, radii, fluxratios, cfr,
-     lnprior, extra) = _hostpar.pmap_block(block, N, idxs, x_inc, x_q, eccs, x_w)
+     lnprior, extra) = _prepare(
+        "BEB", block, N, (idxs, x_inc, x_q, eccs, x_w), M_s=M_s, R_s=R_s, Teff=Teff, idxs=idxs,
+        x_inc=x_inc, x_q=x_q, x_e=eccs, x_w=x_w, P_mean=P_mean, filt=filt,
+        contrast_curve_file=contrast_curve_file, N_comp=bg.N_comp,
+        population=_blocks.Population(bg.masses, radii_comp, bg.Teffs, bg.loggs, bg.fluxratios,
+                                      None, band_fluxratios["TESS"], band_fluxratios[cc_band],
+                                      u1s_comp, u2s_comp))
     return _run_eb(N, host_masses, host_radii, u1s, u2s, P, mtot, incs, qs, eccs, argps, masses,
                    radii, fluxratios, cfr, lnprior, extra, True, scalar_loop=not parallel)
 

@@ -18,13 +18,9 @@ from ._constants import G, Msun, au, pi
 from .funcs import separation_at_contrast
 
 
-def _piecewise_powerlaw(x, select, edges, powers, amps):
-    """In-place inverse-CDF transform of uniform deviates onto a broken power law.
-
-    Segment k spans [edges[k], edges[k+1]] with density amps[k] * r**powers[k].  Only elements
-    where `select` is true are touched; deviates beyond the last CDF knot are left as they are
-    (as in the reference, priors.py:54-111).
-    """
+def powerlaw_tables(edges, powers, amps):
+    """(segment integrals, their running sums, 1 / total) of a broken power law -- the scalars
+    of the inverse-CDF transform, shared by the numpy path below and csrc/host_blocks.c."""
     nseg = len(powers)
     integrals = []
     for k in range(nseg):
@@ -36,7 +32,18 @@ def _piecewise_powerlaw(x, select, edges, powers, amps):
     for k in range(1, nseg):
         tot = tot + integrals[k]
         cum.append(tot)
-    norm = 1 / tot
+    return integrals, cum, 1 / tot
+
+
+def _piecewise_powerlaw(x, select, edges, powers, amps):
+    """In-place inverse-CDF transform of uniform deviates onto a broken power law.
+
+    Segment k spans [edges[k], edges[k+1]] with density amps[k] * r**powers[k].  Only elements
+    where `select` is true are touched; deviates beyond the last CDF knot are left as they are
+    (as in the reference, priors.py:54-111).
+    """
+    nseg = len(powers)
+    integrals, cum, norm = powerlaw_tables(edges, powers, amps)
 
     def transform(xv, sel):
         # all segment masks are taken from the untouched deviates before any is overwritten
@@ -64,18 +71,29 @@ def _piecewise_powerlaw(x, select, edges, powers, amps):
 def sample_rp(x, M_s, flatpriors):
     """Planet radii [R_earth] from uniform deviates x, conditioned on host mass (priors.py:16-116)."""
     if flatpriors == False:  # noqa: E712  (the reference accepts numpy bools here)
-        edges = (0.5, 3.0, 6.0, 20.0)
         # two mass regimes with different middle slopes; their selections are disjoint, so the
         # second pass still sees untouched deviates
-        for powers, select in (((0.0, -4.0, -0.5), M_s > 0.45), ((0.0, -7.0, -0.5), M_s <= 0.45)):
-            p1, p2, p3 = powers
-            A1 = edges[1] ** p1 / edges[1] ** p2
-            A2 = edges[2] ** p2 / edges[2] ** p3
-            _piecewise_powerlaw(x, select, edges, powers, (1.0, A1, A2 * A1))
+        (hi, lo) = rp_specs()
+        _piecewise_powerlaw(x, M_s > 0.45, *hi)
+        _piecewise_powerlaw(x, M_s <= 0.45, *lo)
         return x
     elif flatpriors == True:  # noqa: E712
-        A = 1 / 19.5
-        return x / A + 0.5
+        return x / RP_FLAT_A + 0.5
+
+
+RP_FLAT_A = 1 / 19.5
+
+
+def rp_specs():
+    """(edges, powers, amps) of the planet-radius law for hosts above / not above 0.45 Msun."""
+    edges = (0.5, 3.0, 6.0, 20.0)
+    out = []
+    for powers in ((0.0, -4.0, -0.5), (0.0, -7.0, -0.5)):
+        p1, p2, p3 = powers
+        A1 = edges[1] ** p1 / edges[1] ** p2
+        A2 = edges[2] ** p2 / edges[2] ** p3
+        out.append((edges, powers, (1.0, A1, A2 * A1)))
+    return tuple(out)
 
 
 def sample_inc(x, lower=0, upper=90):
@@ -102,8 +120,13 @@ def sample_w(x):
     return x * 360
 
 
-def _sample_mass_ratio(x, M_s, p2, F_twin):
-    """Shared body of sample_q / sample_q_companion (priors.py:168-274 / :277-383)."""
+Q_LAW = (-0.5, 0.30)             # (p2, F_twin) of sample_q
+Q_COMPANION_LAW = (-0.95, 0.05)   # ... and of sample_q_companion
+
+
+def mass_ratio_spec(M_s, p2, F_twin):
+    """(edges, powers, amps) of the mass-ratio law for primary mass M_s, or None when every
+    mass ratio is 1 (M_s <= 0.1 Msun)."""
     p1 = 0.3
     e2 = p2 + 1
     if M_s >= 1.0 or (M_s < 1.0) & (M_s >= 0.3):
@@ -112,39 +135,41 @@ def _sample_mass_ratio(x, M_s, p2, F_twin):
         A2 = (1 + (F_twin) / (1 - F_twin)
               * ((1.0 ** e2 - 0.3 ** e2) / e2)
               / ((1.0 ** e2 - 0.95 ** e2) / e2))
-        return _piecewise_powerlaw(x, None, (q_lo, 0.3, 0.95, 1.0), (p1, p2, p2),
-                                   (1.0, A1, A2 * A1))
+        return (q_lo, 0.3, 0.95, 1.0), (p1, p2, p2), (1.0, A1, A2 * A1)
     if (M_s < 0.3) & (M_s > 0.1):
         q_lo = 0.1 / M_s
         A2 = (1 + (F_twin) / (1 - F_twin)
               * ((1.0 ** e2 - q_lo ** e2) / e2)
               / ((1.0 ** e2 - 0.95 ** e2) / e2))
-        return _piecewise_powerlaw(x, None, (q_lo, 0.95, 1.0), (p2, p2), (1.0, A2))
-    return np.full(len(x), 1.0)
+        return (q_lo, 0.95, 1.0), (p2, p2), (1.0, A2)
+    return None
+
+
+def _sample_mass_ratio(x, M_s, p2, F_twin):
+    """Shared body of sample_q / sample_q_companion (priors.py:168-274 / :277-383)."""
+    spec = mass_ratio_spec(M_s, p2, F_twin)
+    if spec is None:
+        return np.full(len(x), 1.0)
+    return _piecewise_powerlaw(x, None, *spec)
 
 
 def sample_q(x, M_s):
     """Mass ratios of short-period binaries (priors.py:168-274)."""
-    return _sample_mass_ratio(x, M_s, -0.5, 0.30)
+    return _sample_mass_ratio(x, M_s, *Q_LAW)
 
 
 def sample_q_companion(x, M_s):
     """Mass ratios of long-period bound companions (priors.py:277-383)."""
-    return _sample_mass_ratio(x, M_s, -0.95, 0.05)
+    return _sample_mass_ratio(x, M_s, *Q_COMPANION_LAW)
 
 
-def _bound_companion_lnprior(M_s, plx, delta_mags, separations, contrasts, first_decade):
-    """ln of the fraction of targets with a bound companion inside the contrast-curve limit.
-
-    Piecewise period distribution of Moe & Di Stefano (2017) integrated from log P = 1 (EB
-    scenarios, first_decade=True; priors.py:784-984) or from log P = 3.4 (planet scenarios,
-    first_decade=False; priors.py:580-782) up to the period of the widest allowed orbit.
-    """
+def bound_constants(M_s, plx):
+    """The scalars of the bound-companion prior (period-distribution coefficients of Moe &
+    Di Stefano 2017 for primary mass M_s and the segment integrals), shared by the numpy path
+    below and csrc/host_blocks.c."""
     if np.isnan(plx):
         plx = 0.1
     d = 1000 / plx
-    seps = d * separation_at_contrast(delta_mags, separations, contrasts)
-
     M_act = M_s
     if not (M_s >= 1.0):
         M_s = 1.0
@@ -161,6 +186,23 @@ def _bound_companion_lnprior(M_s, plx, delta_mags, separations, contrasts, first
     t4 = (alpha * dlogP * (5.5 - 3.4) + f2 * (5.5 - 3.4)
           + slope2 * (0.238095 * 5.5 ** 2 - 0.952381 * 5.5 + 0.485714))
     t5 = f3 * (3.33333 - 17.3566 * np.exp(-0.3 * 8.0))
+    return dict(d=d, M_act=M_act, M_s=M_s, f1=f1, f2=f2, f3=f3, alpha=alpha, dlogP=dlogP,
+                slope=slope, slope2=slope2, t2=t2, t3=t3, t4=t4, t5=t5)
+
+
+def _bound_companion_lnprior(M_s, plx, delta_mags, separations, contrasts, first_decade):
+    """ln of the fraction of targets with a bound companion inside the contrast-curve limit.
+
+    Piecewise period distribution of Moe & Di Stefano (2017) integrated from log P = 1 (EB
+    scenarios, first_decade=True; priors.py:784-984) or from log P = 3.4 (planet scenarios,
+    first_decade=False; priors.py:580-782) up to the period of the widest allowed orbit.
+    """
+    K = bound_constants(M_s, plx)
+    d, M_act, M_s = K["d"], K["M_act"], K["M_s"]
+    f1, f2, f3, alpha, dlogP = K["f1"], K["f2"], K["f3"], K["alpha"], K["dlogP"]
+    slope, slope2 = K["slope"], K["slope2"]
+    t2, t3, t4, t5 = K["t2"], K["t3"], K["t4"], K["t5"]
+    seps = d * separation_at_contrast(delta_mags, separations, contrasts)
 
     def fraction(seps):
         max_Porbs = ((4 * pi ** 2) / (G * M_s * Msun) * (seps * au) ** 3) ** (1 / 2) / 86400
