@@ -138,6 +138,20 @@ def _pinned_like(torch, a):
     return t, out
 
 
+def _host_threads():
+    from triceratops_b200 import _hostpar
+    return int(_hostpar.N_THREADS)
+
+
+def _host_preparation():
+    """Which code turns the prior deviates into engine columns in the e2e leg."""
+    from triceratops_b200 import _blocks, _fastrng
+    return {"draws": "csrc/host_rng.c (numpy's MT19937 stream, bit-identical)"
+            if _fastrng._load() is not None else "numpy",
+            "transforms": "csrc/host_blocks.c (numpy's statements in C, bit-identical)"
+            if _blocks.available() else "numpy in threads"}
+
+
 def _cpu_model():
     try:
         for ln in open("/proc/cpuinfo"):
@@ -505,7 +519,8 @@ def run_ours(args):
         "roofline": roofline,
         "clocks": clocks,
         "host_prior_draws_s": host_prep_s,
-        "host": {"cores": _host_cores(), "cpu": _cpu_model()},
+        "host": {"cores": _host_cores(), "cpu": _cpu_model(),
+                 "threads": _host_threads(), "preparation": _host_preparation()},
         "lnZ_check": [float(x) for x in lnZ[:3]],
     }
 

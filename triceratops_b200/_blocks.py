@@ -15,6 +15,7 @@ host-side preparation of the prior draws, not the light-curve path.
 """
 import ctypes
 import os
+import threading
 
 import numpy as np
 
@@ -189,6 +190,12 @@ class Population:
                                u1s, u2s)]
 
 
+def _block_threads(n):
+    """OpenMP threads of one scenario block (TRI_B200_BLOCK_THREADS; default: the host threads)."""
+    v = os.environ.get("TRI_B200_BLOCK_THREADS")
+    return max(1, int(v)) if v else n
+
+
 def run(kind, N, *, M_s, R_s, Teff, x_inc, x_w, x_rp=None, x_q=None, x_e=None, c_comp=None,
         idxs=None, flatpriors=False, molusc=False, P_mean=None, filt="TESS",
         contrast_curve_file=None, plx=None, bound_kind=None, ldc_grid=None, Z=None,
@@ -205,7 +212,7 @@ def run(kind, N, *, M_s, R_s, Teff, x_inc, x_w, x_rp=None, x_q=None, x_e=None, c
     keep = []
     A = _Args()
     A.kind, A.N = KINDS.index(kind), int(N)
-    A.nthreads = 1 if _inline() else int(N_THREADS)
+    A.nthreads = 1 if _inline() else _block_threads(int(N_THREADS))
     A.flatpriors = int(bool(flatpriors))
     A.molusc = int(bool(molusc))
     A.has_cc = int(contrast_curve_file is not None)
@@ -334,15 +341,24 @@ def run(kind, N, *, M_s, R_s, Teff, x_inc, x_w, x_rp=None, x_q=None, x_e=None, c
 
 
 # ---- once per process: the C path against the numpy path ---------------------------------------
+_state_lock = threading.Lock()
+
+
 def available():
+    """True when run() may be used (checked once per process; scenario threads that arrive
+    while the check runs wait for its verdict)."""
     global _state
     if _state is None:
-        _state = False
-        if os.environ.get("TRI_B200_NUMPY_BLOCKS") != "1" and os.path.exists(_build.HOST_SO_PATH):
-            try:
-                _load()
-                from . import _blocks_check
-                _state = bool(_blocks_check.self_check())
-            except Exception:
-                _state = False
+        with _state_lock:
+            if _state is None:
+                ok = False
+                if (os.environ.get("TRI_B200_NUMPY_BLOCKS") != "1"
+                        and os.path.exists(_build.HOST_SO_PATH)):
+                    try:
+                        _load()
+                        from . import _blocks_check
+                        ok = bool(_blocks_check.self_check())
+                    except Exception:
+                        ok = False
+                _state = ok
     return _state
