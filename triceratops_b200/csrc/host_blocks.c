@@ -135,7 +135,48 @@ static void v_pow_op(const np_fn* f, const double* x, double e, double* out, int
 }
 
 /* ---- FITPACK splev (same recurrence as csrc/host_prep.c) ------------------------------------ */
+/* One de Boor step: f = hh / (T[li] - T[lj]) (or the zero-width rule), the two updates. */
+#define DEBOOR(hq, hq1, hh, li, lj)                          \
+    do {                                                     \
+        const double tli = T[li], tlj = T[lj];               \
+        if (tli == tlj) {                                    \
+            hq1 = 0.0;                                       \
+        } else {                                             \
+            const double f = (hh) / (tli - tlj);             \
+            hq = hq + f * (tli - arg);                       \
+            hq1 = f * (arg - tlj);                           \
+        }                                                    \
+    } while (0)
+
+/* cubic splines (every relation of funcs.py is one): the generic recurrence below written out
+ * for k = 3, operation for operation, and the knot interval found by counting instead of by
+ * bisection (the knots are few and sorted: the same interval, without unpredictable branches) */
+static inline double splev_cubic(const tb_spline* s, double arg) {
+    const int nk1 = s->n - 4;
+    const double* T = s->t - 1;
+    const double* C = s->c - 1;
+    int l = 4;
+    for (int i = 5; i <= nk1; i++) l += (arg >= T[i]);
+    double h1 = 1.0, h2 = 0.0, h3 = 0.0, h4 = 0.0, a, b, c;
+    a = h1; h1 = 0.0;
+    DEBOOR(h1, h2, a, l + 1, l);
+    a = h1; b = h2; h1 = 0.0;
+    DEBOOR(h1, h2, a, l + 1, l - 1);
+    DEBOOR(h2, h3, b, l + 2, l);
+    a = h1; b = h2; c = h3; h1 = 0.0;
+    DEBOOR(h1, h2, a, l + 1, l - 2);
+    DEBOOR(h2, h3, b, l + 2, l - 1);
+    DEBOOR(h3, h4, c, l + 3, l);
+    double sp = 0.0;
+    sp = sp + C[l - 3] * h1;
+    sp = sp + C[l - 2] * h2;
+    sp = sp + C[l - 1] * h3;
+    sp = sp + C[l] * h4;
+    return sp;
+}
+
 static inline double splev1(const tb_spline* s, double arg) {
+    if (s->k == 3) return splev_cubic(s, arg);
     const int k = s->k, k1 = k + 1, nk1 = s->n - k1;
     const double* T = s->t - 1;
     const double* C = s->c - 1;
@@ -205,6 +246,38 @@ static int64_t search_with_guess(double key, const double* arr, int64_t len, int
     return imin - 1;
 }
 
+/* Keys for which the search cannot depend on where it starts: every comparison `key >= arr[i]`
+ * is then true up to some index and false after it, as on a sorted table, and any search finds
+ * the same interval.  A key k is unsafe only if an out-of-order pair i < i', arr[i] > arr[i']
+ * has arr[i'] <= k < arr[i]; [*lo, *hi) covers all of those (empty when the table is sorted). */
+static void unsafe_keys(const double* arr, int64_t len, double* lo, double* hi) {
+    *lo = INFINITY;
+    *hi = -INFINITY;
+    for (int64_t i = 0; i < len; i++) {
+        if (isnan(arr[i])) { *lo = -INFINITY; *hi = INFINITY; return; }
+        for (int64_t k = i + 1; k < len; k++) {
+            if (arr[i] > arr[k]) {
+                if (arr[k] < *lo) *lo = arr[k];
+                if (arr[i] > *hi) *hi = arr[i];
+            }
+        }
+    }
+}
+
+/* the interval numpy's search returns for a safe key: the last index with arr[idx] <= key,
+ * -1 below the table, len above it */
+static inline int64_t search_sorted(double key, const double* arr, int64_t len) {
+    if (key > arr[len - 1]) return len;
+    if (key < arr[0]) return -1;
+    int64_t lo = 0, n = len;
+    while (n > 1) {
+        const int64_t half = n >> 1;
+        lo = (key >= arr[lo + half]) ? lo + half : lo;
+        n -= half;
+    }
+    return lo;
+}
+
 static inline double interp_at(double xv, int64_t j, const double* xp, const double* fp,
                                int64_t nxp) {
     if (j == -1) return fp[0];
@@ -231,13 +304,17 @@ static void v_interp(const double* x, const double* xp, const double* fp, int64_
         return;
     }
     /* (numpy tabulates the slopes when nxp <= m: the same quotient either way) */
+    double ulo, uhi;
+    unsafe_keys(xp, nxp, &ulo, &uhi);
     int64_t j = 0;
     for (int64_t i = 0; i < m; i++) {
         const double xv = x[i];
         if (isnan(xv)) {
             out[i] = xv;
         } else {
-            j = search_with_guess(xv, xp, nxp, j);
+            /* numpy's guess-based search only where its starting point could matter */
+            j = (xv >= ulo && xv < uhi) ? search_with_guess(xv, xp, nxp, j)
+                                        : search_sorted(xv, xp, nxp);
             out[i] = interp_at(xv, j, xp, fp, nxp);
         }
         if (jrec) jrec[i] = (int32_t)j;
@@ -322,10 +399,10 @@ static void v_stellar(const tb_args* A, const double* mass, const double* maxR, 
         double r = 0.0, t = 0.0;
         if (x > 0.63) {
             r = splev1(&A->hot_R, x);
-            t = splev1(&A->hot_T, x);
+            if (T) t = splev1(&A->hot_T, x);
         } else if (x <= 0.63) {
             r = splev1(&A->cool_R, x);
-            t = splev1(&A->cool_T, x);
+            if (T) t = splev1(&A->cool_T, x);
         }
         const double cr = maxR ? maxR[i] : maxR_s, ct = maxT ? maxT[i] : maxT_s;
         if (r > cr) r = cr;
@@ -716,11 +793,15 @@ static void stitch_interp(const tb_args* A) {
     double* lnprior = A->out[lnprior_col[A->kind]];
     int32_t* jrec = A->interp_j;
     int64_t g = 0;
+    double ulo, uhi;
+    unsafe_keys(xp, nxp, &ulo, &uhi);
     for (int64_t lo = 0; lo < A->N; lo += CH) {
         const int64_t hi = lo + CH < A->N ? lo + CH : A->N;
         for (int64_t i = lo; lo > 0 && i < hi; i++) {
             const double delta = A->interp_delta[i], xv = fabs(delta);
-            const int64_t jt = isnan(xv) ? g : search_with_guess(xv, xp, nxp, g);
+            const int64_t jt = isnan(xv) ? g
+                               : (xv >= ulo && xv < uhi) ? search_with_guess(xv, xp, nxp, g)
+                                                         : search_sorted(xv, xp, nxp);
             if (jt == jrec[i]) break;
             if (!isnan(xv)) {
                 double sep = interp_at(xv, jt, xp, fp, nxp), ex;
