@@ -20,7 +20,6 @@ import threading
 import numpy as np
 
 from . import _build
-from ._bufpool import empty as _empty
 
 KINDS = ("TTP", "TEB", "PTP", "PEB", "STP", "SEB", "DTP", "DEB", "BTP", "BEB")
 #: number of float64 output columns per kind, and whether a boolean `extra` mask comes with them
@@ -323,16 +322,16 @@ def run(kind, N, *, M_s, R_s, Teff, x_inc, x_w, x_rp=None, x_q=None, x_e=None, c
     elif kind in ("DTP", "DEB", "BTP", "BEB") and A.bgp.mode == 1:
         table = cons
     if table is not None and not order_free(table):
-        delta, jrec = _empty(N), _empty(N, np.int32)
+        delta, jrec = np.empty(N), np.empty(N, dtype=np.int32)
         keep += [delta, jrec]
         A.interp_delta, A.interp_j = _dp(delta), jrec.ctypes.data_as(
             ctypes.POINTER(ctypes.c_int32))
-    outs = [_empty(N) for _ in range(N_OUT[kind])]
+    outs = [np.empty(N) for _ in range(N_OUT[kind])]
     for i, o in enumerate(outs):
         A.out[i] = _dp(o)
     extra = None
     if kind in HAS_EXTRA:
-        extra = _empty(N, bool)
+        extra = np.empty(N, dtype=bool)
         A.extra = extra.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
     rc = L.trih_scenario_block(ctypes.byref(A))
     del keep

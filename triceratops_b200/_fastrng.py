@@ -26,7 +26,6 @@ import os
 import numpy as np
 
 from . import _build
-from ._bufpool import empty as _empty
 
 _U32 = ctypes.POINTER(ctypes.c_uint32)
 _D = ctypes.POINTER(ctypes.c_double)
@@ -127,7 +126,7 @@ def rand(n):
     n = int(n)
     if n < MIN_N or _load() is None:
         return np.random.rand(n)
-    out = _rand(n, _empty(n))
+    out = _rand(n, np.empty(n))
     return out if out is not None else np.random.rand(n)
 
 
@@ -143,7 +142,7 @@ def uniform(low, high, n):
     n = int(n)
     if n < MIN_N or _load() is None:
         return np.random.uniform(low=low, high=high, size=n)
-    out = _rand(n, _empty(n))
+    out = _rand(n, np.empty(n))
     if out is None:
         return np.random.uniform(low=low, high=high, size=n)
     return float(low) + (float(high) - float(low)) * out
@@ -158,7 +157,7 @@ def randint(low, high, n, _force=False):
     if s is None:
         return np.random.randint(low, high, n)
     st, key, pos = s
-    out = _empty(n, np.int64)
+    out = np.empty(n, dtype=np.int64)
     if _lib.trih_mt_randint(key.ctypes.data_as(_U32), ctypes.byref(pos), low, rng,
                             out.ctypes.data_as(_I64), n) != 0:
         return np.random.randint(low, high, n)
@@ -191,7 +190,7 @@ def beta_rvs(a, b, n, _force=False):
     from ._hostpar import N_THREADS
     key, pos = np.array(st[1], dtype=np.uint32), ctypes.c_int32(int(st[2]))
     has_gauss, gauss = ctypes.c_int32(int(st[3])), ctypes.c_double(float(st[4]))
-    out = _empty(n)
+    out = np.empty(n)
     rc = _lib.trih_legacy_beta(key.ctypes.data_as(_U32), ctypes.byref(pos),
                                ctypes.byref(has_gauss), ctypes.byref(gauss), float(a), float(b),
                                out.ctypes.data_as(_D), n, int(N_THREADS))

@@ -88,8 +88,7 @@ def take(table, idx):
             or idx.ndim != 1 or idx.size < 4096
             or not table.flags.c_contiguous or not idx.flags.c_contiguous):
         return table[idx]
-    from ._bufpool import empty as _empty
-    out = _empty(idx.size)
+    out = np.empty(idx.size)
     rc = L.trih_take_f64(table.ctypes.data_as(_D), table.size,
                          idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                          out.ctypes.data_as(_D), idx.size, _c_threads(min(N_THREADS, 8)))
