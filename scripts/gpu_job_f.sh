@@ -1,12 +1,15 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python scripts/host_only.py > gpurun_out/r2_host_only.json 2> gpurun_out/r2_host_only.err; cat gpurun_out/r2_host_only.json; tail -3 gpurun_out/r2_host_only.err
-TRI_B200_SCENARIO_THREADS=1 python scripts/host_only.py > gpurun_out/r2_host_only_st1.json 2>/dev/null; cat gpurun_out/r2_host_only_st1.json
-timeout 300 python bench.py --steps 6 --warmup 3 --no-parity --no-cpu-baseline > gpurun_out/r2_bench_g.json 2> gpurun_out/r2_bench_g.err
-python - <<PY
-import json
-d=json.load(open("gpurun_out/r2_bench_g.json"))
-e=d["e2e"]
-print("e2e_ms", round(e["ms_per_step"],1), [round(x,3) for x in e["all_walls_s"]], "engine", round(e["engine"]["ms_per_step"],1), "dev", round(e["device_sampler"]["ms_per_step"],1))
-PY
-timeout 200 python scripts/chain_trace.py --json gpurun_out/r2_chain_h_full.json > gpurun_out/r2_chain_h.json 2>/dev/null; cut -c1-400 gpurun_out/r2_chain_h.json
+: > gpurun_out/r2_sweep_config5.jsonl
+run() { # workers threads sampler tois
+  TRI_B200_HOST_THREADS=$2 TRI_B200_SCENARIO_THREADS=${5:-1} timeout 400 python scripts/sweep_config5.py --tois $4 --draws 1000000 --workers-per-gpu $1 --sampler $3 2>/dev/null | tail -1 | python -c "
+import sys, json
+d=json.loads(sys.stdin.readline()); d['host_threads_per_worker']=$2; d['scenario_threads']=${5:-1}
+print(json.dumps(d))" | tee -a gpurun_out/r2_sweep_config5.jsonl | cut -c100-420
+}
+run 16 1 host 64
+run 8 2 host 64
+run 4 4 host 64 2
+run 2 8 host 48 4
+run 1 16 host 32 4
+run 2 4 device 96
