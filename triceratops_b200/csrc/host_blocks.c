@@ -21,6 +21,26 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef TB_PROFILE        /* section timers (single-threaded runs only): gcc -DTB_PROFILE */
+#include <stdio.h>
+#include <x86intrin.h>
+enum { S_PIECE, S_INC, S_STELLAR, S_FLUX, S_INTERP, S_BOUND, S_BG, S_LDC, S_TAKE, S_ECC, S_N };
+static const char* s_names[S_N] = {"piecewise", "inc", "stellar", "fluxratio", "interp",
+                                   "bound_rest", "background_rest", "ldc", "take", "ecc"};
+static unsigned long long s_acc[S_N];
+#define TIC unsigned long long _t0 = __rdtsc()
+#define TOC(k) s_acc[k] += __rdtsc() - _t0
+void trih_block_profile_dump(double per) {
+    for (int i = 0; i < S_N; i++) {
+        fprintf(stderr, "%-16s %8.1f\n", s_names[i], (double)s_acc[i] / per);
+        s_acc[i] = 0;
+    }
+}
+#else
+#define TIC ((void)0)
+#define TOC(k) ((void)0)
+#endif
+
 #define CH 8192                 /* elements per chunk: ~25 live arrays of 64 KB stay in L2 */
 #define NBUF 28
 
@@ -326,11 +346,123 @@ typedef struct {
     double* b[NBUF];
     int32_t* ix;
     uint8_t* sel;
+    int32_t* perm;        /* splev_many: draws grouped by knot interval */
+    int32_t* subset;      /* v_stellar: the draws of one mass branch */
+    uint8_t* l8;          /* splev_many: knot interval of every draw */
 } scratch;
+
+#if defined(__GNUC__) && defined(__x86_64__)
+#define CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define CLONES
+#endif
+
+/* The cubic de Boor recurrence of splev_cubic for draws that share the knot interval l: the
+ * knots and coefficients are loop constants, the loop body is straight-line IEEE arithmetic on
+ * the argument (the same operations in the same order, so the same bits) and vectorises,
+ * divisions included.  Requires the six knot differences to be non-zero (the caller checks). */
+CLONES static void deboor3_run(const double* T, const double* C, int l, const double* xin,
+                               double* xout, int64_t n) {
+    const double tm2 = T[l - 2], tm1 = T[l - 1], t0 = T[l], t1 = T[l + 1], t2 = T[l + 2],
+                 t3 = T[l + 3];
+    const double c0 = C[l - 3], c1 = C[l - 2], c2 = C[l - 1], c3 = C[l];
+    const double f1 = 1.0 / (t1 - t0);
+    const double d21 = t1 - tm1, d22 = t2 - t0, d31 = t1 - tm2, d32 = t2 - tm1, d33 = t3 - t0;
+    for (int64_t q = 0; q < n; q++) {
+        const double arg = xin[q];
+        double h1, h2, h3, h4, a, b, c, f;
+        h1 = 0.0 + f1 * (t1 - arg);
+        h2 = f1 * (arg - t0);
+        a = h1; b = h2;
+        f = a / d21;
+        h1 = 0.0 + f * (t1 - arg);
+        h2 = f * (arg - tm1);
+        f = b / d22;
+        h2 = h2 + f * (t2 - arg);
+        h3 = f * (arg - t0);
+        a = h1; b = h2; c = h3;
+        f = a / d31;
+        h1 = 0.0 + f * (t1 - arg);
+        h2 = f * (arg - tm2);
+        f = b / d32;
+        h2 = h2 + f * (t2 - arg);
+        h3 = f * (arg - tm1);
+        f = c / d33;
+        h3 = h3 + f * (t3 - arg);
+        h4 = f * (arg - t0);
+        double sp = 0.0;
+        sp = sp + c0 * h1;
+        sp = sp + c1 * h2;
+        sp = sp + c2 * h3;
+        sp = sp + c3 * h4;
+        xout[q] = sp;
+    }
+}
+
+/* out[i] = spline(x[i]) for the draws i = sel[0..n) (sel == NULL: i = 0..n).  Cubic splines:
+ * the draws are grouped by knot interval (counting sort) and every group runs through
+ * deboor3_run; anything else goes draw by draw through splev1. */
+static void splev_many(const tb_spline* s, const double* x, const int32_t* sel, int64_t n,
+                       double* out, scratch* W) {
+    if (n <= 0) return;
+    if (s->k != 3 || s->n - 4 > 250) {
+        for (int64_t q = 0; q < n; q++) {
+            const int64_t i = sel ? sel[q] : q;
+            out[i] = splev1(s, x[i]);
+        }
+        return;
+    }
+    const int nk1 = s->n - 4;
+    const double* T = s->t - 1;
+    const double* C = s->c - 1;
+    double* tin = W->b[NBUF - 2];
+    double* tout = W->b[NBUF - 3];
+    double* arg = W->b[NBUF - 4];
+    uint8_t* l8 = W->l8;
+    if (sel) {
+        for (int64_t q = 0; q < n; q++) arg[q] = x[sel[q]];
+    } else {
+        memcpy(arg, x, (size_t)n * sizeof(double));
+    }
+    /* knot interval of every draw: 4 + the number of interior knots at or below it */
+    for (int64_t q = 0; q < n; q++) l8[q] = 4;
+    for (int i = 5; i <= nk1; i++) {
+        const double knot = T[i];
+        for (int64_t q = 0; q < n; q++) l8[q] += (uint8_t)(arg[q] >= knot);
+    }
+    int32_t count[256] = {0}, start[256] = {0}, fill[256];
+    for (int64_t q = 0; q < n; q++) count[l8[q]]++;
+    int32_t acc = 0;
+    for (int l = 4; l <= nk1; l++) { start[l] = acc; acc += count[l]; }
+    memcpy(fill, start, sizeof(fill));
+    for (int64_t q = 0; q < n; q++) {
+        const int32_t pos = fill[l8[q]]++;
+        W->perm[pos] = (int32_t)q;
+        tin[pos] = arg[q];
+    }
+    for (int l = 4; l <= nk1; l++) {
+        const int32_t c = count[l];
+        if (!c) continue;
+        const int64_t o = start[l];
+        const int flat = T[l + 1] == T[l] || T[l + 1] == T[l - 1] || T[l + 2] == T[l]
+                         || T[l + 1] == T[l - 2] || T[l + 2] == T[l - 1] || T[l + 3] == T[l];
+        if (flat) {
+            for (int64_t q = o; q < o + c; q++) tout[q] = splev_cubic(s, tin[q]);
+        } else {
+            deboor3_run(T, C, l, tin + o, tout + o, c);
+        }
+    }
+    if (sel) {
+        for (int64_t q = 0; q < n; q++) out[sel[W->perm[q]]] = tout[q];
+    } else {
+        for (int64_t q = 0; q < n; q++) out[W->perm[q]] = tout[q];
+    }
+}
 
 /* ---- priors.py: _piecewise_powerlaw ---------------------------------------------------------- */
 static void v_piecewise(const tb_args* A, const tb_powerlaw* S, const double* x, const uint8_t* sel,
                         double* out, int64_t m, scratch* W) {
+    TIC;
     double* tmp = W->b[NBUF - 1];
     int32_t* ix = W->ix;
     for (int k = 0; k < S->nseg; k++) {
@@ -339,7 +471,8 @@ static void v_piecewise(const tb_args* A, const tb_powerlaw* S, const double* x,
             int in = x[i] <= S->knot[k];
             if (k > 0) in = (x[i] > S->knot[k - 1]) & in;
             if (sel) in = in & sel[i];
-            if (in) ix[c++] = (int32_t)i;
+            ix[c] = (int32_t)i;                 /* (branch-free compaction) */
+            c += in;
         }
         if (!c) continue;
         for (int64_t q = 0; q < c; q++) {
@@ -352,6 +485,7 @@ static void v_piecewise(const tb_args* A, const tb_powerlaw* S, const double* x,
         v_pow_op(&A->f_pow, tmp, S->inv[k], tmp, c);
         for (int64_t q = 0; q < c; q++) out[ix[q]] = tmp[q];
     }
+    TOC(S_PIECE);
 }
 
 /* sample_q / sample_q_companion: the deviates become mass ratios (or np.full(n, 1.0)) */
@@ -382,9 +516,11 @@ static void v_planet_radius(const tb_args* A, const double* x, const double* hm,
 
 /* sample_inc: arccos(c_lo - x / norm) * 180 / pi */
 static void v_inc(const tb_args* A, const double* x, double* out, int64_t m) {
+    TIC;
     for (int64_t i = 0; i < m; i++) out[i] = A->c_lo - x[i] / A->inc_norm;
     v_unary(&A->f_arccos, out, out, m);
     for (int64_t i = 0; i < m; i++) out[i] = out[i] * 180.0 / 3.141592653589793;
+    TOC(S_INC);
 }
 
 static void v_argp(const double* x, double* out, int64_t m) {
@@ -393,33 +529,47 @@ static void v_argp(const double* x, double* out, int64_t m) {
 
 /* funcs.stellar_relations: caps per draw (maxR / maxT) or one value each */
 static void v_stellar(const tb_args* A, const double* mass, const double* maxR, double maxR_s,
-                      const double* maxT, double maxT_s, double* R, double* T, int64_t m) {
-    for (int64_t i = 0; i < m; i++) {
-        const double x = mass[i];
-        double r = 0.0, t = 0.0;
-        if (x > 0.63) {
-            r = splev1(&A->hot_R, x);
-            if (T) t = splev1(&A->hot_T, x);
-        } else if (x <= 0.63) {
-            r = splev1(&A->cool_R, x);
-            if (T) t = splev1(&A->cool_T, x);
+                      const double* maxT, double maxT_s, double* R, double* T, int64_t m,
+                      scratch* W) {
+    TIC;
+    /* Radii[hot] = spline(m[hot]) ...: the two mass branches, each as one batch */
+    for (int64_t i = 0; i < m; i++) { R[i] = 0.0; if (T) T[i] = 0.0; }
+    for (int branch = 0; branch < 2; branch++) {
+        int64_t c = 0;
+        for (int64_t i = 0; i < m; i++) {
+            const int in = branch == 0 ? mass[i] > 0.63 : mass[i] <= 0.63;
+            W->subset[c] = (int32_t)i;
+            c += in;
         }
-        const double cr = maxR ? maxR[i] : maxR_s, ct = maxT ? maxT[i] : maxT_s;
-        if (r > cr) r = cr;
-        if (t > ct) t = ct;
-        if (r < 0.1) r = 0.1;
-        if (t < 2800.0) t = 2800.0;
-        R[i] = r;
-        if (T) T[i] = t;
+        if (!c) continue;
+        splev_many(branch == 0 ? &A->hot_R : &A->cool_R, mass, W->subset, c, R, W);
+        if (T) splev_many(branch == 0 ? &A->hot_T : &A->cool_T, mass, W->subset, c, T, W);
     }
+    for (int64_t i = 0; i < m; i++) {
+        double r = R[i];
+        const double cr = maxR ? maxR[i] : maxR_s;
+        if (r > cr) r = cr;
+        if (r < 0.1) r = 0.1;
+        R[i] = r;
+        if (T) {
+            double t = T[i];
+            const double ct = maxT ? maxT[i] : maxT_s;
+            if (t > ct) t = ct;
+            if (t < 2800.0) t = 2800.0;
+            T[i] = t;
+        }
+    }
+    TOC(S_STELLAR);
 }
 
 /* marginal_likelihoods._fluxratio: f / (f + f0) with f = 10 ** spline(mass) */
 static void v_fluxratio(const tb_args* A, const tb_spline* s, double f0, const double* mass,
-                        double* out, int64_t m) {
-    for (int64_t i = 0; i < m; i++) out[i] = splev1(s, mass[i]);
+                        double* out, int64_t m, scratch* W) {
+    TIC;
+    splev_many(s, mass, NULL, m, out, W);
     v_power_sv(&A->f_pow, 10.0, out, out, m);
     for (int64_t i = 0; i < m; i++) out[i] = out[i] / (out[i] + f0);
+    TOC(S_FLUX);
 }
 
 static inline void v_odds(const double* fr, double* out, int64_t m) {      /* fr / (1 - fr) */
@@ -448,14 +598,19 @@ static void v_bound_prior(const tb_args* A, int64_t lo, const double* term, doub
     v_unary(&A->f_log10, term, delta, m);
     for (int64_t i = 0; i < m; i++) { delta[i] = 2.5 * delta[i]; b3[i] = fabs(delta[i]); }
     if (A->interp_j) memcpy(A->interp_delta + lo, delta, (size_t)m * sizeof(double));
-    v_interp(b3, B->xp, B->fp, B->nxp, lp, m,              /* separation_at_contrast */
-             A->interp_j ? A->interp_j + lo : NULL);
+    {
+        TIC;
+        v_interp(b3, B->xp, B->fp, B->nxp, lp, m,          /* separation_at_contrast */
+                 A->interp_j ? A->interp_j + lo : NULL);
+        TOC(S_INTERP);
+    }
     bound_from_separation(A, lp, delta, lnprior, m, ex);
 }
 
 /* the rest of the bound-companion prior, from the separations [arcsec] in lp (overwritten) */
 static void bound_from_separation(const tb_args* A, double* lp, const double* delta,
                                   double* lnprior, int64_t m, double* ex) {
+    TIC;
     const tb_bound* B = &A->bound;
     for (int64_t i = 0; i < m; i++) lp[i] = (B->d * lp[i]) * B->au;       /* seps * au */
     v_power_vs(&A->f_pow, lp, 3.0, lp, m);                                 /* ** 3 */
@@ -490,14 +645,17 @@ static void bound_from_separation(const tb_args* A, double* lp, const double* de
     }
     v_unary(&A->f_log, lnprior, lnprior, m);
     v_clip(lnprior, delta, m);
+    TOC(S_BOUND);
 }
 
 /* marginal_likelihoods._background_prior: dmag is dmag_tess (no contrast curve) or dmag_cc */
 static void background_from_separation(const tb_args* A, double* lnprior, const double* dmag,
                                        int64_t m) {
+    TIC;
     for (int64_t i = 0; i < m; i++) lnprior[i] = A->bgp.K * (lnprior[i] * lnprior[i]);
     v_unary(&A->f_log, lnprior, lnprior, m);
     v_clip(lnprior, dmag, m);
+    TOC(S_BG);
 }
 
 static void v_background_prior(const tb_args* A, int64_t lo, const double* dmag, double* lnprior,
@@ -510,7 +668,11 @@ static void v_background_prior(const tb_args* A, int64_t lo, const double* dmag,
     }
     for (int64_t i = 0; i < m; i++) b0[i] = fabs(dmag[i]);
     if (A->interp_j) memcpy(A->interp_delta + lo, dmag, (size_t)m * sizeof(double));
-    v_interp(b0, B->xp, B->fp, B->nxp, lnprior, m, A->interp_j ? A->interp_j + lo : NULL);
+    {
+        TIC;
+        v_interp(b0, B->xp, B->fp, B->nxp, lnprior, m, A->interp_j ? A->interp_j + lo : NULL);
+        TOC(S_INTERP);
+    }
     background_from_separation(A, lnprior, dmag, m);
 }
 
@@ -551,15 +713,15 @@ static int v_take(const double* tab, int64_t ntab, const int64_t* idx, double* o
 /* _companion_stars: properties of the drawn bound companions when they host the event */
 static int v_companion_stars(const tb_args* A, const double* qs_comp, double* masses_comp,
                              double* radii_comp, double* teffs_comp, double* frc, double* u1,
-                             double* u2, int64_t m, double* b0) {
+                             double* u2, int64_t m, double* b0, scratch* W) {
     for (int64_t i = 0; i < m; i++) masses_comp[i] = qs_comp[i] * A->M_s;
-    v_stellar(A, masses_comp, NULL, A->R_s, NULL, A->Teff, radii_comp, teffs_comp, m);
+    v_stellar(A, masses_comp, NULL, A->R_s, NULL, A->Teff, radii_comp, teffs_comp, m, W);
     for (int64_t i = 0; i < m; i++) {
         const double c = radii_comp[i] * A->Rsun;
         b0[i] = (A->G * (masses_comp[i] * A->Msun)) / (c * c);
     }
     v_unary(&A->f_log10, b0, b0, m);
-    v_fluxratio(A, &A->flux_tess, A->f0_tess, masses_comp, frc, m);
+    v_fluxratio(A, &A->flux_tess, A->f0_tess, masses_comp, frc, m, W);
     return v_ldc(A, teffs_comp, b0, u1, u2, m);
 }
 
@@ -579,7 +741,9 @@ static int run_chunk(const tb_args* A, int64_t lo, int64_t m, scratch* W) {
                        || A->kind == K_DEB || A->kind == K_BEB;
     if (binary) {
         /* np.power(x_e, 1 / a, out = x_e): scipy.stats.powerlaw.rvs from its deviates */
+        TIC;
         v_power_vs(&A->f_pow, A->x_e + lo, A->ecc_exp, A->x_e + lo, m);
+        TOC(S_ECC);
     }
     double* qs_comp = b[0];
     if (c_comp) {
@@ -602,15 +766,15 @@ static int run_chunk(const tb_args* A, int64_t lo, int64_t m, scratch* W) {
         v_mass_ratio(A, &A->q, x_q, qs, m, W);
         v_argp(x_w, argps, m);
         for (int64_t i = 0; i < m; i++) masses[i] = qs[i] * A->M_s;
-        v_stellar(A, masses, NULL, A->R_s, NULL, A->Teff, radii, NULL, m);
-        v_fluxratio(A, &A->flux_tess, A->f0_tess, masses, fr, m);
+        v_stellar(A, masses, NULL, A->R_s, NULL, A->Teff, radii, NULL, m, W);
+        v_fluxratio(A, &A->flux_tess, A->f0_tess, masses, fr, m, W);
         for (int64_t i = 0; i < m; i++) mtot[i] = A->M_s + masses[i];
         if (A->kind == K_PEB) {
             double *frc = OUT(7), *lnprior = OUT(8);
             for (int64_t i = 0; i < m; i++) b[1][i] = qs_comp[i] * A->M_s;        /* masses_comp */
-            v_fluxratio(A, &A->flux_tess, A->f0_tess, b[1], frc, m);
+            v_fluxratio(A, &A->flux_tess, A->f0_tess, b[1], frc, m, W);
             if (A->has_cc) {
-                v_fluxratio(A, &A->flux_cc, A->f0_cc, b[1], b[2], m);
+                v_fluxratio(A, &A->flux_cc, A->f0_cc, b[1], b[2], m, W);
                 v_odds(b[2], b[2], m);
             } else {
                 v_odds(frc, b[2], m);
@@ -639,9 +803,9 @@ static int run_chunk(const tb_args* A, int64_t lo, int64_t m, scratch* W) {
         if (A->kind == K_PTP) {
             double *frc = OUT(3), *lnprior = OUT(4);
             for (int64_t i = 0; i < m; i++) b[1][i] = qs_comp[i] * A->M_s;
-            v_fluxratio(A, &A->flux_tess, A->f0_tess, b[1], frc, m);
+            v_fluxratio(A, &A->flux_tess, A->f0_tess, b[1], frc, m, W);
             if (A->has_cc) {
-                v_fluxratio(A, &A->flux_cc, A->f0_cc, b[1], b[2], m);
+                v_fluxratio(A, &A->flux_cc, A->f0_cc, b[1], b[2], m, W);
                 v_odds(b[2], b[2], m);
             } else {
                 v_odds(frc, b[2], m);
@@ -669,10 +833,10 @@ static int run_chunk(const tb_args* A, int64_t lo, int64_t m, scratch* W) {
         v_inc(A, x_inc, incs, m);
         v_argp(x_w, argps, m);
         if ((rc = v_companion_stars(A, qs_comp, masses_comp, radii_comp, b[2], frc, u1, u2, m,
-                                    b[3])))
+                                    b[3], W)))
             return rc;
         if (A->has_cc) {
-            v_fluxratio(A, &A->flux_cc, A->f0_cc, masses_comp, b[4], m);
+            v_fluxratio(A, &A->flux_cc, A->f0_cc, masses_comp, b[4], m, W);
             v_odds(b[4], b[4], m);
         } else {
             v_odds(frc, b[4], m);
@@ -689,14 +853,14 @@ static int run_chunk(const tb_args* A, int64_t lo, int64_t m, scratch* W) {
         v_argp(x_w, argps, m);
         double* teffs_comp = b[2];
         if ((rc = v_companion_stars(A, qs_comp, masses_comp, radii_comp, teffs_comp, frc, u1, u2,
-                                    m, b[3])))
+                                    m, b[3], W)))
             return rc;
         for (int64_t i = 0; i < m; i++) masses[i] = qs[i] * masses_comp[i];
-        v_stellar(A, masses, radii_comp, 0.0, teffs_comp, 0.0, radii, NULL, m);
-        v_fluxratio(A, &A->flux_tess, A->f0_tess, masses, fr, m);
+        v_stellar(A, masses, radii_comp, 0.0, teffs_comp, 0.0, radii, NULL, m, W);
+        v_fluxratio(A, &A->flux_tess, A->f0_tess, masses, fr, m, W);
         if (A->has_cc) {
-            v_fluxratio(A, &A->flux_cc, A->f0_cc, masses, b[4], m);
-            v_fluxratio(A, &A->flux_cc, A->f0_cc, masses_comp, b[5], m);
+            v_fluxratio(A, &A->flux_cc, A->f0_cc, masses, b[4], m, W);
+            v_fluxratio(A, &A->flux_cc, A->f0_cc, masses_comp, b[5], m, W);
             v_odds(b[4], b[4], m);
             v_odds(b[5], b[5], m);
         } else {
@@ -743,19 +907,19 @@ static int run_chunk(const tb_args* A, int64_t lo, int64_t m, scratch* W) {
         v_take(A->bg_fr, A->ntab, idxs, cfr, m);
         for (int64_t i = 0; i < m; i++) masses[i] = qs[i] * hm[i];
         v_take(A->bg_teff, A->ntab, idxs, b[1], m);
-        v_stellar(A, masses, hr, 0.0, b[1], 0.0, radii, NULL, m);
+        v_stellar(A, masses, hr, 0.0, b[1], 0.0, radii, NULL, m, W);
         /* distance_corrected("TESS"): _fluxratio(masses) * (cfr_band / _fluxratio(host_masses)) */
         v_take(A->bg_fr_tess, A->ntab, idxs, b[2], m);
-        v_fluxratio(A, &A->flux_tess, A->f0_tess, hm, b[3], m);
-        v_fluxratio(A, &A->flux_tess, A->f0_tess, masses, fr, m);
+        v_fluxratio(A, &A->flux_tess, A->f0_tess, hm, b[3], m, W);
+        v_fluxratio(A, &A->flux_tess, A->f0_tess, masses, fr, m, W);
         for (int64_t i = 0; i < m; i++) fr[i] = fr[i] * (b[2][i] / b[3][i]);
         if (!A->has_cc) {
             v_odds(cfr, b[4], m);
             v_odds(fr, b[5], m);
         } else {
             v_take(A->bg_fr_cc, A->ntab, idxs, b[2], m);                      /* cfr_cc */
-            v_fluxratio(A, &A->flux_cc, A->f0_cc, hm, b[3], m);
-            v_fluxratio(A, &A->flux_cc, A->f0_cc, masses, b[6], m);
+            v_fluxratio(A, &A->flux_cc, A->f0_cc, hm, b[3], m, W);
+            v_fluxratio(A, &A->flux_cc, A->f0_cc, masses, b[6], m, W);
             for (int64_t i = 0; i < m; i++) b[6][i] = b[6][i] * (b[2][i] / b[3][i]);   /* fr_cc */
             v_odds(b[2], b[4], m);
             v_odds(b[6], b[5], m);
@@ -828,7 +992,10 @@ int trih_scenario_block(const tb_args* A) {
         double* arena = (double*)malloc((size_t)NBUF * CH * sizeof(double));
         W.ix = (int32_t*)malloc((size_t)CH * sizeof(int32_t));
         W.sel = (uint8_t*)malloc((size_t)CH);
-        int ok = arena && W.ix && W.sel;
+        W.perm = (int32_t*)malloc((size_t)CH * sizeof(int32_t));
+        W.subset = (int32_t*)malloc((size_t)(CH + 1) * sizeof(int32_t));
+        W.l8 = (uint8_t*)malloc((size_t)CH);
+        int ok = arena && W.ix && W.sel && W.perm && W.subset && W.l8;
         for (int i = 0; i < NBUF; i++) W.b[i] = ok ? arena + (size_t)i * CH : NULL;
 #pragma omp for schedule(dynamic, 1)
         for (int64_t c = 0; c < nchunks; c++) {
@@ -847,6 +1014,9 @@ int trih_scenario_block(const tb_args* A) {
         free(arena);
         free(W.ix);
         free(W.sel);
+        free(W.perm);
+        free(W.subset);
+        free(W.l8);
     }
     if (!err && A->interp_j) stitch_interp(A);
     return err;
