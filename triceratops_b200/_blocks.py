@@ -20,6 +20,7 @@ import threading
 import numpy as np
 
 from . import _build
+from ._bufpool import empty as _pinned_empty
 
 KINDS = ("TTP", "TEB", "PTP", "PEB", "STP", "SEB", "DTP", "DEB", "BTP", "BEB")
 #: number of float64 output columns per kind, and whether a boolean `extra` mask comes with them
@@ -326,7 +327,8 @@ def run(kind, N, *, M_s, R_s, Teff, x_inc, x_w, x_rp=None, x_q=None, x_e=None, c
         keep += [delta, jrec]
         A.interp_delta, A.interp_j = _dp(delta), jrec.ctypes.data_as(
             ctypes.POINTER(ctypes.c_int32))
-    outs = [np.empty(N) for _ in range(N_OUT[kind])]
+    # (page-locked when possible: the engine then uploads them without a staging copy)
+    outs = [_pinned_empty(N) for _ in range(N_OUT[kind])]
     for i, o in enumerate(outs):
         A.out[i] = _dp(o)
     extra = None

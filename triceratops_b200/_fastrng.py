@@ -122,11 +122,19 @@ def _self_check():
         np.random.set_state(saved)
 
 
-def rand(n):
+def _out(n, pinned):
+    if pinned:
+        from ._bufpool import empty
+        return empty(n)
+    return np.empty(n)
+
+
+def rand(n, pinned=False):
+    """np.random.rand(n); pinned: on a page-locked buffer (a column that goes to the GPU)."""
     n = int(n)
     if n < MIN_N or _load() is None:
         return np.random.rand(n)
-    out = _rand(n, np.empty(n))
+    out = _rand(n, _out(n, pinned))
     return out if out is not None else np.random.rand(n)
 
 
@@ -176,7 +184,7 @@ def powerlaw_rvs(a, n):
     return np.power(x, 1.0 / a, out=x)        # (* scale + loc with 1, 0: the same bits)
 
 
-def beta_rvs(a, b, n, _force=False):
+def beta_rvs(a, b, n, _force=False, pinned=False):
     """scipy.stats.beta.rvs(a, b, size=n) on numpy's global generator (legacy_beta: two gamma
     deviates by rejection).  The C walker covers a < 1 < b; anything else goes to scipy."""
     n = int(n)
@@ -190,7 +198,7 @@ def beta_rvs(a, b, n, _force=False):
     from ._hostpar import N_THREADS
     key, pos = np.array(st[1], dtype=np.uint32), ctypes.c_int32(int(st[2]))
     has_gauss, gauss = ctypes.c_int32(int(st[3])), ctypes.c_double(float(st[4]))
-    out = np.empty(n)
+    out = _out(n, pinned)
     rc = _lib.trih_legacy_beta(key.ctypes.data_as(_U32), ctypes.byref(pos),
                                ctypes.byref(has_gauss), ctypes.byref(gauss), float(a), float(b),
                                out.ctypes.data_as(_D), n, int(N_THREADS))

@@ -189,7 +189,11 @@ class Engine:
     def _mask(self, m, N):
         if m is None:
             return None
-        a = np.ascontiguousarray(np.asarray(m).astype(np.uint8))
+        a = np.asarray(m)
+        if a.dtype == np.bool_ and a.flags.c_contiguous:
+            a = a.view(np.uint8)                       # (same bytes, no copy)
+        else:
+            a = np.ascontiguousarray(a.astype(np.uint8))
         if a.shape != (N,):
             raise ValueError("extra_mask has shape %s, expected (%d,)" % (a.shape, N))
         self._keep.append(a)

@@ -89,10 +89,10 @@ def _draw_ecc(N, planet, P_mean):
     global generator -- Beta(0.867, 3.03) for planets, a power law for binaries."""
     _fastrng.skip(N)
     if planet:
-        return _fastrng.beta_rvs(0.867, 3.030, N)
+        return _fastrng.beta_rvs(0.867, 3.030, N, pinned=True)
     # scipy.stats.powerlaw.rvs(a, size=N) is pow(uniform deviates, 1/a): only the deviates are
     # taken here, while the generator is held; _ecc_binary() maps them later, chunk by chunk
-    return _fastrng.rand(N)
+    return _fastrng.rand(N, pinned=True)
 
 
 def _prepare(kind, block, N, arrays, **ckw):
