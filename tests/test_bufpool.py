@@ -20,6 +20,7 @@ def test_lease_follows_the_last_view(monkeypatch):
     # (a stand-in for the pinned allocator: the lease logic does not depend on where the bytes live)
     monkeypatch.setattr(_bufpool, "_pinned_owner", lambda nbytes: np.empty(nbytes, dtype=np.uint8))
     monkeypatch.setattr(_bufpool, "_free", {})
+    monkeypatch.setattr(_bufpool, "_calls", [2])
     n = 300_000
     a = _bufpool.empty(n)
     assert a.shape == (n,) and a.dtype == np.float64 and a.flags.c_contiguous and a.flags.writeable
@@ -41,6 +42,9 @@ def test_lease_follows_the_last_view(monkeypatch):
 @pytest.mark.gpu
 def test_pooled_columns_are_page_locked_and_skip_the_staging_copy(gpu_engine):
     import torch
+    assert _bufpool.empty(500_000).flags.owndata or _bufpool._calls[0] >= 2    # off before a 2nd call
+    _bufpool.note_call()
+    _bufpool.note_call()
     a = _bufpool.empty(500_000)
     assert not a.flags.owndata
     t = torch.from_numpy(a)

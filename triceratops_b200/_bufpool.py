@@ -9,7 +9,9 @@ process neither allocates nor stages.
 The array returned is a view (`owndata` False) of a holder object that keeps the buffer leased
 for as long as the array or any view derived from it is alive.  TRI_B200_PINNED_POOL_MB caps the
 pinned memory the pool may own (default 3072; 0 disables it); beyond the cap, and wherever CUDA
-is not available, `empty()` is `numpy.empty`.
+is not available, `empty()` is `numpy.empty`.  Page-locking ~1.3 GB costs ~0.5 s once, so the
+pool only switches on with a process's SECOND `calc_probs` (`note_call()`): a script that vets
+one target is not slowed down, a sweep gains from its third call on.
 """
 import collections
 import ctypes
@@ -28,6 +30,12 @@ _holders = {}            # nbytes -> ctypes holder type
 _owned = [0]             # pinned bytes allocated by the pool (leased or free)
 _usable = [None]         # None: not tried; False: no pinned memory here
 stats = {"new": 0, "reused": 0, "plain": 0}
+_calls = [0]
+
+
+def note_call():
+    """calc_probs tells the pool that another public call starts (see the module docstring)."""
+    _calls[0] += 1
 
 
 def _holder_type(nbytes):
@@ -69,7 +77,7 @@ def empty(n, dtype=np.float64):
     """Uninitialised 1-D array of n elements, like np.empty(n, dtype), page-locked if possible."""
     dtype = np.dtype(dtype)
     want = int(n) * dtype.itemsize
-    if want < MIN_BYTES or _CAP == 0:
+    if want < MIN_BYTES or _CAP == 0 or _calls[0] < 2:
         return np.empty(int(n), dtype=dtype)
     nbytes = -(-want // _GRAIN) * _GRAIN
     owner = None

@@ -21,7 +21,7 @@ import numpy as np
 from pandas import DataFrame
 from scipy.special import ndtr
 
-from . import _dispatch
+from . import _bufpool, _dispatch
 from ._numerics import _normalize_probabilities
 from .funcs import renorm_flux
 from .marginal_likelihoods import (lnZ_BEB, lnZ_BTP, lnZ_DEB, lnZ_DTP, lnZ_PEB, lnZ_PTP, lnZ_SEB,
@@ -221,6 +221,7 @@ class target:
         # from costing 5 ms each
         switch_interval = sys.getswitchinterval()
         sys.setswitchinterval(_dispatch.gil_switch_interval())
+        _bufpool.note_call()       # (page-locked column buffers from a process's second call on)
         try:
             with _dispatch.deferring():
                 for i, ID in enumerate(filtered["ID"].values if not follower else ()):
