@@ -585,12 +585,19 @@ def prepare(res):
 
 def scenario_threads():
     """Threads calc_probs uses for the host-side preparation of consecutive scenarios
-    (TRI_B200_SCENARIO_THREADS, default 4; 1 = everything in the calling thread)."""
+    (TRI_B200_SCENARIO_THREADS; 1 = everything in the calling thread, the default).
+
+    While a scenario's preparation took 0.1-0.3 s of single-threaded numpy, running it beside the
+    next scenario's draws paid (4 threads, rounds 1-2).  Now that both the generator helpers and
+    the preparation blocks are short multi-threaded C calls, overlapping them only makes them
+    compete for memory bandwidth and cores: on the 16-core GPU box the public call takes 0.209 s
+    with 1 thread, 0.247 s with 2, 0.280 s with 4 (the GPU work overlaps either way: submissions
+    are asynchronous)."""
     import os
     try:
-        return max(1, int(os.environ.get("TRI_B200_SCENARIO_THREADS", "4")))
+        return max(1, int(os.environ.get("TRI_B200_SCENARIO_THREADS", "1")))
     except ValueError:
-        return 4
+        return 1
 
 
 def gil_switch_interval():

@@ -60,7 +60,7 @@ def _worker(worker_id, n_gpus, jobs, out_q, n_workers=None):
     share = max(1, cores // max(1, n_workers or cores))
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("TRI_B200_HOST_THREADS", str(share))
-    os.environ.setdefault("TRI_B200_SCENARIO_THREADS", "2" if share >= 4 else "1")
+    os.environ.setdefault("TRI_B200_SCENARIO_THREADS", "1")
     try:
         for idx, job in jobs:
             out_q.put((idx, run_job(job), None))
