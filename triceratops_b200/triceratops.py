@@ -165,7 +165,7 @@ class target:
         held = []                          # (rows, results) waiting for the group's exchange
         from . import marginal_likelihoods as _ml
         host_sampler = _ml._sampler_mode() == "host"
-        threads = _dispatch.scenario_threads() if host_sampler else 1
+        threads = _dispatch.scenario_threads(_dispatch._dist() is not None) if host_sampler else 1
         eng = _dispatch.get_engine()   # created here, not by whichever scenario thread comes first
         chain = _dispatch.ScenarioChain(threads)
         # Under a process group (one process per GPU) the evidence records and best-draw
