@@ -48,9 +48,12 @@ def _holder_type(nbytes):
             _owner = None
 
             def __del__(self):
-                owner, self._owner = self._owner, None
-                if owner is not None:
-                    _free.setdefault(owner.nbytes, collections.deque()).append(owner)
+                try:
+                    owner, self._owner = self._owner, None
+                    if owner is not None:
+                        _free.setdefault(owner.nbytes, collections.deque()).append(owner)
+                except Exception:      # interpreter shutdown: the module's globals are gone
+                    pass
 
         T = _holders.setdefault(nbytes, Holder)
     return T
