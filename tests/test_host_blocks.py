@@ -175,3 +175,56 @@ def test_small_calls_and_disabled_path_use_numpy(monkeypatch):
     monkeypatch.setattr(_blocks, "_state", False)
     assert _blocks.run("TTP", N, M_s=1.0, R_s=1.0, Teff=5000.0, x_inc=np.zeros(N),
                        x_w=np.zeros(N), x_rp=np.zeros(N)) is None
+
+
+def test_random_stars_small_draw_counts(monkeypatch):
+    """Many random targets (including the regime edges M = 0.1, 0.3, 0.45, 0.63, 1.0 Msun and
+    periods on both sides of the P = 10 d eccentricity switch) at a draw count that leaves
+    ragged chunks: every scenario, bit for bit."""
+    monkeypatch.setattr(_blocks, "MIN_N", 1000)
+    calls = _record(monkeypatch)
+    rng = np.random.default_rng(2026)
+    n = 9_001
+    masses = [0.1, 0.3, 0.45, 0.63, 1.0, 0.2999999, 1.0000001] + list(rng.uniform(0.08, 2.5, 25))
+    mags = (10.3, 9.6, 9.2, 9.1)
+    for k, M in enumerate(masses):
+        R = float(M ** 0.9 * rng.uniform(0.8, 1.2))
+        Te = float(np.clip(5777 * M ** 0.55, 2900, 9500))
+        Z = float(rng.uniform(-0.5, 0.4))
+        P = float(rng.choice([0.7, 3.3, 9.999, 10.0, 10.001, 25.0]))
+        plx = float(rng.choice([0.5, 8.1, 120.0]))
+        cc, filt = [(None, "TESS"), (CC, "TESS"), (CC, "J"), (CC, "H"), (CC, "K"), (CC, "Vis")][k % 6]
+        flat = bool(k % 3 == 0)
+        kw = dict(N=n, parallel=True)
+        tag = "M=%.4f P=%.3f %s" % (M, P, filt)
+        _both_ways(monkeypatch, calls,
+                   lambda: ml.lnZ_TTP(*LC, P, M, R, Te, Z, flatpriors=flat, **kw), "TTP " + tag)
+        _both_ways(monkeypatch, calls, lambda: ml.lnZ_TEB(*LC, P, M, R, Te, Z, **kw), "TEB " + tag)
+        for name in ("PTP", "PEB", "STP", "SEB"):
+            fn = getattr(ml, "lnZ_" + name)
+            _both_ways(monkeypatch, calls,
+                       lambda: fn(*LC, P, M, R, Te, Z, plx, cc, filt, flatpriors=flat, **kw),
+                       name + " " + tag)
+        for name in ("DTP", "DEB"):
+            fn = getattr(ml, "lnZ_" + name)
+            _both_ways(monkeypatch, calls,
+                       lambda: fn(*LC, P, M, R, Te, Z, *mags, TRI, cc, filt, flatpriors=flat, **kw),
+                       name + " " + tag)
+        for name in ("BTP", "BEB"):
+            fn = getattr(ml, "lnZ_" + name)
+            _both_ways(monkeypatch, calls,
+                       lambda: fn(*LC, P, M, R, Te, *mags, TRI, cc, filt, flatpriors=flat, **kw),
+                       name + " " + tag)
+
+
+def test_period_range_inputs(monkeypatch):
+    """P_orb given as a range: the periods are drawn too and the eccentricity law follows their
+    mean (reference marginal_likelihoods.py:67-76)."""
+    calls = _record(monkeypatch)
+    M, R, Te, Z, _ = STARS[0]
+    for P in (np.array([3.0, 12.0]), np.array([11.0, 30.0])):
+        _both_ways(monkeypatch, calls, lambda: ml.lnZ_TEB(*LC, P, M, R, Te, Z, N=N, parallel=True),
+                   "TEB range")
+        _both_ways(monkeypatch, calls,
+                   lambda: ml.lnZ_SEB(*LC, P, M, R, Te, Z, 8.1, CC, "J", N=N, parallel=True),
+                   "SEB range")
